@@ -1,0 +1,89 @@
+"""TEST INFRASTRUCTURE — numpy fp64 restatement of the reference's post-hoc exit policy.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU legs may import this.
+Pinned by `tests/test_oracle.py` against the reference's own `Policy` class (imported from
+/root/reference when present) and against `tests/golden/policy_*.npz`.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def softmax64(x: np.ndarray, axis: int = -1) -> np.ndarray:
+    """scipy.special.softmax semantics (max-shifted), fp64 — used at EE/policy.py:30-32."""
+    x = np.asarray(x, dtype=np.float64)
+    e = np.exp(x - x.max(axis=axis, keepdims=True))
+    return e / e.sum(axis=axis, keepdims=True)
+
+
+def entropy64(x: np.ndarray) -> np.ndarray:
+    """EE/models/EE_modules.py:149-154 evaluated in fp64: log sum e^x - sum x e^x / sum e^x."""
+    x = np.asarray(x, dtype=np.float64)
+    ex = np.exp(x)
+    a = ex.sum(axis=-1)
+    b = (x * ex).sum(axis=-1)
+    return np.log(a) - b / a
+
+
+def temperature_scale(logits: np.ndarray, temperatures: Optional[Sequence[float]]) -> np.ndarray:
+    """EE/generic_scaling.py:54-61 applied per exit as EE/eval.py:312-327 does: logits[e] / T_e."""
+    logits = np.asarray(logits, dtype=np.float64)
+    if temperatures is None:
+        return logits
+    t = np.asarray(temperatures, dtype=np.float64).reshape(-1, 1, 1)
+    assert t.shape[0] == logits.shape[0]
+    return logits / t
+
+
+def criterion(logits: np.ndarray, kind: str) -> np.ndarray:
+    """[E+1,N,K] -> [E+1,N]; "max_confidence" EE/policy.py:30-32, "entropy" EE_modules.py:149."""
+    if kind == "max_confidence":
+        return softmax64(logits).max(axis=-1)
+    if kind == "entropy":
+        return entropy64(logits)
+    raise NotImplementedError(kind)
+
+
+def exit_policy(logits: np.ndarray, thresholds, kind: str = "max_confidence"
+                ) -> Tuple[np.ndarray, np.ndarray, Dict[int, float]]:
+    """First exit whose criterion passes its threshold, else the last one (unconditional).
+
+    Restates the double loop of EE/policy.py:28-45 (strict `>` for max-confidence, :33) and,
+    for entropy, the sign of EE/models/EE_modules.py:142-143 (strict `<`).  `thresholds` is a
+    scalar (global policy, :17) or a per-exit vector (accuracy_calibration_heuristic, :94).
+    Returns (exits_store int32[N], predictions f64[N,K], exit_distribution)."""
+    logits = np.asarray(logits, dtype=np.float64)
+    E1, N, K = logits.shape
+    thr = np.broadcast_to(np.asarray(thresholds, dtype=np.float64), (E1,)) if np.ndim(thresholds) == 0 \
+        else np.asarray(thresholds, dtype=np.float64)
+    exits_store = np.zeros(N, dtype=np.int32)
+    predictions = np.zeros((N, K), dtype=np.float64)
+    for s in range(N):
+        for e in range(E1):
+            if kind == "max_confidence":
+                score = np.max(softmax64(logits[e][s]))
+                fire = score > thr[e]
+            else:
+                score = entropy64(logits[e][s])
+                fire = score < thr[e]
+            if fire or e == E1 - 1:
+                exits_store[s] = e
+                predictions[s] = logits[e][s]
+                break
+    dist = {e: np.count_nonzero(exits_store == e) / N for e in range(E1)}
+    return exits_store, predictions, dist
+
+
+def exit_policy_vectorised(logits, thresholds, kind="max_confidence"):
+    """Vectorised equivalent (the property the reference checks at EE/thresh.py:308-318)."""
+    logits = np.asarray(logits, dtype=np.float64)
+    E1, N, K = logits.shape
+    thr = np.broadcast_to(np.asarray(thresholds, dtype=np.float64).reshape(-1), (E1,)) \
+        if np.size(thresholds) == 1 else np.asarray(thresholds, dtype=np.float64)
+    crit = criterion(logits, kind)
+    fire = crit > thr[:, None] if kind == "max_confidence" else crit < thr[:, None]
+    fire[-1, :] = True
+    idx = fire.argmax(axis=0).astype(np.int32)
+    return idx, logits[idx, np.arange(N)], crit

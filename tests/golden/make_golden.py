@@ -1,0 +1,101 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference model (dev container only).
+
+    python tests/golden/make_golden.py
+
+Weights and inputs come from `mmee.synth` (seeded); the reference model is built by
+`oracle/reference_harness.py` and loaded strictly with that state dict.  Each fixture stores
+the seeds + config needed to regenerate the inputs, and the reference's outputs:
+per-exit logits [E+1,B,K], raw head logits, the reference's own exit criteria, sampled slices
+of the last hidden state, and the reference `Policy` results for a few thresholds.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "multi-modal-early-exit_b200"))
+
+from mmee.config import ExitConfig, ModelDims  # noqa: E402
+from mmee import synth  # noqa: E402
+from mmee.calibration import spread_temperatures  # noqa: E402
+from oracle import reference_harness as RH  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+CASES = {
+    # name: (dims ctor, dims kwargs, ee dict, n_docs, weight seed, doc seed, pad)
+    "tiny_ramp_conf": ("tiny", {}, dict(exits=["text_visual_concat", 1, 2, 3], encoder_layer_strategy="ramp",
+                                        inference_strategy="max_confidence"), 6, 0, 1, True),
+    "tiny_gate_ent": ("tiny", {}, dict(exits=["text_visual_concat", 1, 2, 3], encoder_layer_strategy="gate",
+                                       inference_strategy="entropy"), 6, 0, 2, True),
+    "tiny_ramp_1layer_head": ("tiny", {}, dict(exits=["text_visual_concat", 2], encoder_layer_strategy="ramp",
+                                               inference_strategy="max_confidence", exit_head_num_layers=1), 3, 3, 4, True),
+    "base_ramp_conf": ("base", {}, dict(exits=["text_visual_concat"] + list(range(1, 13)),
+                                        encoder_layer_strategy="ramp", inference_strategy="max_confidence"), 4, 0, 1, True),
+    "base_gate_ent": ("base", {}, dict(exits=["text_visual_concat"] + list(range(1, 13)),
+                                       encoder_layer_strategy="gate", inference_strategy="entropy"), 4, 0, 5, True),
+    "large4_ramp_conf": ("large", {"layers": 4}, dict(exits=["text_visual_concat", 2, 4],
+                                                     encoder_layer_strategy="ramp", inference_strategy="max_confidence"), 2, 0, 6, True),
+}
+
+
+def run_case(name):
+    ctor, kw, eed, n, wseed, dseed, pad = CASES[name]
+    dims = getattr(ModelDims, ctor)(**kw)
+    ee = ExitConfig.from_dict(eed)
+    sd = synth.make_state_dict(dims, ee, seed=wseed)
+    docs = synth.make_docs(dims, n, seed=dseed, pad=pad)
+    t0 = time.time()
+    model = RH.build_reference_model(dims, ee, sd)
+    ref = RH.reference_forward(model, docs)
+    dt = time.time() - t0
+    # reference Policy on the stored logits (EE/eval.py:91-98 call shape), raw and temperature-scaled
+    sys.path.insert(0, os.path.join(RH.REFERENCE_ROOT, "EE"))
+    from policy import Policy  # the reference's class, verbatim
+
+    logits64 = ref["exit_logits"].numpy().astype(np.float64)
+    E1 = logits64.shape[0]
+    temps = spread_temperatures(logits64, "max_confidence")
+    scaled = logits64 / temps[:, None, None]
+    pol = {}
+    import models.EE_modules as EM  # reference criteria fns (EE/models/EE_modules.py:149-160), fp32 torch
+    pol["ref_entropy_cal"] = torch.stack([EM.entropy(torch.from_numpy(scaled[e]).float()) for e in range(E1)]).numpy()
+    pol["ref_maxconf_cal"] = torch.stack([EM.max_confidence(torch.from_numpy(scaled[e]).float()) for e in range(E1)]).numpy()
+    for tag, lg in (("raw", logits64), ("cal", scaled)):
+        for thr in (0.1, 0.5, 0.7, 0.9):
+            ex, pred, _ = Policy(logits=lg, config={"exit_threshold": thr, "device": "cpu"}
+                                 ).max_confidence_global_thresholding_policy()
+            pol[f"policy_{tag}_{thr}_exits"] = ex
+            pol[f"policy_{tag}_{thr}_pred"] = pred.numpy()
+    lh = ref["last_hidden"].numpy()
+    np.savez_compressed(
+        os.path.join(OUT, f"{name}.npz"),
+        meta=json.dumps(dict(ctor=ctor, dims_kw=kw, ee=eed, n=n, wseed=wseed, dseed=dseed, pad=pad,
+                             torch=torch.__version__, ref_seconds=round(dt, 2))),
+        exit_logits=ref["exit_logits"].numpy(),
+        head_logits=ref["head_logits"].numpy(),
+        criteria=ref["criteria"].numpy(),
+        last_hidden_cls=lh[:, 0, :],
+        last_hidden_sample=lh[:, ::37, ::5],
+        temps=temps,
+        input_ids_sum=docs["input_ids"].sum(1).numpy(),
+        bbox_sum=docs["bbox"].sum((1, 2)).numpy(),
+        pixel_sum=docs["pixel_values"].double().sum((1, 2, 3)).numpy(),
+        **pol,
+    )
+    print(f"{name}: reference forward {dt:.1f}s  exit_logits {tuple(ref['exit_logits'].shape)}")
+
+
+if __name__ == "__main__":
+    assert RH.available(), "reference not present"
+    torch.set_num_threads(os.cpu_count())
+    names = sys.argv[1:] or list(CASES)
+    for nm in names:
+        run_case(nm)

@@ -1,0 +1,84 @@
+"""CPU tests: the oracle port and policy port against the golden vectors (outputs of the
+unmodified reference, tests/golden/make_golden.py) and, when /root/reference is present,
+against the reference's own classes live."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import ALL_CASES, load_case
+from oracle import policy_port, port, reference_harness
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_port_matches_reference_golden(name):
+    g, dims, ee, sd, docs = load_case(name)
+    out = port.forward(sd, dims, ee, docs)
+    # same torch build => bit-exact in practice; 2e-6 leaves room for a different BLAS thread split
+    assert np.abs(out["exit_logits"].numpy() - g["exit_logits"]).max() <= 2e-6
+    assert np.abs(out["head_logits"].numpy() - g["head_logits"]).max() <= 2e-6
+    assert np.abs(out["last_hidden"][:, 0].numpy() - g["last_hidden_cls"]).max() <= 2e-5
+    assert np.abs(out["last_hidden"].numpy()[:, ::37, ::5] - g["last_hidden_sample"]).max() <= 2e-5
+    assert (out["exit_logits"].argmax(-1).numpy() == g["exit_logits"].argmax(-1)).all()
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_policy_port_matches_reference_policy_golden(name):
+    g, *_ = load_case(name)
+    lg = g["exit_logits"].astype(np.float64)
+    for tag, l in (("raw", lg), ("cal", policy_port.temperature_scale(lg, g["temps"]))):
+        for thr in (0.1, 0.5, 0.7, 0.9):
+            ex, pred, dist = policy_port.exit_policy(l, thr, "max_confidence")
+            assert np.array_equal(ex, g[f"policy_{tag}_{thr}_exits"])
+            assert np.array_equal(pred, g[f"policy_{tag}_{thr}_pred"])
+            ex2, pred2, _ = policy_port.exit_policy_vectorised(l, thr, "max_confidence")
+            assert np.array_equal(ex2, ex) and np.array_equal(pred2, pred)   # thresh.py:308-318 property
+            assert abs(sum(dist.values()) - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["tiny_gate_ent", "base_gate_ent"])
+def test_criteria_match_reference_functions(name):
+    g, *_ = load_case(name)
+    cal = policy_port.temperature_scale(g["exit_logits"].astype(np.float64), g["temps"])
+    assert np.abs(policy_port.criterion(cal, "entropy") - g["ref_entropy_cal"]).max() < 2e-5
+    assert np.abs(policy_port.criterion(cal, "max_confidence") - g["ref_maxconf_cal"]).max() < 2e-6
+    cal32 = torch.from_numpy(cal).float()
+    for e in range(cal.shape[0]):
+        assert torch.allclose(port.entropy(cal32[e]), torch.from_numpy(g["ref_entropy_cal"][e]), atol=1e-6)
+        assert torch.allclose(port.max_confidence(cal32[e]), torch.from_numpy(g["ref_maxconf_cal"][e]), atol=1e-7)
+
+
+def test_policy_edge_cases():
+    rng = np.random.default_rng(0)
+    lg = rng.normal(size=(5, 64, 16)) * 3
+    # threshold 1.0 can never be exceeded (strict >): everything leaves at the last exit
+    ex, pred, dist = policy_port.exit_policy(lg, 1.0)
+    assert (ex == 4).all() and dist[4] == 1.0 and np.array_equal(pred, lg[4])
+    # threshold 0 always fires at exit 0
+    ex, pred, _ = policy_port.exit_policy(lg, 0.0)
+    assert (ex == 0).all() and np.array_equal(pred, lg[0])
+    # per-exit thresholds, entropy criterion; loop == vectorised
+    thr = np.array([0.5, 1.0, 1.5, 2.0, 0.0])
+    a = policy_port.exit_policy(lg, thr, "entropy")
+    b = policy_port.exit_policy_vectorised(lg, thr, "entropy")
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # single exit (E+1 == 1)
+    ex, pred, _ = policy_port.exit_policy(lg[:1], 0.99)
+    assert (ex == 0).all()
+
+
+@pytest.mark.skipif(not reference_harness.available(), reason="reference tree not present (GPU box)")
+def test_port_matches_live_reference_tiny():
+    from mmee import synth
+    from mmee.config import ExitConfig, ModelDims
+
+    dims = ModelDims.tiny(layers=2)
+    ee = ExitConfig.from_dict(dict(exits=["text_visual_concat", 1, 2], encoder_layer_strategy="gate",
+                                   inference_strategy="entropy"))
+    sd = synth.make_state_dict(dims, ee, seed=11)
+    docs = synth.make_docs(dims, 3, seed=12)
+    model = reference_harness.build_reference_model(dims, ee, sd)
+    ref = reference_harness.reference_forward(model, docs)
+    out = port.forward(sd, dims, ee, docs)
+    assert torch.allclose(out["exit_logits"], ref["exit_logits"], atol=2e-6)
+    assert torch.allclose(out["head_logits"], ref["head_logits"], atol=2e-6)
+    assert torch.allclose(out["last_hidden"], ref["last_hidden"], atol=2e-5)
