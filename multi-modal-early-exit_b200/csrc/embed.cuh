@@ -1,0 +1,184 @@
+// Embedding-stage kernels (HBM-bound gathers + LayerNorm):
+//   posid_kernel        : RoBERTa position ids (HF modeling_layoutlmv3.py:139-147)
+//   text_embed_kernel   : 7-way gather-sum + embeddings.LayerNorm + model LayerNorm  (HF:161-200, 113-137;
+//                         reference call EE/models/LayoutLMv3.py:511-517, 565)
+//   im2col_kernel       : 16x16/s16 patches -> bf16 rows for the patch GEMM (HF:70-82)
+//   visual_ln_kernel    : cls|patch + pos_embed -> norm (eps 1e-6) -> model LayerNorm (EE/models/LayoutLMv3.py:358-373, 565)
+//   meanpool_kernel     : mean over the 709 fused tokens for the text_visual_concat exit (EE/models/LayoutLMv3.py:582)
+// Each token is LayerNormed twice, exactly as the reference does.
+#pragma once
+#include "ptx.cuh"
+
+namespace mmee {
+
+struct EmbedWeights {
+  const float* word;      // [vocab, H]
+  const float* type0;     // [H]  (token_type row 0)
+  const float* pos;       // [max_pos, H]
+  const float* x_emb;     // [1024, coord]
+  const float* y_emb;     // [1024, coord]
+  const float* h_emb;     // [1024, shape]
+  const float* w_emb;     // [1024, shape]
+  const float* ln_emb_w;  const float* ln_emb_b;    // embeddings.LayerNorm
+  const float* ln_model_w; const float* ln_model_b; // layoutlmv3.LayerNorm
+  const float* ln_vis_w;  const float* ln_vis_b;    // layoutlmv3.norm
+  const float* cls_token; // [H]
+  const float* pos_embed; // [n_vis, H]
+};
+
+// one warp per document: pos = cumsum(id != pad) * (id != pad) + pad
+__global__ void posid_kernel(const int64_t* __restrict__ ids, int* __restrict__ pos_out, int n_docs, int n_text,
+                             int pad_id) {
+  const int doc = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (doc >= n_docs) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t* row = ids + static_cast<size_t>(doc) * n_text;
+  int carry = 0;
+  for (int base = 0; base < n_text; base += 32) {
+    const int t = base + lane;
+    const int real = (t < n_text) && (row[t] != pad_id);
+    int incl = real;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (t < n_text) pos_out[static_cast<size_t>(doc) * n_text + t] = real ? (carry + incl + pad_id) : pad_id;
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+// LayerNorm of a row held as `NV` values per lane (column = lane + 32*i); fp32 two-pass.
+template <int NV>
+__device__ __forceinline__ void warp_layernorm(float (&v)[NV], int H, const float* __restrict__ w,
+                                               const float* __restrict__ b, float eps, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) if (lane + 32 * i < H) s += v[i];
+  const float mean = warp_sum(s) / H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) if (lane + 32 * i < H) { const float d = v[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) / H + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H) v[i] = (v[i] - mean) * rstd * __ldg(w + c) + __ldg(b + c);
+  }
+}
+
+// one warp per text token; X row = doc*seq + t
+template <int NV>
+__global__ void text_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ bbox,
+                                  const int* __restrict__ posid, EmbedWeights W, __nv_bfloat16* __restrict__ X,
+                                  int n_docs, int n_text, int seq, int H, int coord, int shape, float eps) {
+  const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= n_docs * n_text) return;
+  const int lane = threadIdx.x & 31;
+  const int doc = tok / n_text, t = tok - doc * n_text;
+  const int64_t id = ids[tok];
+  const int pos = posid[tok];
+  const int64_t* bb = bbox + static_cast<size_t>(tok) * 4;
+  const int x0 = static_cast<int>(bb[0]), y0 = static_cast<int>(bb[1]), x1 = static_cast<int>(bb[2]),
+            y1 = static_cast<int>(bb[3]);
+  const int hh = min(max(y1 - y0, 0), 1023), ww = min(max(x1 - x0, 0), 1023);
+  const float* wrow = W.word + static_cast<size_t>(id) * H;
+  const float* prow = W.pos + static_cast<size_t>(pos) * H;
+  float v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    float e = 0.f;
+    if (c < H) {
+      // same association as the reference: ((word + type) + pos) + spatial
+      e = __ldg(wrow + c) + __ldg(W.type0 + c);
+      e += __ldg(prow + c);
+      float sp;
+      if (c < coord) sp = __ldg(W.x_emb + static_cast<size_t>(x0) * coord + c);
+      else if (c < 2 * coord) sp = __ldg(W.y_emb + static_cast<size_t>(y0) * coord + (c - coord));
+      else if (c < 3 * coord) sp = __ldg(W.x_emb + static_cast<size_t>(x1) * coord + (c - 2 * coord));
+      else if (c < 4 * coord) sp = __ldg(W.y_emb + static_cast<size_t>(y1) * coord + (c - 3 * coord));
+      else if (c < 4 * coord + shape) sp = __ldg(W.h_emb + static_cast<size_t>(hh) * shape + (c - 4 * coord));
+      else sp = __ldg(W.w_emb + static_cast<size_t>(ww) * shape + (c - 4 * coord - shape));
+      e += sp;
+    }
+    v[i] = e;
+  }
+  warp_layernorm<NV>(v, H, W.ln_emb_w, W.ln_emb_b, eps, lane);
+  warp_layernorm<NV>(v, H, W.ln_model_w, W.ln_model_b, eps, lane);
+  __nv_bfloat16* out = X + (static_cast<size_t>(doc) * seq + t) * H;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H) out[c] = __float2bfloat16_rn(v[i]);
+  }
+}
+
+// pixels f32 [B,3,img,img] -> patches bf16 [B*np*np, 3*16*16], k = c*256 + kh*16 + kw (conv weight order)
+__global__ void im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ out, int n_docs, int img,
+                              int patch, int chans) {
+  const int np = img / patch;
+  const int kdim = chans * patch * patch;
+  const size_t total = static_cast<size_t>(n_docs) * np * np * kdim / 4;     // 4 pixels (one float4) per thread
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const size_t e = i * 4;
+  const int k = static_cast<int>(e % kdim);
+  const size_t rowi = e / kdim;
+  const int p = static_cast<int>(rowi % (np * np));
+  const int doc = static_cast<int>(rowi / (np * np));
+  const int c = k / (patch * patch), kh = (k / patch) % patch, kw = k % patch;
+  const int pr = p / np, pc = p % np;
+  const float4 v = *reinterpret_cast<const float4*>(
+      px + ((static_cast<size_t>(doc) * chans + c) * img + (pr * patch + kh)) * img + pc * patch + kw);
+  uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  *reinterpret_cast<uint2*>(out + e) = o;
+}
+
+// one warp per visual token (doc, p); VIS rows 1..n_patch hold conv + bias + pos_embed (written by the patch GEMM)
+template <int NV>
+__global__ void visual_ln_kernel(const float* __restrict__ VIS, EmbedWeights W, __nv_bfloat16* __restrict__ X,
+                                 int n_docs, int n_vis, int n_text, int seq, int H, float eps_vis, float eps) {
+  const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= n_docs * n_vis) return;
+  const int lane = threadIdx.x & 31;
+  const int doc = tok / n_vis, p = tok - doc * n_vis;
+  float v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    float e = 0.f;
+    if (c < H) e = (p == 0) ? (__ldg(W.cls_token + c) + __ldg(W.pos_embed + c))
+                            : VIS[(static_cast<size_t>(doc) * n_vis + p) * H + c];
+    v[i] = e;
+  }
+  warp_layernorm<NV>(v, H, W.ln_vis_w, W.ln_vis_b, eps_vis, lane);
+  warp_layernorm<NV>(v, H, W.ln_model_w, W.ln_model_b, eps, lane);
+  __nv_bfloat16* out = X + (static_cast<size_t>(doc) * seq + n_text + p) * H;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H) out[c] = __float2bfloat16_rn(v[i]);
+  }
+}
+
+// pool[doc][c] = mean_t X[doc*seq + t][c]; grid (ceil(H/32), n_docs), block 256 (8 warps stride the tokens)
+__global__ void meanpool_kernel(const __nv_bfloat16* __restrict__ X, float* __restrict__ pool, int seq, int H) {
+  __shared__ float part[8][33];
+  const int doc = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int w = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < H)
+    for (int t = w; t < seq; t += 8) s += __bfloat162float(X[(static_cast<size_t>(doc) * seq + t) * H + c]);
+  part[w][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (w == 0 && c < H) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += part[i][threadIdx.x];
+    pool[static_cast<size_t>(doc) * H + c] = tot / seq;
+  }
+}
+
+}  // namespace mmee
