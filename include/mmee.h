@@ -1,0 +1,109 @@
+/* libmmee — C ABI of the B200 (sm_100a) early-exit LayoutLMv3 inference engine.
+ *
+ * The reference (Jordy-VL/multi-modal-early-exit) has no FFI of its own: its boundary for this path is two
+ * Python call sites:
+ *   (1) outputs = model.forward(**batch)                       EE/utils.py:179
+ *       -> LayoutLMv3EEForSequenceClassification.forward       EE/models/LayoutLMv3.py:696-896
+ *   (2) Policy(logits, config).max_confidence_global_thresholding_policy()   EE/eval.py:91-98, EE/policy.py:12-53
+ * The entry points below are what a binding for those two call sites needs; the Python mirror of the
+ * reference interface (multi-modal-early-exit_b200/mmee/model.py) binds them with ctypes.
+ * Plain pointers and sizes only; return code 0 = ok, < 0 = error (text via mmee_last_error()).
+ * One engine per (device, model).  Calls on one engine are stream-ordered and NOT thread-safe.
+ */
+#ifndef MMEE_H_
+#define MMEE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMEE_MAX_EXITS 64
+
+typedef struct mmee_engine mmee_engine;
+
+/* Model description: HF LayoutLMv3Config fields (configuration_layoutlmv3.py) + the reference's ExitConfig
+ * (EE/models/EE_modules.py:175-195). */
+typedef struct {
+  int hidden, layers, heads, inter;
+  int n_text;               /* text tokens per document (512) */
+  int image, patch, channels;
+  int n_labels;
+  int coord, shape;         /* coordinate_size, shape_size: 4*coord + 2*shape == hidden */
+  int vocab, max_pos, max_2d;
+  int rel_bins, max_rel, rel2d_bins, max_rel2d;
+  int pad_id;
+  float ln_eps, vis_ln_eps;
+  int n_exits;                             /* E early exits, final classifier not counted */
+  int exit_after_layer[MMEE_MAX_EXITS];    /* ascending; 0 = text_visual_concat (embedding-level), 1..layers */
+  int head_kind;                           /* 0 ramp (EarlyExitHead.RAMP), 1 gate (EarlyExitHead.GATE) */
+  int head_layers;                         /* exit_head_num_layers: 1 | 2 */
+} mmee_model_desc;
+
+/* Exit policy: EarlyExitInference criterion + sign (EE/models/EE_modules.py:116-146), per-exit thresholds
+ * (EE/policy.py:17, :71-79) and per-exit temperatures (EE/generic_scaling.py:54-61, EE/eval.py:312-327). */
+typedef struct {
+  int criterion;              /* 0 max_confidence: exit iff crit > thr ; 1 entropy: exit iff crit < thr */
+  int mode;                   /* 0 dense: every exit head for every document (what the reference computes);
+                                 1 early-exit: exiting documents leave, deeper layers run on survivors only */
+  const float* thresholds;    /* [n_exits]   (host) */
+  const float* temperatures;  /* [n_exits+1] (host) or NULL for T = 1 */
+} mmee_policy;
+
+/* Result buffers.  All nullable except logits / exit_index.  Shapes use B = batch, K = n_labels, E = n_exits.
+ * In early-exit mode rows of all_* for exits a document never reached are NaN. */
+typedef struct {
+  float*   logits;          /* [B, K]     class logits of the exit each document took (Policy `predictions`) */
+  int32_t* exit_index;      /* [B]        index into the E+1 exits (Policy `exits_store`) */
+  float*   criterion;       /* [B]        criterion value at that exit (after temperature) */
+  float*   all_exit_logits; /* [E+1, B, K]  per-exit class logits (what EE/utils.py:182-193 stores) */
+  float*   all_head_logits; /* [E+1, B, K]  raw head outputs = exit_states[j][0] (first 2 cols in gate mode) */
+  float*   all_criteria;    /* [E+1, B] */
+  int64_t* exit_hist;       /* [E+1]      documents per exit */
+} mmee_outputs;
+
+int  mmee_create(const mmee_model_desc* desc, int device, int max_batch, mmee_engine** out);
+void mmee_destroy(mmee_engine* e);
+
+/* Copy one parameter (fp32, host memory) under its reference state-dict name
+ * (e.g. "layoutlmv3.encoder.layer.3.attention.self.query.weight"). */
+int  mmee_set_weight(mmee_engine* e, const char* hf_name, const float* host_data, const int64_t* shape, int rank);
+/* Optional: |rel| -> bucket tables of HF relative_position_bucket (modeling_layoutlmv3.py:393-414) computed
+ * by the caller; which = 0 (1-D, rel_pos_bins/max_rel_pos) or 1 (2-D).  Defaults are computed in C. */
+int  mmee_set_bucket_lut(mmee_engine* e, int which, const uint8_t* lut, int n);
+/* Read back the table in use (for tests). Returns the table length or < 0. */
+int  mmee_get_bucket_lut(mmee_engine* e, int which, uint8_t* lut_out, int capacity);
+/* Pack weights (bf16 conversion, fused QKV, 1/sqrt(d) folded into W_q) and verify none is missing. */
+int  mmee_finalize_weights(mmee_engine* e);
+
+/* One forward over B <= max_batch documents; inputs and outputs in HOST memory (the reference-facing call:
+ * host->device and device->host copies are part of it).
+ *   input_ids i64[B,n_text], bbox i64[B,n_text,4], attention_mask i64[B,n_text], pixel_values f32[B,C,img,img] */
+int  mmee_forward(mmee_engine* e, int B, const int64_t* input_ids, const int64_t* bbox, const int64_t* attention_mask,
+                  const float* pixel_values, const mmee_policy* policy, const mmee_outputs* out);
+/* Same, inputs and outputs already in DEVICE memory of the engine's GPU; asynchronous on `cuda_stream`
+ * (a cudaStream_t; NULL = the engine's own stream, synchronised before returning). */
+int  mmee_forward_device(mmee_engine* e, int B, const int64_t* input_ids, const int64_t* bbox,
+                         const int64_t* attention_mask, const float* pixel_values, const mmee_policy* policy,
+                         const mmee_outputs* out, void* cuda_stream);
+
+/* Number of kernels launched by the engine in the last forward (for the bench's gpu_launches). */
+int64_t mmee_last_launch_count(mmee_engine* e);
+/* Device time of the named stage of the last forward in ms ("total", "embed", "gemm", "attention", "norm", "exit");
+ * only recorded when mmee_set_profiling(e, 1) is on (adds event records between stages). */
+int  mmee_set_profiling(mmee_engine* e, int on);
+/* Synchronise the device and fold the recorded stage events of the last forward into per-stage times. */
+int  mmee_collect_profile(mmee_engine* e);
+double mmee_last_stage_ms(mmee_engine* e, const char* stage);
+/* Test hook: copy an internal activation buffer ("X0","X1","QK","VT","CTX","A1","MID","Y","VIS","POOL","BIAS")
+ * to host memory (synchronises the device). Returns bytes copied or < 0. */
+int64_t mmee_debug_read(mmee_engine* e, const char* name, void* host_dst, int64_t capacity_bytes);
+
+const char* mmee_last_error(void);
+const char* mmee_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMEE_H_ */

@@ -1,0 +1,891 @@
+// libmmee: engine object + C ABI (include/mmee.h).  Orchestrates the sm_100a kernels for the reference's
+// LayoutLMv3EEForSequenceClassification.forward (EE/models/LayoutLMv3.py:696-896) + exit policy
+// (EE/policy.py:12-53) with on-device survivor compaction.  No CPU fallback: every compute step is a
+// CUDA kernel from this directory.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/mmee.h"
+#include "attention.cuh"
+#include "embed.cuh"
+#include "gemm.cuh"
+#include "norm_exit.cuh"
+#include "tmap.h"
+
+using namespace mmee;
+
+namespace {
+
+thread_local std::string g_err;
+
+#define CUDA_OK(x)                                                                                   \
+  do {                                                                                               \
+    cudaError_t e_ = (x);                                                                            \
+    if (e_ != cudaSuccess)                                                                           \
+      throw std::runtime_error(std::string(#x) + ": " + cudaGetErrorString(e_) + " @" + std::to_string(__LINE__)); \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count, bool zero = false) {
+    release();
+    n = count;
+    if (count) {
+      CUDA_OK(cudaMalloc(&p, count * sizeof(T)));
+      if (zero) CUDA_OK(cudaMemset(p, 0, count * sizeof(T)));
+    }
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n, float scale) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i] * scale);
+}
+__global__ void scale_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, float scale) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n) dst[i] = src[i] * scale;
+}
+__global__ void init_forward_kernel(int* slot_doc, int* out_exit, int* n_dev, int* m_dev, unsigned long long* hist,
+                                    int B, int seq, int n_hist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) { slot_doc[i] = i; out_exit[i] = -1; }
+  if (i < n_hist) hist[i] = 0ull;
+  if (i == 0) { n_dev[0] = B; m_dev[0] = B * seq; }
+}
+__global__ void fill_nan_kernel(float* p, size_t n) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n) p[i] = __int_as_float(0x7fc00000);
+}
+// X_dst[new slot] = X_src[slot_src[new slot]] (bf16 rows); used only after an embedding-level exit.
+__global__ void gather_slots_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                    const int* __restrict__ slot_src, const int* __restrict__ n_dev, int seq, int H) {
+  const int slot = blockIdx.y;
+  if (slot >= *n_dev) return;
+  const size_t per_doc = static_cast<size_t>(seq) * H / 8;     // uint4 = 8 bf16
+  const uint4* s = reinterpret_cast<const uint4*>(src) + static_cast<size_t>(slot_src[slot]) * per_doc;
+  uint4* d = reinterpret_cast<uint4*>(dst) + static_cast<size_t>(slot) * per_doc;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < per_doc;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    d[i] = s[i];
+}
+__global__ void hist_to_i64_kernel(const unsigned long long* h, long long* out, int n) {
+  const int i = threadIdx.x;
+  if (i < n) out[i] = static_cast<long long>(h[i]);
+}
+
+struct LayerW {
+  DevBuf<__nv_bfloat16> wqkv, wo, wi, wo2;
+  DevBuf<float> bqkv, bo, bi, bo2, ln1_w, ln1_b, ln2_w, ln2_b;
+  CUtensorMap t_wqkv, t_wo, t_wi, t_wo2;
+};
+
+struct HeadW {
+  DevBuf<float> dense_w, dense_b, out_w, out_b;
+  int n_out = 0;
+  bool two_layer = false;
+  HeadWeights view() const {
+    HeadWeights h;
+    h.dense_w = two_layer ? dense_w.p : nullptr;
+    h.dense_b = dense_b.p;
+    h.out_w = out_w.p;
+    h.out_b = out_b.p;
+    h.n_out = n_out;
+    return h;
+  }
+};
+
+}  // namespace
+
+struct mmee_engine {
+  mmee_model_desc d;
+  int device = 0;
+  int max_batch = 0;
+  int H, L, heads, I, T, P, S, K, n_vis, n_patch, kdim_patch;
+  int kv_pitch = 768, bias_pitch = 712;
+  int m_max = 0;            // padded row capacity of activation buffers
+  int sms = 148;
+  int bn_h, bn_qkv, bn_i;   // BLOCK_N per GEMM family
+  cudaStream_t stream = nullptr;
+  bool finalized = false;
+  int64_t launches = 0;
+  bool profiling = false;
+  std::map<std::string, double> stage_ms;
+  std::vector<std::pair<std::string, cudaEvent_t>> ev;
+
+  // raw fp32 staging of weights until finalize
+  std::map<std::string, std::vector<float>> raw;
+  std::map<std::string, std::vector<int64_t>> raw_shape;
+
+  // weights
+  std::vector<LayerW> layers;
+  DevBuf<float> word, type0, pos, x_emb, y_emb, h_emb, w_emb, ln_emb_w, ln_emb_b, ln_model_w, ln_model_b, ln_vis_w,
+      ln_vis_b, cls_token, pos_embed, patch_b, w1d, wx, wy;
+  DevBuf<__nv_bfloat16> patch_w;
+  CUtensorMap t_patch_w;
+  std::vector<HeadW> exit_heads;     // one per configured exit (concat first if present)
+  HeadW classifier;
+  DevBuf<uint8_t> lut1, lut2;
+  std::vector<uint8_t> h_lut1, h_lut2;
+  DevBuf<int> vis_bbox;
+
+  // activations
+  DevBuf<__nv_bfloat16> X[2], QK, VT, CTX, A1, MID, PATCH;
+  DevBuf<float> Y, VIS, POOL;
+  DevBuf<__half> BIAS;
+  DevBuf<int> posid;
+  CUtensorMap t_x[2], t_qk, t_vt, t_bias, t_ctx, t_a1, t_mid, t_patch;
+
+  // bookkeeping (device)
+  DevBuf<int> n_dev, m_dev;                 // [stages]
+  DevBuf<int> slot_doc[2], slot_src;        // ping-pong slot->doc; new->old slot map
+  DevBuf<int> slot_fire, out_exit;
+  DevBuf<float> slot_logits, slot_head, slot_crit, out_logits, out_crit, all_logits, all_head, all_crit;
+  DevBuf<unsigned long long> hist;
+  DevBuf<long long> hist64;
+  // staged inputs (host path)
+  DevBuf<int64_t> in_ids, in_bbox, in_mask;
+  DevBuf<float> in_px;
+  void* pin_in = nullptr;
+  size_t pin_in_bytes = 0;
+  void* pin_out = nullptr;
+  size_t pin_out_bytes = 0;
+
+  ~mmee_engine() {
+    if (pin_in) cudaFreeHost(pin_in);
+    if (pin_out) cudaFreeHost(pin_out);
+    for (auto& e : ev) cudaEventDestroy(e.second);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+int n_stages(const mmee_engine* e) { return e->d.n_exits + 3; }
+
+std::vector<uint8_t> default_lut(int num_buckets, int max_distance, int n) {
+  // HF relative_position_bucket (modeling_layoutlmv3.py:393-414), bidirectional: table over |rel|.
+  const int nb = num_buckets / 2;
+  const int max_exact = nb / 2;
+  std::vector<uint8_t> lut(n);
+  const float denom = static_cast<float>(log(static_cast<double>(max_distance) / max_exact));
+  for (int i = 0; i < n; ++i) {
+    int v;
+    if (i < max_exact) {
+      v = i;
+    } else {
+      const float q = static_cast<float>(i) / static_cast<float>(max_exact);
+      const float val = logf(q) / denom * static_cast<float>(nb - max_exact);
+      v = max_exact + static_cast<int>(val);
+      if (v > nb - 1) v = nb - 1;
+    }
+    lut[i] = static_cast<uint8_t>(v);
+  }
+  return lut;
+}
+
+const std::vector<float>& need(mmee_engine* e, const std::string& name, std::initializer_list<int64_t> shape) {
+  auto it = e->raw.find(name);
+  if (it == e->raw.end()) throw std::runtime_error("missing weight: " + name);
+  size_t n = 1;
+  for (auto s : shape) n *= static_cast<size_t>(s);
+  if (it->second.size() != n)
+    throw std::runtime_error("bad size for " + name + ": got " + std::to_string(it->second.size()) + " want " +
+                             std::to_string(n));
+  return it->second;
+}
+
+void upload_f32(DevBuf<float>& dst, const std::vector<float>& src, float scale = 1.f) {
+  dst.alloc(src.size());
+  if (scale == 1.f) {
+    CUDA_OK(cudaMemcpy(dst.p, src.data(), src.size() * 4, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<float> t(src);
+    for (auto& v : t) v *= scale;
+    CUDA_OK(cudaMemcpy(dst.p, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+  }
+}
+
+// dst[offset ...] = bf16(src * scale)
+void upload_bf16(__nv_bfloat16* dst, const std::vector<float>& src, float scale = 1.f) {
+  DevBuf<float> tmp;
+  tmp.alloc(src.size());
+  CUDA_OK(cudaMemcpy(tmp.p, src.data(), src.size() * 4, cudaMemcpyHostToDevice));
+  f32_to_bf16_kernel<<<static_cast<unsigned>((src.size() + 255) / 256), 256>>>(tmp.p, dst, src.size(), scale);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaDeviceSynchronize());
+}
+
+void load_head(mmee_engine* e, HeadW& h, const std::string& prefix, int n_out) {
+  const int H = e->H;
+  h.n_out = n_out;
+  h.two_layer = e->d.head_layers == 2;
+  if (h.two_layer) {
+    upload_f32(h.dense_w, need(e, prefix + ".dense.weight", {H, H}));
+    upload_f32(h.dense_b, need(e, prefix + ".dense.bias", {H}));
+  }
+  upload_f32(h.out_w, need(e, prefix + ".out_proj.weight", {n_out, H}));
+  upload_f32(h.out_b, need(e, prefix + ".out_proj.bias", {n_out}));
+}
+
+template <int BN, int EPI>
+void launch_gemm_t(mmee_engine* e, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t st) {
+  auto kern = gemm_tc_kernel<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::DYN_BYTES));
+    configured = true;
+  }
+  kern<<<e->sms, GEMM_THREADS, GemmSmem<BN>::DYN_BYTES, st>>>(ta, tb, a);
+  CUDA_OK(cudaGetLastError());
+  e->launches++;
+}
+
+template <int EPI>
+void launch_gemm(mmee_engine* e, int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a,
+                 cudaStream_t st) {
+  if (bn == 256) launch_gemm_t<256, EPI>(e, ta, tb, a, st);
+  else launch_gemm_t<128, EPI>(e, ta, tb, a, st);
+}
+
+int pick_bn(int n) { return (n % 256 == 0) ? 256 : 128; }
+
+template <typename F>
+void launch_nv(int H, F&& f) {   // dispatch on values-per-lane for the warp-per-row kernels
+  if (H <= 128) f(std::integral_constant<int, 4>{});
+  else if (H <= 256) f(std::integral_constant<int, 8>{});
+  else if (H <= 768) f(std::integral_constant<int, 24>{});
+  else if (H <= 1024) f(std::integral_constant<int, 32>{});
+  else throw std::runtime_error("hidden size > 1024 not supported");
+}
+
+void mark(mmee_engine* e, const char* name, cudaStream_t st) {
+  if (!e->profiling) return;
+  cudaEvent_t evn;
+  CUDA_OK(cudaEventCreate(&evn));
+  CUDA_OK(cudaEventRecord(evn, st));
+  e->ev.emplace_back(name, evn);
+}
+
+void finalize(mmee_engine* e) {
+  const mmee_model_desc& d = e->d;
+  const int H = e->H, I = e->I, h = e->heads;
+  CUDA_OK(cudaSetDevice(e->device));
+  const std::string p = "layoutlmv3.";
+  const std::string em = p + "embeddings.";
+  upload_f32(e->word, need(e, em + "word_embeddings.weight", {d.vocab, H}));
+  {
+    const auto& tt = e->raw.at(em + "token_type_embeddings.weight");
+    if (tt.size() < static_cast<size_t>(H)) throw std::runtime_error("token_type_embeddings too small");
+    std::vector<float> row0(tt.begin(), tt.begin() + H);
+    upload_f32(e->type0, row0);
+  }
+  upload_f32(e->pos, need(e, em + "position_embeddings.weight", {d.max_pos, H}));
+  upload_f32(e->x_emb, need(e, em + "x_position_embeddings.weight", {d.max_2d, d.coord}));
+  upload_f32(e->y_emb, need(e, em + "y_position_embeddings.weight", {d.max_2d, d.coord}));
+  upload_f32(e->h_emb, need(e, em + "h_position_embeddings.weight", {d.max_2d, d.shape}));
+  upload_f32(e->w_emb, need(e, em + "w_position_embeddings.weight", {d.max_2d, d.shape}));
+  upload_f32(e->ln_emb_w, need(e, em + "LayerNorm.weight", {H}));
+  upload_f32(e->ln_emb_b, need(e, em + "LayerNorm.bias", {H}));
+  upload_f32(e->ln_model_w, need(e, p + "LayerNorm.weight", {H}));
+  upload_f32(e->ln_model_b, need(e, p + "LayerNorm.bias", {H}));
+  upload_f32(e->ln_vis_w, need(e, p + "norm.weight", {H}));
+  upload_f32(e->ln_vis_b, need(e, p + "norm.bias", {H}));
+  upload_f32(e->cls_token, need(e, p + "cls_token", {H}));
+  upload_f32(e->pos_embed, need(e, p + "pos_embed", {e->n_vis, H}));
+  upload_f32(e->patch_b, need(e, p + "patch_embed.proj.bias", {H}));
+  e->patch_w.alloc(static_cast<size_t>(H) * e->kdim_patch);
+  upload_bf16(e->patch_w.p, need(e, p + "patch_embed.proj.weight", {H, e->kdim_patch}));
+  upload_f32(e->w1d, need(e, p + "encoder.rel_pos_bias.weight", {h, d.rel_bins}));
+  upload_f32(e->wx, need(e, p + "encoder.rel_pos_x_bias.weight", {h, d.rel2d_bins}));
+  upload_f32(e->wy, need(e, p + "encoder.rel_pos_y_bias.weight", {h, d.rel2d_bins}));
+
+  const float qscale = 1.0f / sqrtf(static_cast<float>(H / h));   // 0.125: exact power of two
+  e->layers.resize(e->L);
+  for (int i = 0; i < e->L; ++i) {
+    LayerW& w = e->layers[i];
+    const std::string lp = p + "encoder.layer." + std::to_string(i) + ".";
+    w.wqkv.alloc(static_cast<size_t>(3) * H * H);
+    upload_bf16(w.wqkv.p, need(e, lp + "attention.self.query.weight", {H, H}), qscale);
+    upload_bf16(w.wqkv.p + static_cast<size_t>(H) * H, need(e, lp + "attention.self.key.weight", {H, H}));
+    upload_bf16(w.wqkv.p + static_cast<size_t>(2) * H * H, need(e, lp + "attention.self.value.weight", {H, H}));
+    {
+      std::vector<float> b(3 * H);
+      const auto& bq = need(e, lp + "attention.self.query.bias", {H});
+      const auto& bk = need(e, lp + "attention.self.key.bias", {H});
+      const auto& bv = need(e, lp + "attention.self.value.bias", {H});
+      for (int j = 0; j < H; ++j) { b[j] = bq[j] * qscale; b[H + j] = bk[j]; b[2 * H + j] = bv[j]; }
+      upload_f32(w.bqkv, b);
+    }
+    w.wo.alloc(static_cast<size_t>(H) * H);
+    upload_bf16(w.wo.p, need(e, lp + "attention.output.dense.weight", {H, H}));
+    upload_f32(w.bo, need(e, lp + "attention.output.dense.bias", {H}));
+    upload_f32(w.ln1_w, need(e, lp + "attention.output.LayerNorm.weight", {H}));
+    upload_f32(w.ln1_b, need(e, lp + "attention.output.LayerNorm.bias", {H}));
+    w.wi.alloc(static_cast<size_t>(I) * H);
+    upload_bf16(w.wi.p, need(e, lp + "intermediate.dense.weight", {I, H}));
+    upload_f32(w.bi, need(e, lp + "intermediate.dense.bias", {I}));
+    w.wo2.alloc(static_cast<size_t>(H) * I);
+    upload_bf16(w.wo2.p, need(e, lp + "output.dense.weight", {H, I}));
+    upload_f32(w.bo2, need(e, lp + "output.dense.bias", {H}));
+    upload_f32(w.ln2_w, need(e, lp + "output.LayerNorm.weight", {H}));
+    upload_f32(w.ln2_b, need(e, lp + "output.LayerNorm.bias", {H}));
+    w.t_wqkv = make_tmap_2d_sw128(w.wqkv.p, 3 * H, H, H, e->bn_qkv);
+    w.t_wo = make_tmap_2d_sw128(w.wo.p, H, H, H, e->bn_h);
+    w.t_wi = make_tmap_2d_sw128(w.wi.p, I, H, H, e->bn_i);
+    w.t_wo2 = make_tmap_2d_sw128(w.wo2.p, H, I, I, e->bn_h);
+  }
+  e->t_patch_w = make_tmap_2d_sw128(e->patch_w.p, H, e->kdim_patch, e->kdim_patch, e->bn_h);
+
+  const int n_head_out = d.head_kind == 0 ? d.n_labels : 2;
+  e->exit_heads.resize(d.n_exits);
+  int k_enc = 0;
+  for (int x = 0; x < d.n_exits; ++x) {
+    if (d.exit_after_layer[x] == 0) load_head(e, e->exit_heads[x], p + "concat_exit_embeddings", n_head_out);
+    else load_head(e, e->exit_heads[x], p + "encoder.early_exits." + std::to_string(k_enc++), n_head_out);
+  }
+  load_head(e, e->classifier, "classifier", d.n_labels);
+  e->classifier.two_layer = true;   // HF ClassificationHead always has dense + out_proj (HF:798-822)
+  if (!e->classifier.dense_w.p) {
+    upload_f32(e->classifier.dense_w, need(e, "classifier.dense.weight", {H, H}));
+    upload_f32(e->classifier.dense_b, need(e, "classifier.dense.bias", {H}));
+  }
+
+  if (e->h_lut1.empty()) e->h_lut1 = default_lut(d.rel_bins, d.max_rel, 1024);
+  if (e->h_lut2.empty()) e->h_lut2 = default_lut(d.rel2d_bins, d.max_rel2d, 1024);
+  e->lut1.alloc(e->h_lut1.size());
+  e->lut2.alloc(e->h_lut2.size());
+  CUDA_OK(cudaMemcpy(e->lut1.p, e->h_lut1.data(), e->h_lut1.size(), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(e->lut2.p, e->h_lut2.data(), e->h_lut2.size(), cudaMemcpyHostToDevice));
+
+  // visual token boxes (HF:576-602): CLS [1,1,999,999]; grid edges trunc(1000*k/n)
+  {
+    const int ns = d.image / d.patch;
+    std::vector<int> vb(static_cast<size_t>(e->n_vis) * 4);
+    vb[0] = 1; vb[1] = 1; vb[2] = 999; vb[3] = 999;
+    for (int r = 0; r < ns; ++r)
+      for (int c = 0; c < ns; ++c) {
+        int* b = &vb[static_cast<size_t>(1 + r * ns + c) * 4];
+        b[0] = 1000 * c / ns; b[1] = 1000 * r / ns; b[2] = 1000 * (c + 1) / ns; b[3] = 1000 * (r + 1) / ns;
+      }
+    e->vis_bbox.alloc(vb.size());
+    CUDA_OK(cudaMemcpy(e->vis_bbox.p, vb.data(), vb.size() * 4, cudaMemcpyHostToDevice));
+  }
+  e->raw.clear();
+  e->raw_shape.clear();
+  e->finalized = true;
+}
+
+void allocate(mmee_engine* e) {
+  const int B = e->max_batch, S = e->S, H = e->H, I = e->I, heads = e->heads;
+  e->m_max = ((B * S + 127) / 128) * 128 + 128;
+  const size_t M = e->m_max;
+  for (int i = 0; i < 2; ++i) e->X[i].alloc(M * H, true);
+  e->QK.alloc(M * 2 * H, true);
+  e->VT.alloc(static_cast<size_t>(B) * heads * 64 * e->kv_pitch, true);
+  e->CTX.alloc(M * H, true);
+  e->A1.alloc(M * H, true);
+  e->MID.alloc(M * I, true);
+  e->Y.alloc(M * H, true);
+  const size_t mp = (static_cast<size_t>(B) * e->n_patch + 127) / 128 * 128 + 128;
+  e->PATCH.alloc(mp * e->kdim_patch, true);
+  e->VIS.alloc(static_cast<size_t>(B) * e->n_vis * H, true);
+  e->POOL.alloc(static_cast<size_t>(B) * H, true);
+  e->BIAS.alloc(static_cast<size_t>(B) * heads * S * e->bias_pitch + 64 * 1024, true);
+  e->posid.alloc(static_cast<size_t>(B) * e->T);
+
+  e->t_x[0] = make_tmap_2d_sw128(e->X[0].p, M, H, H, 128);
+  e->t_x[1] = make_tmap_2d_sw128(e->X[1].p, M, H, H, 128);
+  e->t_qk = make_tmap_2d_sw128(e->QK.p, M, 2 * H, 2 * H, 128);
+  e->t_vt = make_tmap_2d_sw128(e->VT.p, static_cast<uint64_t>(B) * heads * 64, e->kv_pitch, e->kv_pitch, 64);
+  e->t_bias = make_tmap_2d_sw128(e->BIAS.p, static_cast<uint64_t>(B) * heads * S, e->bias_pitch, e->bias_pitch, 128,
+                                 CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+  e->t_ctx = make_tmap_2d_sw128(e->CTX.p, M, H, H, 128);
+  e->t_a1 = make_tmap_2d_sw128(e->A1.p, M, H, H, 128);
+  e->t_mid = make_tmap_2d_sw128(e->MID.p, M, I, I, 128);
+  e->t_patch = make_tmap_2d_sw128(e->PATCH.p, mp, e->kdim_patch, e->kdim_patch, 128);
+
+  const int st = n_stages(e);
+  e->n_dev.alloc(st, true);
+  e->m_dev.alloc(st, true);
+  e->slot_doc[0].alloc(B);
+  e->slot_doc[1].alloc(B);
+  e->slot_src.alloc(B);
+  e->slot_fire.alloc(B);
+  e->out_exit.alloc(B);
+  const int K = e->K, E1 = e->d.n_exits + 1;
+  e->slot_logits.alloc(static_cast<size_t>(B) * K);
+  e->slot_head.alloc(static_cast<size_t>(B) * K);
+  e->slot_crit.alloc(B);
+  e->out_logits.alloc(static_cast<size_t>(B) * K);
+  e->out_crit.alloc(B);
+  e->all_logits.alloc(static_cast<size_t>(E1) * B * K);
+  e->all_head.alloc(static_cast<size_t>(E1) * B * K);
+  e->all_crit.alloc(static_cast<size_t>(E1) * B);
+  e->hist.alloc(E1, true);
+  e->hist64.alloc(E1, true);
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bbox, const int64_t* mask,
+                    const float* px, const mmee_policy* pol, const mmee_outputs* out, cudaStream_t st) {
+  if (!e->finalized) throw std::runtime_error("weights not finalized");
+  if (B < 1 || B > e->max_batch) throw std::runtime_error("batch out of range");
+  if (!pol || (e->d.n_exits > 0 && !pol->thresholds)) throw std::runtime_error("policy/thresholds missing");
+  if (!out || !out->logits || !out->exit_index) throw std::runtime_error("outputs missing");
+  const mmee_model_desc& d = e->d;
+  const int H = e->H, S = e->S, T = e->T, K = e->K, heads = e->heads, I = e->I;
+  const int E = d.n_exits, E1 = E + 1;
+  const bool leave = pol->mode == 1;
+  const bool gate = d.head_kind == 1;
+  const int n_head = gate ? 2 : K;
+  e->launches = 0;
+  for (auto& x : e->ev) cudaEventDestroy(x.second);
+  e->ev.clear();
+  mark(e, "start", st);
+
+  init_forward_kernel<<<(std::max(B, E1) + 255) / 256, 256, 0, st>>>(e->slot_doc[0].p, e->out_exit.p, e->n_dev.p,
+                                                                       e->m_dev.p, e->hist.p, B, S, E1);
+  e->launches++;
+  const bool want_all = out->all_exit_logits || out->all_head_logits || out->all_criteria;
+  if (want_all) {
+    const size_t n1 = static_cast<size_t>(E1) * B * K, n2 = static_cast<size_t>(E1) * B;
+    fill_nan_kernel<<<static_cast<unsigned>((n1 + 255) / 256), 256, 0, st>>>(e->all_logits.p, n1);
+    fill_nan_kernel<<<static_cast<unsigned>((n1 + 255) / 256), 256, 0, st>>>(e->all_head.p, n1);
+    fill_nan_kernel<<<static_cast<unsigned>((n2 + 255) / 256), 256, 0, st>>>(e->all_crit.p, n2);
+    e->launches += 3;
+  }
+
+  // ---- embeddings
+  EmbedWeights ew;
+  ew.word = e->word.p; ew.type0 = e->type0.p; ew.pos = e->pos.p; ew.x_emb = e->x_emb.p; ew.y_emb = e->y_emb.p;
+  ew.h_emb = e->h_emb.p; ew.w_emb = e->w_emb.p; ew.ln_emb_w = e->ln_emb_w.p; ew.ln_emb_b = e->ln_emb_b.p;
+  ew.ln_model_w = e->ln_model_w.p; ew.ln_model_b = e->ln_model_b.p; ew.ln_vis_w = e->ln_vis_w.p;
+  ew.ln_vis_b = e->ln_vis_b.p; ew.cls_token = e->cls_token.p; ew.pos_embed = e->pos_embed.p;
+
+  posid_kernel<<<(B + 7) / 8, 256, 0, st>>>(ids, e->posid.p, B, T, d.pad_id);
+  e->launches++;
+  launch_nv(H, [&](auto nv) {
+    text_embed_kernel<decltype(nv)::value><<<(B * T + 7) / 8, 256, 0, st>>>(
+        ids, bbox, e->posid.p, ew, e->X[0].p, B, T, S, H, d.coord, d.shape, d.ln_eps);
+  });
+  e->launches++;
+  {
+    const size_t total = static_cast<size_t>(B) * e->n_patch * e->kdim_patch / 4;
+    im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(px, e->PATCH.p, B, d.image, d.patch,
+                                                                              d.channels);
+    e->launches++;
+    GemmArgs ga{};
+    ga.m_dev = nullptr; ga.m_static = B * e->n_patch; ga.N = H; ga.K = e->kdim_patch; ga.bias = e->patch_b.p;
+    ga.out = e->VIS.p; ga.ld_out = H; ga.pos = e->pos_embed.p; ga.n_patch = e->n_patch; ga.n_vis = e->n_vis;
+    launch_gemm<EPI_PATCH>(e, e->bn_h, e->t_patch, e->t_patch_w, ga, st);
+    launch_nv(H, [&](auto nv) {
+      visual_ln_kernel<decltype(nv)::value><<<(B * e->n_vis + 7) / 8, 256, 0, st>>>(
+          e->VIS.p, ew, e->X[0].p, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps);
+    });
+    e->launches++;
+  }
+  {
+    BiasArgs ba;
+    ba.bbox = bbox; ba.mask = mask; ba.vis_bbox = e->vis_bbox.p; ba.w1d = e->w1d.p; ba.wx = e->wx.p; ba.wy = e->wy.p;
+    ba.lut1 = e->lut1.p; ba.lut2 = e->lut2.p; ba.lut1_n = static_cast<int>(e->lut1.n); ba.lut2_n = static_cast<int>(e->lut2.n);
+    ba.bins1 = d.rel_bins; ba.bins2 = d.rel2d_bins; ba.heads = heads; ba.n_text = T; ba.seq = S; ba.pitch = e->bias_pitch;
+    ba.scale = 1.0f / sqrtf(static_cast<float>(H / heads)); ba.out = e->BIAS.p;
+    const size_t smem = static_cast<size_t>(heads) * (d.rel_bins + 2 * d.rel2d_bins) * 4;
+    bias_build_kernel<<<dim3((e->bias_pitch + 127) / 128, S, B), 128, smem, st>>>(ba);
+    e->launches++;
+  }
+  mark(e, "embed", st);
+
+  int stage = 0;       // index into n_dev / m_dev
+  int cur = 0;         // X buffer holding the current layer input
+  int sd = 0;          // slot_doc ping-pong index
+  int exit_no = 0;     // next exit to evaluate
+
+  auto run_exit = [&](const float* rows, size_t row_stride, const float* ln_w, const float* ln_b,
+                      const HeadW& head, bool is_final, const int* rows_slot_src) {
+    ExitArgs xa{};
+    xa.rows = rows; xa.row_stride = row_stride; xa.ln_w = ln_w; xa.ln_b = ln_b; xa.ln_eps = d.ln_eps; xa.H = H;
+    xa.slot_src = rows_slot_src;
+    const bool use_cls = gate && !is_final;
+    xa.head = head.view();
+    xa.cls = e->classifier.view();
+    xa.gate_mode = use_cls ? 1 : 0;
+    xa.n_labels = K;
+    xa.criterion = pol->criterion;
+    const float Te = pol->temperatures ? pol->temperatures[exit_no] : 1.f;
+    xa.inv_temp = 1.0f / Te;
+    xa.threshold = is_final ? 0.f : pol->thresholds[exit_no];
+    xa.force = is_final ? 1 : 0;
+    xa.n_active_dev = e->n_dev.p + stage;
+    xa.slot_logits = e->slot_logits.p; xa.slot_head = e->slot_head.p; xa.slot_crit = e->slot_crit.p;
+    xa.slot_fire = e->slot_fire.p;
+    exit_head_kernel<<<(B + EXIT_DOCS_PER_CTA - 1) / EXIT_DOCS_PER_CTA, EXIT_THREADS, 0, st>>>(xa);
+    CompactArgs ca{};
+    ca.n_active_dev = e->n_dev.p + stage; ca.n_next_dev = e->n_dev.p + stage + 1; ca.m_next_dev = e->m_dev.p + stage + 1;
+    ca.seq = S; ca.slot_doc = e->slot_doc[sd].p; ca.next_slot_doc = e->slot_doc[sd ^ 1].p;
+    ca.next_slot_src = e->slot_src.p; ca.slot_fire = e->slot_fire.p; ca.slot_logits = e->slot_logits.p;
+    ca.slot_head = e->slot_head.p; ca.slot_crit = e->slot_crit.p; ca.K = K;
+    ca.n_head = head.n_out;
+    ca.exit_index = exit_no; ca.leave = (leave || is_final) ? 1 : 0;
+    ca.out_logits = e->out_logits.p; ca.out_crit = e->out_crit.p; ca.out_exit = e->out_exit.p;
+    ca.all_logits = want_all ? e->all_logits.p : nullptr; ca.all_head = want_all ? e->all_head.p : nullptr;
+    ca.all_crit = want_all ? e->all_crit.p : nullptr; ca.B = B; ca.n_head_max = K; ca.hist = e->hist.p;
+    compact_kernel<<<1, 1024, 0, st>>>(ca);
+    e->launches += 2;
+    stage += 1; sd ^= 1; exit_no += 1;
+  };
+
+  // ---- embedding-level exit (text_visual_concat): mean over the 709 fused tokens
+  if (E > 0 && d.exit_after_layer[0] == 0) {
+    meanpool_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->X[cur].p, e->POOL.p, S, H);
+    e->launches++;
+    run_exit(e->POOL.p, H, nullptr, nullptr, e->exit_heads[0], false, nullptr);
+    if (leave) {
+      gather_slots_kernel<<<dim3(32, B), 256, 0, st>>>(e->X[cur].p, e->X[cur ^ 1].p, e->slot_src.p, e->n_dev.p + stage, S, H);
+      e->launches++;
+      cur ^= 1;
+    }
+    mark(e, "exit", st);
+  }
+
+  // ---- encoder layers
+  for (int l = 0; l < e->L; ++l) {
+    LayerW& w = e->layers[l];
+    const int* mdev = e->m_dev.p + stage;
+    GemmArgs ga{};
+    ga.m_dev = mdev; ga.N = 3 * H; ga.K = H; ga.bias = w.bqkv.p; ga.out = e->QK.p; ga.ld_out = 2 * H;
+    ga.vt = e->VT.p; ga.qk_cols = 2 * H; ga.seq = S; ga.kv_pitch = e->kv_pitch; ga.heads = heads;
+    launch_gemm<EPI_QKV>(e, e->bn_qkv, e->t_x[cur], w.t_wqkv, ga, st);
+    mark(e, "gemm", st);
+
+    AttArgs aa;
+    aa.n_active_dev = e->n_dev.p + stage; aa.slot_doc = e->slot_doc[sd].p; aa.ctx = e->CTX.p; aa.H = H;
+    aa.heads = heads; aa.seq = S;
+    {
+      static bool configured = false;
+      if (!configured) {
+        CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
+        configured = true;
+      }
+      attention_kernel<<<dim3((S + ATT_BQ - 1) / ATT_BQ, heads, B), ATT_THREADS, AttSmem::DYN_BYTES, st>>>(
+          e->t_qk, e->t_vt, e->t_bias, aa);
+      CUDA_OK(cudaGetLastError());
+      e->launches++;
+    }
+    mark(e, "attention", st);
+
+    ga = GemmArgs{};
+    ga.m_dev = mdev; ga.N = H; ga.K = H; ga.bias = w.bo.p; ga.out = e->Y.p; ga.ld_out = H; ga.resid = e->X[cur].p;
+    launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_ctx, w.t_wo, ga, st);
+    mark(e, "gemm", st);
+    launch_nv(H, [&](auto nv) {
+      ln_rows_kernel<decltype(nv)::value><<<(B * S + 7) / 8, 256, 0, st>>>(e->Y.p, e->A1.p, w.ln1_w.p, w.ln1_b.p,
+                                                                          d.ln_eps, H, S, mdev, nullptr);
+    });
+    e->launches++;
+    mark(e, "norm", st);
+
+    ga = GemmArgs{};
+    ga.m_dev = mdev; ga.N = I; ga.K = H; ga.bias = w.bi.p; ga.out = e->MID.p; ga.ld_out = I;
+    launch_gemm<EPI_GELU_BF16>(e, e->bn_i, e->t_a1, w.t_wi, ga, st);
+    ga = GemmArgs{};
+    ga.m_dev = mdev; ga.N = H; ga.K = I; ga.bias = w.bo2.p; ga.out = e->Y.p; ga.ld_out = H; ga.resid = e->A1.p;
+    launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_mid, w.t_wo2, ga, st);
+    mark(e, "gemm", st);
+
+    const bool last = (l == e->L - 1);
+    const bool exit_here = (exit_no < E && d.exit_after_layer[exit_no] == l + 1);
+    const int* ln_src = nullptr;
+    if (exit_here) {
+      run_exit(e->Y.p, static_cast<size_t>(S) * H, w.ln2_w.p, w.ln2_b.p, e->exit_heads[exit_no], false, nullptr);
+      if (leave) ln_src = e->slot_src.p;
+      mark(e, "exit", st);
+    }
+    if (!last) {
+      launch_nv(H, [&](auto nv) {
+        ln_rows_kernel<decltype(nv)::value><<<(B * S + 7) / 8, 256, 0, st>>>(
+            e->Y.p, e->X[cur ^ 1].p, w.ln2_w.p, w.ln2_b.p, d.ln_eps, H, S, e->m_dev.p + stage, ln_src);
+      });
+      e->launches++;
+      cur ^= 1;
+      mark(e, "norm", st);
+    } else {
+      // final classifier on the CLS row of the last layer (EE/models/LayoutLMv3.py:730-731); rows still live in
+      // Y under the pre-compaction slot numbering when an exit was just taken at layer L.
+      run_exit(e->Y.p, static_cast<size_t>(S) * H, w.ln2_w.p, w.ln2_b.p, e->classifier, true, ln_src);
+      mark(e, "exit", st);
+    }
+  }
+
+  // ---- results (device -> caller's device buffers)
+  hist_to_i64_kernel<<<1, 64, 0, st>>>(e->hist.p, e->hist64.p, E1);
+  e->launches++;
+  CUDA_OK(cudaMemcpyAsync(out->logits, e->out_logits.p, static_cast<size_t>(B) * K * 4, cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(out->exit_index, e->out_exit.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, st));
+  if (out->criterion) CUDA_OK(cudaMemcpyAsync(out->criterion, e->out_crit.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, st));
+  if (out->all_exit_logits) CUDA_OK(cudaMemcpyAsync(out->all_exit_logits, e->all_logits.p, static_cast<size_t>(E1) * B * K * 4, cudaMemcpyDeviceToDevice, st));
+  if (out->all_head_logits) CUDA_OK(cudaMemcpyAsync(out->all_head_logits, e->all_head.p, static_cast<size_t>(E1) * B * K * 4, cudaMemcpyDeviceToDevice, st));
+  if (out->all_criteria) CUDA_OK(cudaMemcpyAsync(out->all_criteria, e->all_crit.p, static_cast<size_t>(E1) * B * 4, cudaMemcpyDeviceToDevice, st));
+  if (out->exit_hist) CUDA_OK(cudaMemcpyAsync(out->exit_hist, e->hist64.p, static_cast<size_t>(E1) * 8, cudaMemcpyDeviceToDevice, st));
+  mark(e, "end", st);
+}
+
+void collect_profile(mmee_engine* e) {
+  e->stage_ms.clear();
+  if (!e->profiling || e->ev.size() < 2) return;
+  double total = 0;
+  for (size_t i = 1; i < e->ev.size(); ++i) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev[i - 1].second, e->ev[i].second);
+    e->stage_ms[e->ev[i].first] += ms;
+    total += ms;
+  }
+  e->stage_ms["total"] = total;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+#define MMEE_TRY try {
+#define MMEE_CATCH                                  \
+  }                                                 \
+  catch (const std::exception& ex) {                \
+    g_err = ex.what();                              \
+    return -1;                                      \
+  }                                                 \
+  catch (...) {                                     \
+    g_err = "unknown error";                        \
+    return -2;                                      \
+  }
+
+extern "C" {
+
+const char* mmee_last_error(void) { return g_err.c_str(); }
+const char* mmee_version(void) { return "mmee-b200 0.1 (sm_100a)"; }
+
+int mmee_create(const mmee_model_desc* desc, int device, int max_batch, mmee_engine** out) {
+  MMEE_TRY
+  if (!desc || !out) throw std::runtime_error("null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw std::runtime_error("no CUDA device: libmmee has no CPU fallback");
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) throw std::runtime_error(std::string("libmmee is built for sm_100a only; device is ") + prop.name);
+  const mmee_model_desc& d = *desc;
+  if (d.hidden % d.heads || d.hidden / d.heads != 64) throw std::runtime_error("head_dim must be 64");
+  if (4 * d.coord + 2 * d.shape != d.hidden) throw std::runtime_error("4*coord + 2*shape != hidden");
+  if (d.hidden % 128 || d.inter % 128 || d.hidden > 1024) throw std::runtime_error("hidden/inter must be multiples of 128, hidden <= 1024");
+  if (d.n_labels > 32 || d.n_labels < 2) throw std::runtime_error("n_labels must be in [2, 32]");
+  if (d.n_exits < 0 || d.n_exits > MMEE_MAX_EXITS) throw std::runtime_error("bad n_exits");
+  for (int i = 0; i < d.n_exits; ++i) {
+    if (d.exit_after_layer[i] < 0 || d.exit_after_layer[i] > d.layers) throw std::runtime_error("exit layer out of range");
+    if (i && d.exit_after_layer[i] <= d.exit_after_layer[i - 1]) throw std::runtime_error("exits must be ascending");
+  }
+  if ((d.channels * d.patch * d.patch) % 64) throw std::runtime_error("patch K dim must be a multiple of 64");
+  if (max_batch < 1) throw std::runtime_error("max_batch < 1");
+  auto* e = new mmee_engine();
+  e->d = d;
+  e->device = device;
+  e->max_batch = max_batch;
+  e->H = d.hidden; e->L = d.layers; e->heads = d.heads; e->I = d.inter; e->T = d.n_text; e->K = d.n_labels;
+  e->n_patch = (d.image / d.patch) * (d.image / d.patch);
+  e->n_vis = e->n_patch + 1;
+  e->S = e->T + e->n_vis;
+  e->kdim_patch = d.channels * d.patch * d.patch;
+  e->kv_pitch = ((e->S + 127) / 128) * 128;
+  e->bias_pitch = ((e->S + 7) / 8) * 8;
+  e->sms = prop.multiProcessorCount;
+  e->bn_h = pick_bn(e->H); e->bn_qkv = pick_bn(e->H) ; e->bn_i = pick_bn(e->I);
+  if ((2 * e->H) % e->bn_qkv) e->bn_qkv = 128;
+  try {
+    CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    allocate(e);
+  } catch (...) {
+    delete e;
+    throw;
+  }
+  *out = e;
+  return 0;
+  MMEE_CATCH
+}
+
+void mmee_destroy(mmee_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  delete e;
+}
+
+int mmee_set_weight(mmee_engine* e, const char* hf_name, const float* host_data, const int64_t* shape, int rank) {
+  MMEE_TRY
+  if (!e || !hf_name || !host_data) throw std::runtime_error("null argument");
+  size_t n = 1;
+  std::vector<int64_t> sh;
+  for (int i = 0; i < rank; ++i) { n *= static_cast<size_t>(shape[i]); sh.push_back(shape[i]); }
+  e->raw[hf_name].assign(host_data, host_data + n);
+  e->raw_shape[hf_name] = sh;
+  e->finalized = false;
+  return 0;
+  MMEE_CATCH
+}
+
+int mmee_set_bucket_lut(mmee_engine* e, int which, const uint8_t* lut, int n) {
+  MMEE_TRY
+  if (!e || !lut || n < 1) throw std::runtime_error("bad argument");
+  (which == 0 ? e->h_lut1 : e->h_lut2).assign(lut, lut + n);
+  e->finalized = false;
+  return 0;
+  MMEE_CATCH
+}
+
+int mmee_get_bucket_lut(mmee_engine* e, int which, uint8_t* lut_out, int capacity) {
+  MMEE_TRY
+  if (!e) throw std::runtime_error("null engine");
+  std::vector<uint8_t> t = which == 0 ? e->h_lut1 : e->h_lut2;
+  if (t.empty()) t = which == 0 ? default_lut(e->d.rel_bins, e->d.max_rel, 1024) : default_lut(e->d.rel2d_bins, e->d.max_rel2d, 1024);
+  const int n = static_cast<int>(t.size());
+  if (lut_out) memcpy(lut_out, t.data(), std::min(n, capacity));
+  return n;
+  MMEE_CATCH
+}
+
+int mmee_finalize_weights(mmee_engine* e) {
+  MMEE_TRY
+  if (!e) throw std::runtime_error("null engine");
+  finalize(e);
+  return 0;
+  MMEE_CATCH
+}
+
+int mmee_forward_device(mmee_engine* e, int B, const int64_t* input_ids, const int64_t* bbox,
+                        const int64_t* attention_mask, const float* pixel_values, const mmee_policy* policy,
+                        const mmee_outputs* out, void* cuda_stream) {
+  MMEE_TRY
+  if (!e) throw std::runtime_error("null engine");
+  CUDA_OK(cudaSetDevice(e->device));
+  cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->stream;
+  forward_device(e, B, input_ids, bbox, attention_mask, pixel_values, policy, out, st);
+  if (!cuda_stream) {
+    CUDA_OK(cudaStreamSynchronize(st));
+    collect_profile(e);
+  }
+  return 0;
+  MMEE_CATCH
+}
+
+int mmee_forward(mmee_engine* e, int B, const int64_t* input_ids, const int64_t* bbox, const int64_t* attention_mask,
+                 const float* pixel_values, const mmee_policy* policy, const mmee_outputs* out) {
+  MMEE_TRY
+  if (!e || !out) throw std::runtime_error("null argument");
+  if (B < 1 || B > e->max_batch) throw std::runtime_error("batch out of range");
+  CUDA_OK(cudaSetDevice(e->device));
+  const int T = e->T, K = e->K, E1 = e->d.n_exits + 1;
+  const size_t n_ids = static_cast<size_t>(B) * T, n_px = static_cast<size_t>(B) * e->d.channels * e->d.image * e->d.image;
+  if (!e->in_ids.p) {
+    const size_t mb = e->max_batch;
+    e->in_ids.alloc(mb * T); e->in_bbox.alloc(mb * T * 4); e->in_mask.alloc(mb * T);
+    e->in_px.alloc(mb * e->d.channels * e->d.image * e->d.image);
+  }
+  cudaStream_t st = e->stream;
+  CUDA_OK(cudaMemcpyAsync(e->in_ids.p, input_ids, n_ids * 8, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->in_bbox.p, bbox, n_ids * 32, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->in_mask.p, attention_mask, n_ids * 8, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->in_px.p, pixel_values, n_px * 4, cudaMemcpyHostToDevice, st));
+  // run with outputs in the engine's own device buffers, then copy what was asked for to the host
+  mmee_outputs dv{};
+  dv.logits = e->out_logits.p;       // forward_device copies onto itself harmlessly for these two: use scratch instead
+  DevBuf<float> d_logits, d_crit;
+  DevBuf<int32_t> d_exit;
+  DevBuf<int64_t> d_hist;
+  d_logits.alloc(static_cast<size_t>(B) * K); d_crit.alloc(B); d_exit.alloc(B); d_hist.alloc(E1);
+  dv.logits = d_logits.p; dv.exit_index = d_exit.p; dv.criterion = d_crit.p; dv.exit_hist = reinterpret_cast<int64_t*>(d_hist.p);
+  DevBuf<float> d_all, d_allh, d_allc;
+  if (out->all_exit_logits) { d_all.alloc(static_cast<size_t>(E1) * B * K); dv.all_exit_logits = d_all.p; }
+  if (out->all_head_logits) { d_allh.alloc(static_cast<size_t>(E1) * B * K); dv.all_head_logits = d_allh.p; }
+  if (out->all_criteria) { d_allc.alloc(static_cast<size_t>(E1) * B); dv.all_criteria = d_allc.p; }
+  forward_device(e, B, e->in_ids.p, e->in_bbox.p, e->in_mask.p, e->in_px.p, policy, &dv, st);
+  CUDA_OK(cudaMemcpyAsync(out->logits, dv.logits, static_cast<size_t>(B) * K * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(out->exit_index, dv.exit_index, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, st));
+  if (out->criterion) CUDA_OK(cudaMemcpyAsync(out->criterion, dv.criterion, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, st));
+  if (out->exit_hist) CUDA_OK(cudaMemcpyAsync(out->exit_hist, dv.exit_hist, static_cast<size_t>(E1) * 8, cudaMemcpyDeviceToHost, st));
+  if (out->all_exit_logits) CUDA_OK(cudaMemcpyAsync(out->all_exit_logits, dv.all_exit_logits, static_cast<size_t>(E1) * B * K * 4, cudaMemcpyDeviceToHost, st));
+  if (out->all_head_logits) CUDA_OK(cudaMemcpyAsync(out->all_head_logits, dv.all_head_logits, static_cast<size_t>(E1) * B * K * 4, cudaMemcpyDeviceToHost, st));
+  if (out->all_criteria) CUDA_OK(cudaMemcpyAsync(out->all_criteria, dv.all_criteria, static_cast<size_t>(E1) * B * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  collect_profile(e);
+  return 0;
+  MMEE_CATCH
+}
+
+int64_t mmee_last_launch_count(mmee_engine* e) { return e ? e->launches : -1; }
+
+int mmee_collect_profile(mmee_engine* e) {
+  MMEE_TRY
+  if (!e) throw std::runtime_error("null engine");
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  collect_profile(e);
+  return 0;
+  MMEE_CATCH
+}
+
+int64_t mmee_debug_read(mmee_engine* e, const char* name, void* host_dst, int64_t capacity_bytes) {
+  try {
+    if (!e || !name || !host_dst) throw std::runtime_error("null argument");
+    CUDA_OK(cudaSetDevice(e->device));
+    CUDA_OK(cudaDeviceSynchronize());
+    const std::string n(name);
+    const void* src = nullptr;
+    size_t bytes = 0;
+    if (n == "X0") { src = e->X[0].p; bytes = e->X[0].n * 2; }
+    else if (n == "X1") { src = e->X[1].p; bytes = e->X[1].n * 2; }
+    else if (n == "QK") { src = e->QK.p; bytes = e->QK.n * 2; }
+    else if (n == "VT") { src = e->VT.p; bytes = e->VT.n * 2; }
+    else if (n == "CTX") { src = e->CTX.p; bytes = e->CTX.n * 2; }
+    else if (n == "A1") { src = e->A1.p; bytes = e->A1.n * 2; }
+    else if (n == "MID") { src = e->MID.p; bytes = e->MID.n * 2; }
+    else if (n == "Y") { src = e->Y.p; bytes = e->Y.n * 4; }
+    else if (n == "VIS") { src = e->VIS.p; bytes = e->VIS.n * 4; }
+    else if (n == "POOL") { src = e->POOL.p; bytes = e->POOL.n * 4; }
+    else if (n == "BIAS") { src = e->BIAS.p; bytes = e->BIAS.n * 2; }
+    else throw std::runtime_error("unknown buffer " + n);
+    if (static_cast<int64_t>(bytes) > capacity_bytes) bytes = static_cast<size_t>(capacity_bytes);
+    CUDA_OK(cudaMemcpy(host_dst, src, bytes, cudaMemcpyDeviceToHost));
+    return static_cast<int64_t>(bytes);
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+
+int mmee_set_profiling(mmee_engine* e, int on) {
+  if (!e) return -1;
+  e->profiling = on != 0;
+  return 0;
+}
+
+double mmee_last_stage_ms(mmee_engine* e, const char* stage) {
+  if (!e || !stage) return -1.0;
+  auto it = e->stage_ms.find(stage);
+  return it == e->stage_ms.end() ? 0.0 : it->second;
+}
+
+}  // extern "C"

@@ -1,0 +1,355 @@
+// LayerNorm (+ survivor compaction), attention-bias build, fused exit head / criterion / threshold /
+// prefix-sum compaction kernels.
+//
+//   ln_rows_kernel   : X[dst] = LN(Y[src]) ; dst slot s' <- src slot slot_src[s'] (compaction is free: the
+//                      post-LN write goes straight to the survivor's new slot).  HF:300-304, 509-513.
+//   bias_build_kernel: (rel_pos + rel_2d_pos)/sqrt(d) + key mask, once per forward, reused by every layer
+//                      (EE/models/LayoutLMv3.py:170-179; HF:393-458; mask HF:270-272).
+//   exit_head_kernel : CLS row -> [LN] -> dense/tanh/out_proj (EE/models/LayoutLMv3.py:86-93, 226-227; gate mode
+//                      also classifier(CLS) :768) -> logits/T -> max-softmax | entropy (EE_modules.py:149-160)
+//                      -> strict threshold test (EE_modules.py:139-143, policy.py:33).
+//   compact_kernel   : block prefix-sum over the fire flags -> survivor list for the next layer, results of
+//                      leaving documents scattered to their original document index; no host round-trip.
+#pragma once
+#include "embed.cuh"
+#include "ptx.cuh"
+
+namespace mmee {
+
+// one warp per destination row; rows >= *m_dst_dev are skipped.
+template <int NV>
+__global__ void ln_rows_kernel(const float* __restrict__ Y, __nv_bfloat16* __restrict__ X,
+                               const float* __restrict__ w, const float* __restrict__ b, float eps, int H, int seq,
+                               const int* __restrict__ m_dst_dev, const int* __restrict__ slot_src) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= *m_dst_dev) return;
+  const int lane = threadIdx.x & 31;
+  size_t src_row = row;
+  if (slot_src) {
+    const int s = row / seq;
+    src_row = static_cast<size_t>(slot_src[s]) * seq + (row - s * seq);
+  }
+  const float* y = Y + src_row * H;
+  float v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = (c < H) ? y[c] : 0.f;
+  }
+  warp_layernorm<NV>(v, H, w, b, eps, lane);
+  __nv_bfloat16* out = X + static_cast<size_t>(row) * H;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H) out[c] = __float2bfloat16_rn(v[i]);
+  }
+}
+
+// ------------------------------------------------------------------ attention bias
+struct BiasArgs {
+  const int64_t* bbox;       // [B, n_text, 4]
+  const int64_t* mask;       // [B, n_text] (1 = real token)
+  const int* vis_bbox;       // [n_vis, 4]
+  const float* w1d;          // [heads, bins1]   (rel_pos_bias.weight)
+  const float* wx;           // [heads, bins2]
+  const float* wy;           // [heads, bins2]
+  const uint8_t* lut1;       // |rel| -> bucket offset, 1-D   (size lut1_n)
+  const uint8_t* lut2;       // 2-D
+  int lut1_n, lut2_n;
+  int bins1, bins2;          // rel_pos_bins, rel_2d_pos_bins
+  int heads, n_text, seq, pitch;
+  float scale;               // 1/sqrt(d)
+  __half* out;               // [B][heads][seq][pitch]
+};
+
+// grid (ceil(pitch/128), seq, B); thread = one key column j of query row i; loops over heads.
+__global__ void bias_build_kernel(BiasArgs a) {
+  extern __shared__ float s_tab[];       // w1d | wx | wy
+  const int n1 = a.heads * a.bins1, n2 = a.heads * a.bins2;
+  for (int i = threadIdx.x; i < n1; i += blockDim.x) s_tab[i] = a.w1d[i];
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) { s_tab[n1 + i] = a.wx[i]; s_tab[n1 + n2 + i] = a.wy[i]; }
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  const int doc = blockIdx.z;
+  if (j >= a.pitch) return;
+  __half* out = a.out + ((static_cast<size_t>(doc) * a.heads) * a.seq + i) * a.pitch + j;
+  const size_t head_stride = static_cast<size_t>(a.seq) * a.pitch;
+  bool masked = (j >= a.seq);
+  if (!masked && j < a.n_text) masked = (a.mask[static_cast<size_t>(doc) * a.n_text + j] == 0);
+  if (masked) {
+    for (int h = 0; h < a.heads; ++h) out[h * head_stride] = __ushort_as_half(0xFC00);   // -inf
+    return;
+  }
+  auto coords = [&](int t, int& pos, int& x0, int& y1) {
+    if (t < a.n_text) {
+      const int64_t* bb = a.bbox + (static_cast<size_t>(doc) * a.n_text + t) * 4;
+      pos = t; x0 = static_cast<int>(bb[0]); y1 = static_cast<int>(bb[3]);
+    } else {
+      const int p = t - a.n_text;
+      pos = p; x0 = a.vis_bbox[p * 4 + 0]; y1 = a.vis_bbox[p * 4 + 3];
+    }
+  };
+  int pi, xi, yi, pj, xj, yj;
+  coords(i, pi, xi, yi);
+  coords(j, pj, xj, yj);
+  auto bucket = [](int rel, const uint8_t* lut, int lut_n, int bins) {
+    const int n = min(abs(rel), lut_n - 1);
+    return (rel > 0 ? (bins >> 1) : 0) + lut[n];
+  };
+  const int b1 = bucket(pj - pi, a.lut1, a.lut1_n, a.bins1);
+  const int bx = bucket(xj - xi, a.lut2, a.lut2_n, a.bins2);
+  const int by = bucket(yj - yi, a.lut2, a.lut2_n, a.bins2);
+  for (int h = 0; h < a.heads; ++h) {
+    // reference association: rel_pos + (rel_x + rel_y), then / sqrt(d)
+    const float v = (s_tab[h * a.bins1 + b1] + (s_tab[n1 + h * a.bins2 + bx] + s_tab[n1 + n2 + h * a.bins2 + by])) * a.scale;
+    out[h * head_stride] = __float2half_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------ exit head
+struct HeadWeights {
+  const float* dense_w;   // [H, H] or nullptr (1-layer head)
+  const float* dense_b;   // [H]
+  const float* out_w;     // [n_out, H]
+  const float* out_b;     // [n_out]
+  int n_out;
+};
+
+struct ExitArgs {
+  // input rows: either fp32 pre-LN rows (row = slot*row_stride) normalised here, or an fp32 [n, H] matrix used as is
+  const float* rows;
+  size_t row_stride;        // in floats
+  const int* slot_src;      // optional: row of slot s lives at slot_src[s] (rows not yet compacted)
+  const float* ln_w;        // nullptr -> no LayerNorm
+  const float* ln_b;
+  float ln_eps;
+  int H;
+  HeadWeights head;         // ramp: class logits; gate: 2-way gate logits
+  HeadWeights cls;          // gate mode: final classifier applied to the same row ("gated logits"); else unused
+  int gate_mode;
+  int n_labels;
+  int criterion;            // 0 max_confidence (fire if >), 1 entropy (fire if <)
+  float inv_temp;           // 1/T_e
+  float threshold;
+  int force;                // final classifier: always fires
+  const int* n_active_dev;
+  // per-slot outputs
+  float* slot_logits;       // [n, n_labels]  class logits of this exit
+  float* slot_head;         // [n, head.n_out] raw head output (gate logits in gate mode)
+  float* slot_crit;         // [n]
+  int* slot_fire;           // [n]
+};
+
+constexpr int EXIT_DOCS_PER_CTA = 4;
+constexpr int EXIT_THREADS = 256;
+constexpr int EXIT_MAX_H = 1024;
+constexpr int EXIT_MAX_OUT = 32;
+
+// y[d][j] = act(sum_k W[j,k] * x[d][k] + b[j]) for the CTA's docs; one warp per output feature j.
+template <bool TANH>
+__device__ __forceinline__ void head_linear(const float* __restrict__ W, const float* __restrict__ b, int n_out, int H,
+                                            const float (*x)[EXIT_MAX_H], float* y, int y_stride, int nd) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < n_out; j += nw) {
+    float acc[EXIT_DOCS_PER_CTA] = {0.f, 0.f, 0.f, 0.f};
+    const float* wr = W + static_cast<size_t>(j) * H;
+    for (int k = lane * 4; k < H; k += 128) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
+#pragma unroll
+      for (int d = 0; d < EXIT_DOCS_PER_CTA; ++d) {
+        const float4 x4 = *reinterpret_cast<const float4*>(&x[d][k]);
+        acc[d] = fmaf(w4.x, x4.x, acc[d]);
+        acc[d] = fmaf(w4.y, x4.y, acc[d]);
+        acc[d] = fmaf(w4.z, x4.z, acc[d]);
+        acc[d] = fmaf(w4.w, x4.w, acc[d]);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < EXIT_DOCS_PER_CTA; ++d) acc[d] = warp_sum(acc[d]);
+    if (lane == 0) {
+      const float bj = __ldg(b + j);
+      for (int d = 0; d < nd; ++d) y[d * y_stride + j] = TANH ? tanhf(acc[d] + bj) : (acc[d] + bj);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(EXIT_THREADS) exit_head_kernel(ExitArgs a) {
+  __shared__ __align__(16) float s_x[EXIT_DOCS_PER_CTA][EXIT_MAX_H];
+  __shared__ __align__(16) float s_t[EXIT_DOCS_PER_CTA][EXIT_MAX_H];
+  __shared__ float s_head[EXIT_DOCS_PER_CTA][EXIT_MAX_OUT];
+  __shared__ float s_cls[EXIT_DOCS_PER_CTA][EXIT_MAX_OUT];
+  const int n_active = *a.n_active_dev;
+  const int slot0 = blockIdx.x * EXIT_DOCS_PER_CTA;
+  if (slot0 >= n_active) return;
+  const int nd = min(EXIT_DOCS_PER_CTA, n_active - slot0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = a.H;
+
+  // 1. load (+ LayerNorm) the rows: warp d handles doc d
+  if (warp < EXIT_DOCS_PER_CTA) {
+    const int d = warp;
+    if (d < nd) {
+      const int src_slot = a.slot_src ? a.slot_src[slot0 + d] : (slot0 + d);
+      const float* r = a.rows + static_cast<size_t>(src_slot) * a.row_stride;
+      float s = 0.f;
+      for (int c = lane; c < H; c += 32) { const float v = r[c]; s_x[d][c] = v; s += v; }
+      if (a.ln_w) {
+        const float mean = warp_sum(s) / H;
+        float q = 0.f;
+        for (int c = lane; c < H; c += 32) { const float dv = s_x[d][c] - mean; q += dv * dv; }
+        const float rstd = rsqrtf(warp_sum(q) / H + a.ln_eps);
+        for (int c = lane; c < H; c += 32) s_x[d][c] = (s_x[d][c] - mean) * rstd * __ldg(a.ln_w + c) + __ldg(a.ln_b + c);
+      }
+    } else {
+      for (int c = lane; c < H; c += 32) s_x[d][c] = 0.f;
+    }
+  }
+  __syncthreads();
+
+  // 2. exit head (ramp logits or gate logits)
+  if (a.head.dense_w) {
+    head_linear<true>(a.head.dense_w, a.head.dense_b, H, H, s_x, &s_t[0][0], EXIT_MAX_H, nd);
+    __syncthreads();
+    head_linear<false>(a.head.out_w, a.head.out_b, a.head.n_out, H, s_t, &s_head[0][0], EXIT_MAX_OUT, nd);
+  } else {
+    head_linear<false>(a.head.out_w, a.head.out_b, a.head.n_out, H, s_x, &s_head[0][0], EXIT_MAX_OUT, nd);
+  }
+  __syncthreads();
+  // 3. gate mode: class logits come from the final classifier on the same row
+  if (a.gate_mode) {
+    if (a.cls.dense_w) {
+      head_linear<true>(a.cls.dense_w, a.cls.dense_b, H, H, s_x, &s_t[0][0], EXIT_MAX_H, nd);
+      __syncthreads();
+      head_linear<false>(a.cls.out_w, a.cls.out_b, a.cls.n_out, H, s_t, &s_cls[0][0], EXIT_MAX_OUT, nd);
+    } else {
+      head_linear<false>(a.cls.out_w, a.cls.out_b, a.cls.n_out, H, s_x, &s_cls[0][0], EXIT_MAX_OUT, nd);
+    }
+    __syncthreads();
+  }
+
+  // 4. criterion + threshold: warp d, lane k = label k (n_labels <= 32)
+  if (warp < nd) {
+    const int d = warp;
+    const int slot = slot0 + d;
+    const float (*lg)[EXIT_MAX_OUT] = a.gate_mode ? s_cls : s_head;
+    const int K = a.n_labels;
+    const float raw = (lane < K) ? lg[d][lane] : 0.f;
+    if (lane < K) a.slot_logits[static_cast<size_t>(slot) * K + lane] = raw;
+    if (lane < a.head.n_out) a.slot_head[static_cast<size_t>(slot) * a.head.n_out + lane] = s_head[d][lane];
+    const float z = raw * a.inv_temp;
+    float crit;
+    if (a.criterion == 0) {
+      // max softmax = 1 / sum_k exp(z_k - z_max)
+      const float zmax = warp_max(lane < K ? z : -INFINITY);
+      const float e = (lane < K) ? expf(z - zmax) : 0.f;
+      crit = 1.0f / warp_sum(e);
+    } else {
+      // reference form (un-stabilised in the reference): log(sum e^z) - sum z e^z / sum e^z.
+      // Evaluated max-shifted here: identical in exact arithmetic, finite for any T.
+      const float zmax = warp_max(lane < K ? z : -INFINITY);
+      const float e = (lane < K) ? expf(z - zmax) : 0.f;
+      const float A = warp_sum(e);
+      const float Bz = warp_sum((lane < K) ? (z - zmax) * e : 0.f);
+      crit = logf(A) - Bz / A;
+    }
+    if (lane == 0) {
+      a.slot_crit[slot] = crit;
+      const bool fire = a.force || (a.criterion == 0 ? (crit > a.threshold) : (crit < a.threshold));
+      a.slot_fire[slot] = fire ? 1 : 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ compaction
+struct CompactArgs {
+  const int* n_active_dev;     // current number of active slots
+  int* n_next_dev;             // out: survivors
+  int* m_next_dev;             // out: survivors * seq  (row count for the next layer's GEMMs)
+  int seq;
+  const int* slot_doc;         // [n] slot -> original document index
+  int* next_slot_doc;          // [n_next]
+  int* next_slot_src;          // [n_next] new slot -> old slot (row gather map for the LN that follows)
+  const int* slot_fire;
+  const float* slot_logits;    // [n, K]
+  const float* slot_head;      // [n, n_head]
+  const float* slot_crit;
+  int K, n_head;
+  int exit_index;              // e
+  int leave;                   // 1: firing documents leave (early-exit mode); 0: dense mode, everyone stays
+  // per-document outputs
+  float* out_logits;           // [B, K]
+  float* out_crit;             // [B]
+  int* out_exit;               // [B]  (-1 = undecided)
+  float* all_logits;           // [(E+1), B, K] or nullptr
+  float* all_head;             // [(E+1), B, n_head_max] or nullptr
+  float* all_crit;             // [(E+1), B] or nullptr
+  int B, n_head_max;
+  unsigned long long* hist;    // [E+1]
+};
+
+// single CTA of 1024 threads; handles any n via a chunked scan.
+__global__ void __launch_bounds__(1024) compact_kernel(CompactArgs a) {
+  __shared__ int s_warp[32];
+  __shared__ int s_total;
+  __shared__ int s_base;
+  __shared__ int s_fired;
+  const int n = *a.n_active_dev;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_base = 0; s_fired = 0; }
+  __syncthreads();
+  for (int start = 0; start < n; start += 1024) {
+    const int s = start + threadIdx.x;
+    const bool valid = s < n;
+    int doc = -1, fire = 0, first = 0;
+    if (valid) {
+      doc = a.slot_doc[s];
+      fire = a.slot_fire[s];
+      // record per-exit outputs for every active document
+      if (a.all_logits)
+        for (int k = 0; k < a.K; ++k)
+          a.all_logits[(static_cast<size_t>(a.exit_index) * a.B + doc) * a.K + k] = a.slot_logits[static_cast<size_t>(s) * a.K + k];
+      if (a.all_head)
+        for (int k = 0; k < a.n_head; ++k)
+          a.all_head[(static_cast<size_t>(a.exit_index) * a.B + doc) * a.n_head_max + k] = a.slot_head[static_cast<size_t>(s) * a.n_head + k];
+      if (a.all_crit) a.all_crit[static_cast<size_t>(a.exit_index) * a.B + doc] = a.slot_crit[s];
+      first = fire && (a.out_exit[doc] < 0);
+      if (first) {
+        a.out_exit[doc] = a.exit_index;
+        a.out_crit[doc] = a.slot_crit[s];
+        for (int k = 0; k < a.K; ++k) a.out_logits[static_cast<size_t>(doc) * a.K + k] = a.slot_logits[static_cast<size_t>(s) * a.K + k];
+      }
+    }
+    const int stay = valid && !(a.leave && fire);
+    // block-wide exclusive scan of `stay`
+    const unsigned ball = __ballot_sync(0xffffffffu, stay);
+    const int wprefix = __popc(ball & ((1u << lane) - 1));
+    const unsigned fball = __ballot_sync(0xffffffffu, first);
+    if (lane == 0) { s_warp[warp] = __popc(ball); if (fball) atomicAdd(&s_fired, __popc(fball)); }
+    __syncthreads();
+    if (warp == 0) {
+      const int v = s_warp[lane];
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      s_warp[lane] = incl - v;                 // exclusive per-warp offsets
+      if (lane == 31) s_total = incl;
+    }
+    __syncthreads();
+    if (stay) {
+      const int dst = s_base + s_warp[warp] + wprefix;
+      a.next_slot_doc[dst] = doc;
+      a.next_slot_src[dst] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += s_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *a.n_next_dev = s_base;
+    *a.m_next_dev = s_base * a.seq;
+    if (s_fired) atomicAdd(a.hist + a.exit_index, static_cast<unsigned long long>(s_fired));
+  }
+}
+
+}  // namespace mmee
