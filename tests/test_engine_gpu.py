@@ -1,0 +1,222 @@
+"""GPU parity tests (B200): the CUDA engine, called through the C ABI, against the golden vectors
+(outputs of the unmodified reference) and the oracle port / policy port on the same seeded inputs.
+
+Tolerances (north_star): logits within 1e-2 absolute (bf16 engine); predicted classes identical wherever
+the reference's top-2 logit gap exceeds 2x that tolerance; exit indices bit-exact for every document
+whose criterion margin to its threshold exceeds DELTA (stated per criterion below).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import ALL_CASES, load_case
+from mmee import synth
+from mmee.calibration import spread_temperatures, thresholds_for
+from mmee.config import ExitConfig, ModelDims
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-2          # bf16 engine, absolute
+DELTA_CONF = 2e-2         # decisive margin on calibrated max-softmax (logit error x 1/T amplification)
+DELTA_ENT = 6e-2          # decisive margin on calibrated entropy (nats)
+
+_models = {}
+
+
+def _engine(name, max_batch=8):
+    from mmee.model import B200EEForSequenceClassification
+
+    if name not in _models:
+        g, dims, ee, sd, docs = load_case(name)
+        _models[name] = (B200EEForSequenceClassification(dims, ee, sd, device=0, max_batch=max_batch), g, dims, ee, sd, docs)
+    return _models[name]
+
+
+def _cuda(docs):
+    return {k: v.cuda() for k, v in docs.items()}
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_dense_logits_match_reference_golden(name):
+    model, g, dims, ee, sd, docs = _engine(name)
+    out = model.forward(**_cuda(docs))
+    got = out.exit_logits.cpu().numpy()
+    ref = g["exit_logits"]
+    assert got.shape == ref.shape
+    err = np.abs(got - ref).max()
+    print(f"{name}: max|logits - reference| = {err:.3e}")
+    assert err <= LOGIT_TOL
+    # predicted classes identical wherever the reference's decision is not a numerical tie
+    srt = np.sort(ref, axis=-1)
+    decisive = (srt[..., -1] - srt[..., -2]) > 2 * LOGIT_TOL
+    assert (got.argmax(-1) == ref.argmax(-1))[decisive].all()
+    # raw head outputs (exit_states[j][0]) and the reference-shaped output object
+    n_head = g["head_logits"].shape[-1]
+    heads = torch.stack([s[0] for s in out.exit_states]).cpu().numpy()
+    assert heads.shape == g["head_logits"].shape
+    assert np.abs(heads - g["head_logits"]).max() <= LOGIT_TOL
+    assert len(out.exit_criteria) == ref.shape[0]
+    assert np.abs(torch.stack(out.exit_criteria).cpu().numpy() - g["criteria"]).max() <= 2e-2
+    assert np.abs(out.logits.cpu().numpy() - ref[-1]).max() <= LOGIT_TOL
+    if ee.encoder_layer_strategy == "gate":
+        assert n_head == 2 and len(out.gated_logits) == ref.shape[0] - 1
+        assert np.abs(torch.stack(out.gated_logits).cpu().numpy() - ref[:-1]).max() <= LOGIT_TOL
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_early_exit_matches_reference_policy(name):
+    """Exit indices vs the reference Policy results stored in the golden (calibrated logits, several thresholds)."""
+    model, g, dims, ee, sd, docs = _engine(name)
+    temps = g["temps"]
+    ref_cal = g["exit_logits"].astype(np.float64) / temps[:, None, None]
+    from oracle import policy_port
+
+    conf = policy_port.criterion(ref_cal, "max_confidence")
+    total = agree = 0
+    for thr in (0.1, 0.5, 0.7, 0.9):
+        res = model.infer(**_cuda(docs), exit_threshold=thr, temperatures=temps, criterion="max_confidence")
+        want = g[f"policy_cal_{thr}_exits"]
+        margin = np.abs(conf[:-1] - thr).min(axis=0) if conf.shape[0] > 1 else np.full(want.shape, 1.0)
+        decisive = margin > DELTA_CONF
+        assert (res.exits_store[decisive] == want[decisive]).all(), (thr, res.exits_store, want, margin)
+        total += want.size
+        agree += int((res.exits_store == want).sum())
+        # returned logits are those of the exit taken
+        same = res.exits_store == want
+        assert np.abs(res.predictions.numpy()[same] - g[f"policy_cal_{thr}_pred"][same] * temps[want[same]][:, None]
+                      ).max() <= LOGIT_TOL
+        assert res.exit_hist.sum() == want.size
+        assert abs(sum(res.exit_distribution.values()) - 1.0) < 1e-9
+    print(f"{name}: exit-layer agreement with the reference policy {agree}/{total}")
+
+
+@pytest.mark.parametrize("name", ["tiny_ramp_conf", "tiny_gate_ent", "base_gate_ent"])
+@pytest.mark.parametrize("criterion", ["max_confidence", "entropy"])
+def test_early_exit_equals_dense_posthoc(name, criterion):
+    """Real compaction == post-hoc policy on the engine's own dense logits, bit-exact (per-document
+    arithmetic does not depend on which slot a document occupies)."""
+    from oracle import policy_port
+
+    model, g, dims, ee, sd, docs = _engine(name)
+    dense = model.infer(**_cuda(docs), exit_threshold=2.0 if criterion == "max_confidence" else -1.0,
+                        criterion=criterion, early_exit=False, return_all=True)
+    all_logits = dense.all_exit_logits.cpu().numpy()
+    temps = spread_temperatures(all_logits, criterion)
+    for conf_thr in (0.3, 0.6, 0.8, 0.95):
+        thr = thresholds_for(criterion, conf_thr, dims.n_labels)
+        ee_res = model.infer(**_cuda(docs), exit_threshold=thr, temperatures=temps, criterion=criterion,
+                             return_all=True)
+        dn_res = model.infer(**_cuda(docs), exit_threshold=thr, temperatures=temps, criterion=criterion,
+                             early_exit=False, return_all=True)
+        assert np.array_equal(ee_res.exits_store, dn_res.exits_store)
+        assert torch.equal(ee_res.logits, dn_res.logits)
+        assert np.array_equal(ee_res.criteria, dn_res.criteria)
+        assert np.array_equal(ee_res.exit_hist, dn_res.exit_hist)
+        # exits a document reached carry identical logits; the ones it skipped are NaN
+        a, b = ee_res.all_exit_logits.cpu().numpy(), dn_res.all_exit_logits.cpu().numpy()
+        reached = np.arange(a.shape[0])[:, None] <= ee_res.exits_store[None, :]
+        assert np.array_equal(a[reached], b[reached])
+        assert np.isnan(a[~reached]).all()
+        # and both agree with the fp64 policy oracle applied to the engine's dense logits (outside the margin)
+        cal = policy_port.temperature_scale(all_logits, temps)
+        want, _, crit = policy_port.exit_policy_vectorised(cal, thr, criterion)
+        margin = np.abs(crit[:-1] - thr).min(axis=0)
+        decisive = margin > 1e-4
+        assert (ee_res.exits_store[decisive] == want[decisive]).all()
+
+
+def test_host_path_equals_device_path():
+    model, g, dims, ee, sd, docs = _engine("tiny_ramp_conf")
+    temps = g["temps"]
+    a = model.infer(**_cuda(docs), exit_threshold=0.5, temperatures=temps, return_all=True)
+    b = model.infer(**docs, exit_threshold=0.5, temperatures=temps, return_all=True)     # CPU tensors -> mmee_forward
+    assert not b.logits.is_cuda
+    assert np.array_equal(a.exits_store, b.exits_store)
+    assert torch.equal(a.logits.cpu(), b.logits)
+    assert np.array_equal(a.exit_hist, b.exit_hist)
+    o1 = model.forward(**_cuda(docs))
+    o2 = model.forward(**docs)
+    assert torch.equal(o1.exit_logits.cpu(), o2.exit_logits)
+
+
+def test_batch_composition_invariance():
+    """A document's result does not depend on its neighbours or its position in the batch."""
+    model, g, dims, ee, sd, docs = _engine("tiny_ramp_conf")
+    full = model.forward(**_cuda(docs)).exit_logits.cpu()
+    perm = torch.tensor([3, 0, 5, 1])
+    sub = {k: v[perm].cuda() for k, v in docs.items()}
+    part = model.forward(**sub).exit_logits.cpu()
+    assert torch.equal(part, full[:, perm])
+    one = {k: v[2:3].cuda() for k, v in docs.items()}
+    assert torch.equal(model.forward(**one).exit_logits.cpu(), full[:, 2:3])
+
+
+def test_edge_cases_thresholds():
+    model, g, dims, ee, sd, docs = _engine("tiny_ramp_conf")
+    n = docs["input_ids"].shape[0]
+    E1 = g["exit_logits"].shape[0]
+    # threshold that can never be exceeded (strict >): everything leaves at the final classifier
+    r = model.infer(**_cuda(docs), exit_threshold=1.0)
+    assert (r.exits_store == E1 - 1).all() and r.exit_hist[-1] == n
+    # threshold 0: max-softmax > 0 always -> everything leaves at exit 0 (no encoder layer runs)
+    r = model.infer(**_cuda(docs), exit_threshold=0.0)
+    assert (r.exits_store == 0).all() and r.exit_hist[0] == n
+    assert np.abs(r.predictions.numpy() - g["exit_logits"][0]).max() <= LOGIT_TOL
+    # per-exit thresholds: only exit 2 can fire
+    thr = [1.0] * (E1 - 1)
+    thr[2] = 0.0
+    r = model.infer(**_cuda(docs), exit_threshold=thr)
+    assert (r.exits_store == 2).all()
+    # batch of one document, fully padded text except <s> </s>
+    d1 = synth.make_docs(dims, 1, seed=9)
+    d1["input_ids"][0, 2:] = dims.pad_id
+    d1["input_ids"][0, 1] = 2
+    d1["attention_mask"][0, 2:] = 0
+    d1["bbox"][0] = 0
+    from oracle import port
+
+    want = port.forward(sd, dims, ee, d1)["exit_logits"].numpy()
+    got = model.forward(**_cuda(d1)).exit_logits.cpu().numpy()
+    assert np.abs(got - want).max() <= LOGIT_TOL
+
+
+def test_bucket_lut_c_default_equals_torch():
+    """The C default |rel|->bucket table equals the table computed with the reference's torch ops."""
+    from mmee.model import B200EEForSequenceClassification, bucket_lut
+    from mmee import _lib
+    import ctypes as C
+
+    model, g, dims, *_ = _engine("tiny_ramp_conf")
+    assert np.array_equal(model.bucket_lut_in_use(0), bucket_lut(dims.rel_bins, dims.max_rel))
+    assert np.array_equal(model.bucket_lut_in_use(1), bucket_lut(dims.rel2d_bins, dims.max_rel2d))
+
+
+def test_full_size_batch_properties():
+    """BASELINE config-2 shape (base, B=256 per GPU is covered by bench; here B=32 full-length documents):
+    size-independent properties — early-exit == dense, histogram sums to B, duplicated documents give
+    bit-identical rows, exit depth is monotone in the threshold."""
+    dims = ModelDims.base()
+    ee = ExitConfig.from_dict(dict(exits=["text_visual_concat"] + list(range(1, 13)), encoder_layer_strategy="ramp",
+                                   inference_strategy="max_confidence"))
+    from mmee.model import B200EEForSequenceClassification
+
+    sd = synth.make_state_dict(dims, ee, seed=0)
+    model = B200EEForSequenceClassification(dims, ee, sd, device=0, max_batch=32)
+    docs = synth.make_docs(dims, 16, seed=21, pad=False)
+    docs = {k: torch.cat([v, v]) for k, v in docs.items()}          # every document twice
+    dev = _cuda(docs)
+    dense = model.infer(**dev, exit_threshold=2.0, early_exit=False, return_all=True)
+    al = dense.all_exit_logits.cpu().numpy()
+    assert np.array_equal(al[:, :16], al[:, 16:])
+    assert np.isfinite(al).all()
+    temps = spread_temperatures(al, "max_confidence")
+    prev_mean = -1.0
+    for thr in (0.5, 0.7, 0.9, 0.99):
+        a = model.infer(**dev, exit_threshold=thr, temperatures=temps)
+        b = model.infer(**dev, exit_threshold=thr, temperatures=temps, early_exit=False)
+        assert np.array_equal(a.exits_store, b.exits_store) and torch.equal(a.logits, b.logits)
+        assert a.exit_hist.sum() == 32
+        assert np.array_equal(a.exits_store[:16], a.exits_store[16:])
+        assert a.exits_store.mean() >= prev_mean
+        prev_mean = a.exits_store.mean()
+    model.close()
