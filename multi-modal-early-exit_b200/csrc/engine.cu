@@ -146,7 +146,7 @@ struct mmee_engine {
 
   // activations
   DevBuf<__nv_bfloat16> X[2], QK, VT, CTX, A1, MID, PATCH;
-  DevBuf<float> Y, VIS, POOL;
+  DevBuf<float> Y, VIS, POOL, Z, T0, T1;
   DevBuf<__half> BIAS;
   DevBuf<int> posid;
   CUtensorMap t_x[2], t_qk, t_vt, t_bias, t_ctx, t_a1, t_mid, t_patch;
@@ -406,6 +406,9 @@ void allocate(mmee_engine* e) {
   e->PATCH.alloc(mp * e->kdim_patch, true);
   e->VIS.alloc(static_cast<size_t>(B) * e->n_vis * H, true);
   e->POOL.alloc(static_cast<size_t>(B) * H, true);
+  e->Z.alloc(static_cast<size_t>(B) * H, true);
+  e->T0.alloc(static_cast<size_t>(B) * H, true);
+  e->T1.alloc(static_cast<size_t>(B) * H, true);
   e->BIAS.alloc(static_cast<size_t>(B) * heads * S * e->bias_pitch + 64 * 1024, true);
   e->posid.alloc(static_cast<size_t>(B) * e->T);
 
@@ -453,7 +456,6 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   const int E = d.n_exits, E1 = E + 1;
   const bool leave = pol->mode == 1;
   const bool gate = d.head_kind == 1;
-  const int n_head = gate ? 2 : K;
   e->launches = 0;
   for (auto& x : e->ev) cudaEventDestroy(x.second);
   e->ev.clear();
@@ -519,29 +521,52 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
 
   auto run_exit = [&](const float* rows, size_t row_stride, const float* ln_w, const float* ln_b,
                       const HeadW& head, bool is_final, const int* rows_slot_src) {
-    ExitArgs xa{};
-    xa.rows = rows; xa.row_stride = row_stride; xa.ln_w = ln_w; xa.ln_b = ln_b; xa.ln_eps = d.ln_eps; xa.H = H;
-    xa.slot_src = rows_slot_src;
-    const bool use_cls = gate && !is_final;
+    const int* nact = e->n_dev.p + stage;
+    ExitRowsArgs ra{};
+    ra.rows = rows; ra.row_stride = row_stride; ra.slot_src = rows_slot_src; ra.ln_w = ln_w; ra.ln_b = ln_b;
+    ra.ln_eps = d.ln_eps; ra.H = H; ra.n_active_dev = nact; ra.Z = e->Z.p;
+    exit_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(ra);
+    e->launches++;
+    const bool use_cls = gate && !is_final;               // class logits = classifier(CLS_j) ("gated logits")
+    const bool need_head = !use_cls || want_all;          // the 2-way gate output is only an API output
+    ExitDenseArgs da{};
+    da.Z = e->Z.p; da.H = H; da.n_active_dev = nact;
+    int jobs = 0;
+    const float* in_head = e->Z.p;
+    const float* in_cls = e->Z.p;
+    if (need_head && head.two_layer) {
+      da.w[jobs] = head.dense_w.p; da.b[jobs] = head.dense_b.p; da.T[jobs] = e->T0.p; in_head = e->T0.p; ++jobs;
+    }
+    if (use_cls) {
+      da.w[jobs] = e->classifier.dense_w.p; da.b[jobs] = e->classifier.dense_b.p; da.T[jobs] = e->T1.p;
+      in_cls = e->T1.p; ++jobs;
+    }
+    if (jobs) {
+      exit_dense_kernel<<<dim3(H / EXD_FEATS, (B + EXD_DOCS - 1) / EXD_DOCS, jobs), 256, 0, st>>>(da);
+      e->launches++;
+    }
+    ExitOutArgs xa{};
+    xa.in_head = in_head; xa.in_cls = in_cls;
     xa.head = head.view();
+    if (!need_head) xa.head.out_w = nullptr;
     xa.cls = e->classifier.view();
     xa.gate_mode = use_cls ? 1 : 0;
-    xa.n_labels = K;
+    xa.H = H; xa.n_labels = K;
     xa.criterion = pol->criterion;
     const float Te = pol->temperatures ? pol->temperatures[exit_no] : 1.f;
     xa.inv_temp = 1.0f / Te;
     xa.threshold = is_final ? 0.f : pol->thresholds[exit_no];
     xa.force = is_final ? 1 : 0;
-    xa.n_active_dev = e->n_dev.p + stage;
+    xa.n_active_dev = nact;
     xa.slot_logits = e->slot_logits.p; xa.slot_head = e->slot_head.p; xa.slot_crit = e->slot_crit.p;
     xa.slot_fire = e->slot_fire.p;
-    exit_head_kernel<<<(B + EXIT_DOCS_PER_CTA - 1) / EXIT_DOCS_PER_CTA, EXIT_THREADS, 0, st>>>(xa);
+    exit_out_kernel<<<(B + 7) / 8, 256, 0, st>>>(xa);
     CompactArgs ca{};
     ca.n_active_dev = e->n_dev.p + stage; ca.n_next_dev = e->n_dev.p + stage + 1; ca.m_next_dev = e->m_dev.p + stage + 1;
     ca.seq = S; ca.slot_doc = e->slot_doc[sd].p; ca.next_slot_doc = e->slot_doc[sd ^ 1].p;
     ca.next_slot_src = e->slot_src.p; ca.slot_fire = e->slot_fire.p; ca.slot_logits = e->slot_logits.p;
     ca.slot_head = e->slot_head.p; ca.slot_crit = e->slot_crit.p; ca.K = K;
-    ca.n_head = head.n_out;
+    ca.n_head = need_head ? head.n_out : 0;
     ca.exit_index = exit_no; ca.leave = (leave || is_final) ? 1 : 0;
     ca.out_logits = e->out_logits.p; ca.out_crit = e->out_crit.p; ca.out_exit = e->out_exit.p;
     ca.all_logits = want_all ? e->all_logits.p : nullptr; ca.all_head = want_all ? e->all_head.p : nullptr;
@@ -583,7 +608,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
         CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
         configured = true;
       }
-      attention_kernel<<<dim3((S + ATT_BQ - 1) / ATT_BQ, heads, B), ATT_THREADS, AttSmem::DYN_BYTES, st>>>(
+      attention_kernel<<<e->sms, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(
           e->t_qk, e->t_vt, e->t_bias, aa);
       CUDA_OK(cudaGetLastError());
       e->launches++;

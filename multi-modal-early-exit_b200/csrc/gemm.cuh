@@ -4,8 +4,9 @@
 //   W  : nn.Linear weight, bf16 row-major [N, K]  (TMA, BLOCK_N x 64 boxes, SWIZZLE_128B)
 //   acc: fp32 in TMEM, 2 accumulator buffers of BLOCK_N columns (epilogue of tile i overlaps MMA of i+1)
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected lane),
-// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).  M (the surviving-token count) is read from
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected lane),
+// warps 2..9 = epilogue (TMEM lane quarter = warp % 4, column half = (warp-2)/4); each warp transposes its
+// 32x32 chunk through a private swizzled smem slab so global stores are row-contiguous (coalesced).  M (the surviving-token count) is read from
 // device memory so the grid never depends on a host round-trip: grid = #SMs, static round-robin tiles.
 //
 // Replaces the nn.Linear call sites of HF LayoutLMv3 used by the reference: query/key/value
@@ -20,7 +21,8 @@ namespace mmee {
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;                    // two warps per TMEM lane quarter (column halves)
+constexpr int GEMM_THREADS = 64 + GEMM_EPI_WARPS * 32;
 
 enum GemmEpilogue : int {
   EPI_BIAS_BF16 = 0,   // out_bf16[m, n] = acc + bias[n]
@@ -55,24 +57,27 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BIAS_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = BIAS_OFF + 2 * BLOCK_N * 4;
+  static constexpr int STG_OFF = STAGES * STAGE_BYTES;             // per-warp 32 x 128 B transpose staging
+  static constexpr int BAR_OFF = STG_OFF + GEMM_EPI_WARPS * 4096;
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;   // slack for manual 1024 B alignment
 };
 
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  // x * Phi(x) with erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): matches torch's exact GELU
-  // (activations.py "gelu" -> nn.functional.gelu) far inside bf16 output rounding.
+  // x * Phi(x), Phi(x) = 1 - 0.5*erfc(x/sqrt2), erfc by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7 before the
+  // approximate MUFU ops): matches torch's exact-erf GELU (activations.py "gelu" -> nn.functional.gelu) far
+  // inside the bf16 rounding of the output.  2 MUFU (rcp, ex2) + ~12 FMA-pipe ops.
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float e = poly * __expf(-z * z);          // 1 - erf(z)
-  const float phi = (x >= 0.f) ? (1.0f - 0.5f * e) : (0.5f * e);
+  float ex;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(z * z * -1.4426950408889634f));
+  const float half_erfc = 0.5f * poly * t * ex;                 // 0.5 * erfc(|x|/sqrt2)
+  const float phi = (x >= 0.f) ? (1.0f - half_erfc) : half_erfc;
   return x * phi;
 }
 
@@ -86,7 +91,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* s_bias = reinterpret_cast<float*>(smem + SM::BIAS_OFF);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
@@ -111,7 +115,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], GEMM_EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -172,73 +176,86 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps (2..5)
+    // ------------------------------------------------------------ epilogue warps (2..9)
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int ep_tid = threadIdx.x - 64;          // 0..127
+    const int half = (warp - 2) >> 2;             // which half of the tile's columns
+    uint8_t* stg = smem + SM::STG_OFF + (warp - 2) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_blocks) * GEMM_BLOCK_M;
       const int n0 = (tile % n_blocks) * BLOCK_N;
-      float* sb = s_bias + acc * BLOCK_N;
-      for (int i = ep_tid; i < BLOCK_N; i += 128) sb[i] = __ldg(args.bias + n0 + i);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-
+      if constexpr (EPI == EPI_RESID_F32) {
+        // pull the NEXT tile's residual slab (32 rows x BLOCK_N/2 bf16 of this warp) into L2 while this tile's
+        // MMAs are still running: the residual was written a layer ago and has long left the cache
+        const int nt = tile + gridDim.x;
+        if (nt < total_tiles) {
+          const int pr = (nt / n_blocks) * GEMM_BLOCK_M + quarter * 32 + lane;
+          if (pr < M) {
+            const __nv_bfloat16* pp = args.resid + static_cast<size_t>(pr) * args.N + (nt % n_blocks) * BLOCK_N +
+                                      half * (BLOCK_N / 2);
+#pragma unroll
+            for (int b = 0; b < BLOCK_N; b += 128)      // BLOCK_N/2 bf16 = BLOCK_N bytes per row
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(pp) + b));
+          }
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
+      const int row_base = m0 + quarter * 32;     // first row of this warp's 32-row slab
+      const int row = row_base + lane;
       const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
 
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
+      for (int c = half * (BLOCK_N / 2); c < (half + 1) * (BLOCK_N / 2); c += 32) {
+        const int n = n0 + c;
+        uint2 rs[8];
+        if constexpr (EPI == EPI_RESID_F32) {       // residual loads first: independent of the accumulator
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int grow = row_base + (lane >> 3) + 4 * i;
+            rs[i] = (grow < M) ? __ldg(reinterpret_cast<const uint2*>(args.resid + static_cast<size_t>(grow) * args.N + n + (lane & 7) * 4))
+                               : make_uint2(0u, 0u);
+          }
+        }
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
+        float bv[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + n) + q);
+          bv[q * 4 + 0] = b4.x; bv[q * 4 + 1] = b4.y; bv[q * 4 + 2] = b4.z; bv[q * 4 + 3] = b4.w;
+        }
         tmem_ld_wait();
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + sb[c + j];
-        const int n = n0 + c;
-        if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16) {
-          if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) +
-                                                  static_cast<size_t>(row) * args.ld_out + n);
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bv[j];
+
+        if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_QKV) {
+          bool transposed_v = false;
+          if constexpr (EPI == EPI_QKV) transposed_v = (n >= args.qk_cols);
+          if (!transposed_v) {
+            // bf16 row slab: 64 B per row; thread = row writes 4 x 16 B chunks (chunk ^ ((row>>1)&3): conflict-free)
+            __syncwarp();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float g[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                g[j] = (EPI == EPI_GELU_BF16) ? gelu_erf_fast(f[q * 8 + j]) : f[q * 8 + j];
-              }
-              dst[q] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
-                                  pack_bf16x2(g[6], g[7]));
+              for (int j = 0; j < 8; ++j) g[j] = (EPI == EPI_GELU_BF16) ? gelu_erf_fast(f[q * 8 + j]) : f[q * 8 + j];
+              *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
+                             pack_bf16x2(g[6], g[7]));
             }
-          }
-        } else if constexpr (EPI == EPI_RESID_F32) {
-          if (row_ok) {
-            const uint4* rs = reinterpret_cast<const uint4*>(args.resid + static_cast<size_t>(row) * args.N + n);
-            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out) +
-                                                    static_cast<size_t>(row) * args.ld_out + n);
+            __syncwarp();
+            // 4 lanes cover one row's 64 B; 8 rows per store instruction
+            __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(args.out);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 r = __ldg(rs + q);
-              const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y), r2 = unpack_bf16x2(r.z),
-                           r3 = unpack_bf16x2(r.w);
-              dst[2 * q] = make_float4(f[q * 8 + 0] + r0.x, f[q * 8 + 1] + r0.y, f[q * 8 + 2] + r1.x,
-                                       f[q * 8 + 3] + r1.y);
-              dst[2 * q + 1] = make_float4(f[q * 8 + 4] + r2.x, f[q * 8 + 5] + r2.y, f[q * 8 + 6] + r3.x,
-                                           f[q * 8 + 7] + r3.y);
-            }
-          }
-        } else if constexpr (EPI == EPI_QKV) {
-          if (n < args.qk_cols) {
-            if (row_ok) {
-              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) +
-                                                    static_cast<size_t>(row) * args.ld_out + n);
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                dst[q] = make_uint4(pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
-                                    pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
+            for (int i = 0; i < 4; ++i) {
+              const int r = (lane >> 2) + 8 * i, q = lane & 3;
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
+              if (row_base + r < M)
+                *reinterpret_cast<uint4*>(outp + static_cast<size_t>(row_base + r) * args.ld_out + n + q * 8) = val;
             }
           } else if (row_ok) {
             // V is stored transposed per (doc, head): vt[d][token] so that P*V takes a K-major B operand.
@@ -252,17 +269,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * args.kv_pitch] = __float2bfloat16_rn(f[j]);
           }
-        } else if constexpr (EPI == EPI_PATCH) {
-          if (row_ok) {
-            const int doc = row / args.n_patch;
-            const int p = row - doc * args.n_patch;
-            const float4* ps = reinterpret_cast<const float4*>(args.pos + static_cast<size_t>(1 + p) * args.N + n);
-            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out) +
-                (static_cast<size_t>(doc) * args.n_vis + 1 + p) * args.ld_out + n);
+        } else {
+          // fp32 row slab: 128 B per row; thread = row writes 8 x 16 B chunks (chunk ^ (row&7): conflict-free)
+          __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 pe = __ldg(ps + q);
-              dst[q] = make_float4(f[q * 4 + 0] + pe.x, f[q * 4 + 1] + pe.y, f[q * 4 + 2] + pe.z, f[q * 4 + 3] + pe.w);
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                make_float4(f[q * 4 + 0], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+          __syncwarp();
+          // 8 lanes cover one row's 128 B; 4 rows per store instruction; residual / pos-embed added here (coalesced)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = (lane >> 3) + 4 * i, q = lane & 7;
+            float4 val = *reinterpret_cast<const float4*>(stg + r * 128 + ((q ^ (r & 7)) << 4));
+            const int grow = row_base + r;
+            if (grow < M) {
+              if constexpr (EPI == EPI_RESID_F32) {
+                const float2 r0 = unpack_bf16x2(rs[i].x), r1 = unpack_bf16x2(rs[i].y);
+                val.x += r0.x; val.y += r0.y; val.z += r1.x; val.w += r1.y;
+                *reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(grow) * args.ld_out + n + q * 4) = val;
+              } else {   // EPI_PATCH
+                const int doc = grow / args.n_patch;
+                const int p = grow - doc * args.n_patch;
+                const float4 pe = __ldg(reinterpret_cast<const float4*>(args.pos + static_cast<size_t>(1 + p) * args.N + n + q * 4));
+                val.x += pe.x; val.y += pe.y; val.z += pe.z; val.w += pe.w;
+                *reinterpret_cast<float4*>(static_cast<float*>(args.out) +
+                    (static_cast<size_t>(doc) * args.n_vis + 1 + p) * args.ld_out + n + q * 4) = val;
+              }
             }
           }
         }

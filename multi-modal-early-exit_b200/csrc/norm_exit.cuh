@@ -116,148 +116,172 @@ struct HeadWeights {
   int n_out;
 };
 
-struct ExitArgs {
-  // input rows: either fp32 pre-LN rows (row = slot*row_stride) normalised here, or an fp32 [n, H] matrix used as is
-  const float* rows;
+// (1) gather the exit input rows of the active slots (+ LayerNorm): Z[slot][H] fp32.  One warp per slot.
+struct ExitRowsArgs {
+  const float* rows;        // fp32 rows; row of slot s starts at rows + src(s) * row_stride
   size_t row_stride;        // in floats
-  const int* slot_src;      // optional: row of slot s lives at slot_src[s] (rows not yet compacted)
-  const float* ln_w;        // nullptr -> no LayerNorm
+  const int* slot_src;      // optional: rows not yet compacted -> src(s) = slot_src[s]
+  const float* ln_w;        // nullptr -> no LayerNorm (mean-pooled embedding exit)
   const float* ln_b;
   float ln_eps;
   int H;
-  HeadWeights head;         // ramp: class logits; gate: 2-way gate logits
-  HeadWeights cls;          // gate mode: final classifier applied to the same row ("gated logits"); else unused
+  const int* n_active_dev;
+  float* Z;                 // [n, H]
+};
+
+__global__ void exit_rows_kernel(ExitRowsArgs a) {
+  const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (slot >= *a.n_active_dev) return;
+  const int lane = threadIdx.x & 31;
+  const int H = a.H;
+  const int src = a.slot_src ? a.slot_src[slot] : slot;
+  const float* r = a.rows + static_cast<size_t>(src) * a.row_stride;
+  float* z = a.Z + static_cast<size_t>(slot) * H;
+  if (!a.ln_w) {
+    for (int c = lane; c < H; c += 32) z[c] = r[c];
+    return;
+  }
+  float s = 0.f;
+  for (int c = lane; c < H; c += 32) s += r[c];
+  const float mean = warp_sum(s) / H;
+  float q = 0.f;
+  for (int c = lane; c < H; c += 32) { const float d = r[c] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) / H + a.ln_eps);
+  for (int c = lane; c < H; c += 32) z[c] = (r[c] - mean) * rstd * __ldg(a.ln_w + c) + __ldg(a.ln_b + c);
+}
+
+// (2) T[w][slot][j] = tanh(sum_k W_w[j,k] Z[slot][k] + b_w[j]) for up to two heads w (exit head, classifier).
+// fp32 SIMT tile: 32 slots x 64 features per CTA, K staged through shared memory in chunks of 32.
+struct ExitDenseArgs {
+  const float* Z;           // [n, H]
+  const float* w[2];        // [H, H] each
+  const float* b[2];
+  float* T[2];              // [n, H] each
+  int H;
+  const int* n_active_dev;
+};
+
+constexpr int EXD_DOCS = 32, EXD_FEATS = 64, EXD_K = 32;
+
+__global__ void __launch_bounds__(256) exit_dense_kernel(ExitDenseArgs a) {
+  __shared__ float sZ[EXD_DOCS][EXD_K + 1];
+  __shared__ float sW[EXD_FEATS][EXD_K + 1];
+  const int n = *a.n_active_dev;
+  const int d0 = blockIdx.y * EXD_DOCS;
+  if (d0 >= n) return;
+  const int f0 = blockIdx.x * EXD_FEATS;
+  const int which = blockIdx.z;
+  const float* __restrict__ W = a.w[which];
+  const int H = a.H;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // 4 features x 2 slots per thread
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (int k0 = 0; k0 < H; k0 += EXD_K) {
+    for (int i = threadIdx.x; i < EXD_DOCS * EXD_K; i += 256) {
+      const int d = i >> 5, k = i & 31;
+      sZ[d][k] = (d0 + d < n) ? a.Z[static_cast<size_t>(d0 + d) * H + k0 + k] : 0.f;
+    }
+    for (int i = threadIdx.x; i < EXD_FEATS * EXD_K; i += 256) {
+      const int f = i >> 5, k = i & 31;
+      sW[f][k] = __ldg(W + static_cast<size_t>(f0 + f) * H + k0 + k);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < EXD_K; ++k) {
+      const float z0 = sZ[ty * 2][k], z1 = sZ[ty * 2 + 1][k];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const float w = sW[tx * 4 + f][k];
+        acc[0][f] = fmaf(w, z0, acc[0][f]);
+        acc[1][f] = fmaf(w, z1, acc[1][f]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int dd = 0; dd < 2; ++dd) {
+    const int d = d0 + ty * 2 + dd;
+    if (d >= n) continue;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const int j = f0 + tx * 4 + f;
+      a.T[which][static_cast<size_t>(d) * H + j] = tanhf(acc[dd][f] + __ldg(a.b[which] + j));
+    }
+  }
+}
+
+// (3) out_proj + temperature + criterion + strict threshold test.  One warp per slot.
+struct ExitOutArgs {
+  const float* in_head;     // [n, H] input of the exit head's out_proj (tanh(dense) or Z for 1-layer heads)
+  const float* in_cls;      // [n, H] input of the classifier's out_proj (gate mode), else unused
+  HeadWeights head;         // ramp: class logits; gate: 2-way gate logits (skipped when head.out_w == nullptr)
+  HeadWeights cls;          // gate mode: the final classifier ("gated logits", EE/models/LayoutLMv3.py:768)
   int gate_mode;
-  int n_labels;
+  int H, n_labels;
   int criterion;            // 0 max_confidence (fire if >), 1 entropy (fire if <)
   float inv_temp;           // 1/T_e
   float threshold;
   int force;                // final classifier: always fires
   const int* n_active_dev;
-  // per-slot outputs
   float* slot_logits;       // [n, n_labels]  class logits of this exit
   float* slot_head;         // [n, head.n_out] raw head output (gate logits in gate mode)
   float* slot_crit;         // [n]
   int* slot_fire;           // [n]
 };
 
-constexpr int EXIT_DOCS_PER_CTA = 4;
-constexpr int EXIT_THREADS = 256;
-constexpr int EXIT_MAX_H = 1024;
-constexpr int EXIT_MAX_OUT = 32;
-
-// y[d][j] = act(sum_k W[j,k] * x[d][k] + b[j]) for the CTA's docs; one warp per output feature j.
-template <bool TANH>
-__device__ __forceinline__ void head_linear(const float* __restrict__ W, const float* __restrict__ b, int n_out, int H,
-                                            const float (*x)[EXIT_MAX_H], float* y, int y_stride, int nd) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int j = warp; j < n_out; j += nw) {
-    float acc[EXIT_DOCS_PER_CTA] = {0.f, 0.f, 0.f, 0.f};
-    const float* wr = W + static_cast<size_t>(j) * H;
-    for (int k = lane * 4; k < H; k += 128) {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
-#pragma unroll
-      for (int d = 0; d < EXIT_DOCS_PER_CTA; ++d) {
-        const float4 x4 = *reinterpret_cast<const float4*>(&x[d][k]);
-        acc[d] = fmaf(w4.x, x4.x, acc[d]);
-        acc[d] = fmaf(w4.y, x4.y, acc[d]);
-        acc[d] = fmaf(w4.z, x4.z, acc[d]);
-        acc[d] = fmaf(w4.w, x4.w, acc[d]);
-      }
-    }
-#pragma unroll
-    for (int d = 0; d < EXIT_DOCS_PER_CTA; ++d) acc[d] = warp_sum(acc[d]);
-    if (lane == 0) {
-      const float bj = __ldg(b + j);
-      for (int d = 0; d < nd; ++d) y[d * y_stride + j] = TANH ? tanhf(acc[d] + bj) : (acc[d] + bj);
-    }
+__device__ __forceinline__ float warp_dot(const float* __restrict__ w, const float* __restrict__ x, int H, int lane) {
+  float acc = 0.f;
+  for (int k = lane * 4; k < H; k += 128) {
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + k));
+    const float4 x4 = *reinterpret_cast<const float4*>(x + k);
+    acc = fmaf(w4.x, x4.x, acc);
+    acc = fmaf(w4.y, x4.y, acc);
+    acc = fmaf(w4.z, x4.z, acc);
+    acc = fmaf(w4.w, x4.w, acc);
   }
+  return warp_sum(acc);
 }
 
-__global__ void __launch_bounds__(EXIT_THREADS) exit_head_kernel(ExitArgs a) {
-  __shared__ __align__(16) float s_x[EXIT_DOCS_PER_CTA][EXIT_MAX_H];
-  __shared__ __align__(16) float s_t[EXIT_DOCS_PER_CTA][EXIT_MAX_H];
-  __shared__ float s_head[EXIT_DOCS_PER_CTA][EXIT_MAX_OUT];
-  __shared__ float s_cls[EXIT_DOCS_PER_CTA][EXIT_MAX_OUT];
-  const int n_active = *a.n_active_dev;
-  const int slot0 = blockIdx.x * EXIT_DOCS_PER_CTA;
-  if (slot0 >= n_active) return;
-  const int nd = min(EXIT_DOCS_PER_CTA, n_active - slot0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int H = a.H;
-
-  // 1. load (+ LayerNorm) the rows: warp d handles doc d
-  if (warp < EXIT_DOCS_PER_CTA) {
-    const int d = warp;
-    if (d < nd) {
-      const int src_slot = a.slot_src ? a.slot_src[slot0 + d] : (slot0 + d);
-      const float* r = a.rows + static_cast<size_t>(src_slot) * a.row_stride;
-      float s = 0.f;
-      for (int c = lane; c < H; c += 32) { const float v = r[c]; s_x[d][c] = v; s += v; }
-      if (a.ln_w) {
-        const float mean = warp_sum(s) / H;
-        float q = 0.f;
-        for (int c = lane; c < H; c += 32) { const float dv = s_x[d][c] - mean; q += dv * dv; }
-        const float rstd = rsqrtf(warp_sum(q) / H + a.ln_eps);
-        for (int c = lane; c < H; c += 32) s_x[d][c] = (s_x[d][c] - mean) * rstd * __ldg(a.ln_w + c) + __ldg(a.ln_b + c);
-      }
-    } else {
-      for (int c = lane; c < H; c += 32) s_x[d][c] = 0.f;
+__global__ void exit_out_kernel(ExitOutArgs a) {
+  const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (slot >= *a.n_active_dev) return;
+  const int lane = threadIdx.x & 31;
+  const int H = a.H, K = a.n_labels;
+  float head_val = 0.f;                 // lane j holds head logit j
+  if (a.head.out_w) {
+    const float* x = a.in_head + static_cast<size_t>(slot) * H;
+    for (int j = 0; j < a.head.n_out; ++j) {
+      const float v = warp_dot(a.head.out_w + static_cast<size_t>(j) * H, x, H, lane) + __ldg(a.head.out_b + j);
+      if (lane == j) head_val = v;
     }
+    if (lane < a.head.n_out) a.slot_head[static_cast<size_t>(slot) * a.head.n_out + lane] = head_val;
   }
-  __syncthreads();
-
-  // 2. exit head (ramp logits or gate logits)
-  if (a.head.dense_w) {
-    head_linear<true>(a.head.dense_w, a.head.dense_b, H, H, s_x, &s_t[0][0], EXIT_MAX_H, nd);
-    __syncthreads();
-    head_linear<false>(a.head.out_w, a.head.out_b, a.head.n_out, H, s_t, &s_head[0][0], EXIT_MAX_OUT, nd);
-  } else {
-    head_linear<false>(a.head.out_w, a.head.out_b, a.head.n_out, H, s_x, &s_head[0][0], EXIT_MAX_OUT, nd);
-  }
-  __syncthreads();
-  // 3. gate mode: class logits come from the final classifier on the same row
+  float raw = head_val;                 // class logit of lane k
   if (a.gate_mode) {
-    if (a.cls.dense_w) {
-      head_linear<true>(a.cls.dense_w, a.cls.dense_b, H, H, s_x, &s_t[0][0], EXIT_MAX_H, nd);
-      __syncthreads();
-      head_linear<false>(a.cls.out_w, a.cls.out_b, a.cls.n_out, H, s_t, &s_cls[0][0], EXIT_MAX_OUT, nd);
-    } else {
-      head_linear<false>(a.cls.out_w, a.cls.out_b, a.cls.n_out, H, s_x, &s_cls[0][0], EXIT_MAX_OUT, nd);
+    raw = 0.f;
+    const float* x = a.in_cls + static_cast<size_t>(slot) * H;
+    for (int j = 0; j < K; ++j) {
+      const float v = warp_dot(a.cls.out_w + static_cast<size_t>(j) * H, x, H, lane) + __ldg(a.cls.out_b + j);
+      if (lane == j) raw = v;
     }
-    __syncthreads();
   }
-
-  // 4. criterion + threshold: warp d, lane k = label k (n_labels <= 32)
-  if (warp < nd) {
-    const int d = warp;
-    const int slot = slot0 + d;
-    const float (*lg)[EXIT_MAX_OUT] = a.gate_mode ? s_cls : s_head;
-    const int K = a.n_labels;
-    const float raw = (lane < K) ? lg[d][lane] : 0.f;
-    if (lane < K) a.slot_logits[static_cast<size_t>(slot) * K + lane] = raw;
-    if (lane < a.head.n_out) a.slot_head[static_cast<size_t>(slot) * a.head.n_out + lane] = s_head[d][lane];
-    const float z = raw * a.inv_temp;
-    float crit;
-    if (a.criterion == 0) {
-      // max softmax = 1 / sum_k exp(z_k - z_max)
-      const float zmax = warp_max(lane < K ? z : -INFINITY);
-      const float e = (lane < K) ? expf(z - zmax) : 0.f;
-      crit = 1.0f / warp_sum(e);
-    } else {
-      // reference form (un-stabilised in the reference): log(sum e^z) - sum z e^z / sum e^z.
-      // Evaluated max-shifted here: identical in exact arithmetic, finite for any T.
-      const float zmax = warp_max(lane < K ? z : -INFINITY);
-      const float e = (lane < K) ? expf(z - zmax) : 0.f;
-      const float A = warp_sum(e);
-      const float Bz = warp_sum((lane < K) ? (z - zmax) * e : 0.f);
-      crit = logf(A) - Bz / A;
-    }
-    if (lane == 0) {
-      a.slot_crit[slot] = crit;
-      const bool fire = a.force || (a.criterion == 0 ? (crit > a.threshold) : (crit < a.threshold));
-      a.slot_fire[slot] = fire ? 1 : 0;
-    }
+  if (lane < K) a.slot_logits[static_cast<size_t>(slot) * K + lane] = raw;
+  const float z = raw * a.inv_temp;
+  const float zmax = warp_max(lane < K ? z : -INFINITY);
+  const float e = (lane < K) ? expf(z - zmax) : 0.f;
+  const float A = warp_sum(e);
+  float crit;
+  if (a.criterion == 0) {
+    crit = 1.0f / A;                    // max softmax = exp(0) / sum_k exp(z_k - z_max)
+  } else {
+    // entropy of EE/models/EE_modules.py:149-154, log(sum e^z) - sum z e^z / sum e^z, evaluated max-shifted
+    // (identical in exact arithmetic, finite for any temperature).
+    const float Bz = warp_sum((lane < K) ? (z - zmax) * e : 0.f);
+    crit = logf(A) - Bz / A;
+  }
+  if (lane == 0) {
+    a.slot_crit[slot] = crit;
+    const bool fire = a.force || (a.criterion == 0 ? (crit > a.threshold) : (crit < a.threshold));
+    a.slot_fire[slot] = fire ? 1 : 0;
   }
 }
 
