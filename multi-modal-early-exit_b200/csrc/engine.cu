@@ -147,7 +147,10 @@ struct mmee_engine {
   // activations
   DevBuf<__nv_bfloat16> X[2], QK, VT, CTX, A1, MID, PATCH;
   DevBuf<float> Y, VIS, POOL, Z, T0, T1;
-  DevBuf<__half> BIAS;
+  DevBuf<uint8_t> BIAS;
+  DevBuf<float> maskadd, bias_inv_scale, bias_scale2;
+  DevBuf<int> tileflag;
+  int n_kv_tiles = 6;
   DevBuf<int> posid;
   CUtensorMap t_x[2], t_qk, t_vt, t_bias, t_ctx, t_a1, t_mid, t_patch;
 
@@ -315,7 +318,30 @@ void finalize(mmee_engine* e) {
   upload_f32(e->wx, need(e, p + "encoder.rel_pos_x_bias.weight", {h, d.rel2d_bins}));
   upload_f32(e->wy, need(e, p + "encoder.rel_pos_y_bias.weight", {h, d.rel2d_bins}));
 
-  const float qscale = 1.0f / sqrtf(static_cast<float>(H / h));   // 0.125: exact power of two
+  // Q carries log2(e)/sqrt(d): the attention softmax runs in the log2 domain (exp2 without a per-element multiply)
+  const float qscale = 1.4426950408889634f / sqrtf(static_cast<float>(H / h));
+  {
+    // per-head linear scale of the uint8 attention bias: the largest |bias| the three tables can produce / 127
+    const auto& t1 = need(e, p + "encoder.rel_pos_bias.weight", {h, d.rel_bins});
+    const auto& tx = need(e, p + "encoder.rel_pos_x_bias.weight", {h, d.rel2d_bins});
+    const auto& ty = need(e, p + "encoder.rel_pos_y_bias.weight", {h, d.rel2d_bins});
+    std::vector<float> inv(h), sc2(h);
+    for (int hh = 0; hh < h; ++hh) {
+      float m1 = 0.f, mx = 0.f, my = 0.f;
+      for (int b = 0; b < d.rel_bins; ++b) m1 = fmaxf(m1, fabsf(t1[static_cast<size_t>(hh) * d.rel_bins + b]));
+      for (int b = 0; b < d.rel2d_bins; ++b) {
+        mx = fmaxf(mx, fabsf(tx[static_cast<size_t>(hh) * d.rel2d_bins + b]));
+        my = fmaxf(my, fabsf(ty[static_cast<size_t>(hh) * d.rel2d_bins + b]));
+      }
+      float bound = (m1 + mx + my) / sqrtf(static_cast<float>(H / h));
+      if (!(bound > 0.f)) bound = 1.f;
+      const float scale = bound / 127.0f;
+      inv[hh] = 1.0f / scale;
+      sc2[hh] = scale * 1.4426950408889634f;
+    }
+    upload_f32(e->bias_inv_scale, inv);
+    upload_f32(e->bias_scale2, sc2);
+  }
   e->layers.resize(e->L);
   for (int i = 0; i < e->L; ++i) {
     LayerW& w = e->layers[i];
@@ -416,8 +442,10 @@ void allocate(mmee_engine* e) {
   e->t_x[1] = make_tmap_2d_sw128(e->X[1].p, M, H, H, 128);
   e->t_qk = make_tmap_2d_sw128(e->QK.p, M, 2 * H, 2 * H, 128);
   e->t_vt = make_tmap_2d_sw128(e->VT.p, static_cast<uint64_t>(B) * heads * 64, e->kv_pitch, e->kv_pitch, 64);
-  e->t_bias = make_tmap_2d_sw128(e->BIAS.p, static_cast<uint64_t>(B) * heads * S, e->bias_pitch, e->bias_pitch, 128,
-                                 CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+  e->t_bias = make_tmap_2d_u8_sw128(e->BIAS.p, static_cast<uint64_t>(B) * heads * S, e->bias_pitch, e->bias_pitch, 128);
+  e->n_kv_tiles = (S + ATT_BKV - 1) / ATT_BKV;
+  e->maskadd.alloc(static_cast<size_t>(B) * e->kv_pitch, true);
+  e->tileflag.alloc(static_cast<size_t>(B) * e->n_kv_tiles, true);
   e->t_ctx = make_tmap_2d_sw128(e->CTX.p, M, H, H, 128);
   e->t_a1 = make_tmap_2d_sw128(e->A1.p, M, H, H, 128);
   e->t_mid = make_tmap_2d_sw128(e->MID.p, M, I, I, 128);
@@ -504,13 +532,16 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   }
   {
     BiasArgs ba;
-    ba.bbox = bbox; ba.mask = mask; ba.vis_bbox = e->vis_bbox.p; ba.w1d = e->w1d.p; ba.wx = e->wx.p; ba.wy = e->wy.p;
+    ba.bbox = bbox; ba.vis_bbox = e->vis_bbox.p; ba.w1d = e->w1d.p; ba.wx = e->wx.p; ba.wy = e->wy.p;
+    ba.inv_scale = e->bias_inv_scale.p;
     ba.lut1 = e->lut1.p; ba.lut2 = e->lut2.p; ba.lut1_n = static_cast<int>(e->lut1.n); ba.lut2_n = static_cast<int>(e->lut2.n);
     ba.bins1 = d.rel_bins; ba.bins2 = d.rel2d_bins; ba.heads = heads; ba.n_text = T; ba.seq = S; ba.pitch = e->bias_pitch;
     ba.scale = 1.0f / sqrtf(static_cast<float>(H / heads)); ba.out = e->BIAS.p;
-    const size_t smem = static_cast<size_t>(heads) * (d.rel_bins + 2 * d.rel2d_bins) * 4;
-    bias_build_kernel<<<dim3((e->bias_pitch + 127) / 128, S, B), 128, smem, st>>>(ba);
-    e->launches++;
+    const size_t smem = (static_cast<size_t>(heads) * (d.rel_bins + 2 * d.rel2d_bins) + heads) * 4;
+    const int threads = ((e->bias_pitch / 16 + 31) / 32) * 32;
+    bias_build_kernel<<<dim3(1, S, B), threads, smem, st>>>(ba);
+    keymask_kernel<<<B, e->kv_pitch, 0, st>>>(mask, e->maskadd.p, e->tileflag.p, T, S, e->kv_pitch, e->n_kv_tiles);
+    e->launches += 2;
   }
   mark(e, "embed", st);
 
@@ -601,7 +632,8 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
 
     AttArgs aa;
     aa.n_active_dev = e->n_dev.p + stage; aa.slot_doc = e->slot_doc[sd].p; aa.ctx = e->CTX.p; aa.H = H;
-    aa.heads = heads; aa.seq = S;
+    aa.heads = heads; aa.seq = S; aa.kv_pitch = e->kv_pitch; aa.tileflag = e->tileflag.p; aa.maskadd = e->maskadd.p;
+    aa.bias_scale2 = e->bias_scale2.p;
     {
       static bool configured = false;
       if (!configured) {
@@ -736,7 +768,8 @@ int mmee_create(const mmee_model_desc* desc, int device, int max_batch, mmee_eng
   e->S = e->T + e->n_vis;
   e->kdim_patch = d.channels * d.patch * d.patch;
   e->kv_pitch = ((e->S + 127) / 128) * 128;
-  e->bias_pitch = ((e->S + 7) / 8) * 8;
+  e->bias_pitch = ((e->S + 15) / 16) * 16;
+  if (e->kv_pitch > 1024) throw std::runtime_error("sequence too long for keymask_kernel");
   e->sms = prop.multiProcessorCount;
   e->bn_h = pick_bn(e->H); e->bn_qkv = pick_bn(e->H) ; e->bn_i = pick_bn(e->I);
   if ((2 * e->H) % e->bn_qkv) e->bn_qkv = 128;
@@ -890,7 +923,8 @@ int64_t mmee_debug_read(mmee_engine* e, const char* name, void* host_dst, int64_
     else if (n == "Y") { src = e->Y.p; bytes = e->Y.n * 4; }
     else if (n == "VIS") { src = e->VIS.p; bytes = e->VIS.n * 4; }
     else if (n == "POOL") { src = e->POOL.p; bytes = e->POOL.n * 4; }
-    else if (n == "BIAS") { src = e->BIAS.p; bytes = e->BIAS.n * 2; }
+    else if (n == "BIAS") { src = e->BIAS.p; bytes = e->BIAS.n; }
+    else if (n == "BIAS_SCALE2") { src = e->bias_scale2.p; bytes = e->bias_scale2.n * 4; }
     else throw std::runtime_error("unknown buffer " + n);
     if (static_cast<int64_t>(bytes) > capacity_bytes) bytes = static_cast<size_t>(capacity_bytes);
     CUDA_OK(cudaMemcpy(host_dst, src, bytes, cudaMemcpyDeviceToHost));

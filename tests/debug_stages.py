@@ -56,19 +56,18 @@ def main():
     X0 = bf16_to_f32(model.debug_read("X0", np.uint16, n * S * H)).reshape(n, S, H)
     rep("X0 text", X0[:, :T], x0[:, :T].numpy())
     rep("X0 visual", X0[:, T:], x0[:, T:].numpy())
-    pitch = ((S + 7) // 8) * 8
-    B_ = model.debug_read("BIAS", np.float16, n * h * S * pitch).reshape(n, h, S, pitch)
+    pitch = ((S + 15) // 16) * 16
+    LOG2E = 1.4426950408889634
+    B_ = model.debug_read("BIAS", np.uint8, n * h * S * pitch).reshape(n, h, S, pitch)
+    sc2 = model.debug_read("BIAS_SCALE2", np.float32, h)
     want_b = (bias / 8.0).numpy()
-    mk = (mask == 0).numpy()
-    got_b = B_[..., :S].astype(np.float32)
-    for b in range(n):
-        assert np.all(np.isneginf(got_b[b][:, :, mk[b]])), "masked keys must be -inf"
-    valid = ~np.broadcast_to(mk[:, None, None, :], got_b.shape)
-    rep("bias", np.where(valid, got_b, 0), np.where(valid, want_b, 0))
+    got_b = (B_[..., :S].astype(np.float32) - 128.0) * (sc2 / LOG2E)[None, :, None, None]
+    rep("bias(u8)", got_b, want_b)
+    print("bias quantisation step per head", sc2 / LOG2E)
     QK = bf16_to_f32(model.debug_read("QK", np.uint16, n * S * 2 * H)).reshape(n, S, 2 * H)
-    q = parts["q"].transpose(1, 2).reshape(n, S, H).numpy() / 8.0
+    q = parts["q"].transpose(1, 2).reshape(n, S, H).numpy() / 8.0 * LOG2E
     k = parts["k"].transpose(1, 2).reshape(n, S, H).numpy()
-    rep("Q/8", QK[..., :H], q)
+    rep("Q*log2e/8", QK[..., :H], q)
     rep("K", QK[..., H:], k)
     kvp = ((S + 127) // 128) * 128
     VT = bf16_to_f32(model.debug_read("VT", np.uint16, n * h * 64 * kvp)).reshape(n, h, 64, kvp)
