@@ -23,6 +23,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace mmee {
@@ -33,32 +35,37 @@ constexpr int ATT_THREADS = 64 + ATT_SM_WARPS * 32;
 constexpr int ATT_BQ = 128;    // query rows per CTA
 constexpr int ATT_BKV = 128;   // keys per tile
 constexpr int ATT_D = 64;
+constexpr int ATT_DV = 80;     // V^T rows fed to the PV MMA: 64 dims + a ones row (row sum of P) + 15 zero rows
 constexpr int ATT_STAGES = 3;
 
 struct AttSmem {
   static constexpr int Q_BYTES = ATT_BQ * ATT_D * 2;           // 16 KB
   static constexpr int K_BYTES = ATT_BKV * ATT_D * 2;          // 16 KB
-  static constexpr int V_BYTES = ATT_D * ATT_BKV * 2;          // 16 KB  (two [64 x 64] sub-tiles)
+  static constexpr int VSUB_BYTES = ATT_DV * 128;              // 10 KB: [80 rows x 64 keys] bf16, SW128
+  static constexpr int V_BYTES = 2 * VSUB_BYTES;               // 20 KB (keys 0-63 | keys 64-127)
   static constexpr int B_BYTES = ATT_BQ * ATT_BKV;             // 16 KB  uint8 [128 x 128]
   static constexpr int P_BYTES = ATT_BQ * ATT_BKV * 2;         // 32 KB  (two [128 x 64] bf16 sub-tiles)
-  static constexpr int KV_STAGE = K_BYTES + V_BYTES + B_BYTES; // 48 KB
+  static constexpr int KV_STAGE = K_BYTES + V_BYTES + B_BYTES; // 52 KB
+  static constexpr int TX_BYTES = K_BYTES + 2 * (ATT_D * 128) + B_BYTES;   // bytes TMA writes per stage
   static constexpr int Q_OFF = 0;                              // 2 Q buffers
   static constexpr int KV_OFF = Q_OFF + 2 * Q_BYTES;
   static constexpr int P_OFF = KV_OFF + ATT_STAGES * KV_STAGE;
-  static constexpr int X_OFF = P_OFF + P_BYTES;                // row-max [2][NSPLIT][128] + row-sum [NSPLIT][128]
-  static constexpr int BAR_OFF = X_OFF + 3 * ATT_NSPLIT * ATT_BQ * 4;
+  static constexpr int X_OFF = P_OFF + P_BYTES;                // partial row max exchange [2][NSPLIT][128] floats
+  static constexpr int BAR_OFF = X_OFF + 2 * ATT_NSPLIT * ATT_BQ * 4;
   static constexpr int N_BARS = 2 + 2 + 2 * ATT_STAGES + 2 + 2 + 2 + 2;
   static constexpr int TOTAL = BAR_OFF + N_BARS * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;
 };
 static_assert(AttSmem::DYN_BYTES <= 232448, "attention smem budget");
+static_assert(AttSmem::KV_STAGE % 1024 == 0 && AttSmem::VSUB_BYTES % 1024 == 0, "SW128 tiles need 1024 B alignment");
 
 struct AttArgs {
   const int* n_active_dev;
-  const int* slot_doc;         // slot -> original document (bias / mask are indexed by document)
-  const int* tileflag;         // [docs][n_kv] 0 none masked, 1 some, 2 all
+  const uint32_t* slot_meta;   // slot -> (doc << 16) | (partial_tiles << 8) | live_tiles   (see slot_meta_kernel)
   const float* maskadd;        // [docs][kv_pitch] 0 / -inf
   const float* bias_scale2;    // [heads] scale_h * log2(e)
+  int* err_flag;               // set to 1 if a score ran > 2^100 above its row reference (never in practice)
+  long long* trace;            // optional developer trace (clock64 stamps of CTA 0), nullptr = off
   __nv_bfloat16* ctx;          // [M, H]
   int H, heads, seq, kv_pitch;
 };
@@ -69,18 +76,70 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// byte K of w -> float(byte) - 128, exactly: PRMT builds 0x4B0000bb = 2^23 + bb, one FADD removes the offset.
+// byte K of w -> 2^23 + byte as a float (one PRMT); the caller's FADD removes the offset (and more, see below).
 template <int K>
-__device__ __forceinline__ float u8_to_centered_float(uint32_t w) {
-  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 | K)) - 8388736.0f;
+__device__ __forceinline__ float u8_magic(uint32_t w) {
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 | K));
 }
 
 // Position in this CTA's (item, key tile) sequence; fully masked tiles are skipped.  Every role walks the same
-// sequence so the pipeline counters stay in lock-step.
+// sequence so the pipeline counters stay in lock-step.  Passed by value so it lives in registers.
 struct AttCursor {
   int item, ii, j, slot, head, q0, doc, first_j, last_j;
+  uint32_t live, partial;      // bit j: tile j is processed / has padded keys inside the document
+  uint32_t nmeta;              // slot_meta of the NEXT item of this CTA, loaded one item ahead (latency hidden)
   bool valid;
 };
+
+__device__ __forceinline__ uint32_t att_item_meta(int item, int total_items, int n_qt, const AttArgs& args) {
+  return (item < total_items) ? __ldg(args.slot_meta + (item / n_qt) / args.heads) : 0u;
+}
+
+__device__ __forceinline__ AttCursor att_enter(int item, int ii, uint32_t meta, int total_items, int n_qt, int stride,
+                                               const AttArgs& args) {
+  AttCursor c;
+  c.item = item; c.ii = ii; c.valid = item < total_items;
+  c.j = 0; c.slot = 0; c.head = 0; c.q0 = 0; c.doc = 0; c.first_j = 0; c.last_j = 0; c.live = 1u; c.partial = 0u;
+  c.nmeta = 0u;
+  if (!c.valid) return c;
+  const int qt = item % n_qt;
+  const int sh = item / n_qt;
+  c.head = sh % args.heads;
+  c.slot = sh / args.heads;
+  c.q0 = qt * ATT_BQ;
+  c.doc = static_cast<int>(meta >> 16);
+  c.live = meta & 0xFFu;
+  c.partial = (meta >> 8) & 0xFFu;
+  c.first_j = __ffs(c.live) - 1;
+  c.last_j = 31 - __clz(c.live);
+  c.j = c.first_j;
+  c.nmeta = att_item_meta(item + stride, total_items, n_qt, args);
+  return c;
+}
+__device__ __forceinline__ AttCursor att_first(int total_items, int n_qt, int stride, const AttArgs& args) {
+  return att_enter(blockIdx.x, 0, att_item_meta(blockIdx.x, total_items, n_qt, args), total_items, n_qt, stride, args);
+}
+__device__ __forceinline__ AttCursor att_next(AttCursor c, int total_items, int n_qt, int stride, const AttArgs& args) {
+  const uint32_t rest = c.live & ~((2u << c.j) - 1u);
+  if (rest) { c.j = __ffs(rest) - 1; return c; }
+  return att_enter(c.item + stride, c.ii + 1, c.nmeta, total_items, n_qt, stride, args);
+}
+
+// slot_meta[slot] = (doc << 16) | (partial << 8) | live, from the per-document tile flags (keymask_kernel).
+__global__ void slot_meta_kernel(const int* __restrict__ slot_doc, const int* __restrict__ tileflag,
+                                 const int* __restrict__ n_active_dev, uint32_t* __restrict__ slot_meta, int n_kv) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= *n_active_dev) return;
+  const int doc = slot_doc[s];
+  uint32_t live = 0u, partial = 0u;
+  for (int j = 0; j < n_kv; ++j) {
+    const int f = tileflag[doc * n_kv + j];
+    if (f != 2) live |= 1u << j;
+    if (f == 1) partial |= 1u << j;
+  }
+  if (live == 0u) live = 1u;                     // degenerate: keep one tile so the row sum is defined
+  slot_meta[s] = (static_cast<uint32_t>(doc) << 16) | (partial << 8) | live;
+}
 
 // tmap_qk : bf16 [M_max, 2H]                    box [128 x 64]
 // tmap_vt : bf16 [docs*heads*64, kv_pitch]       box [64 x 64]
@@ -133,48 +192,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;            // 2 x 128 columns
-  const uint32_t tmem_O = tmem_base + 256;      // 2 x 64 columns
+  const uint32_t tmem_O = tmem_base + 256;      // 2 x 128-column slots, 80 used: 64 dims + row sum + padding
 
-  // ---- shared cursor logic
-  auto enter_item = [&](AttCursor& c) {                   // fills the item fields; valid = false when out of items
-    if (c.item >= total_items) { c.valid = false; return; }
-    const int qt = c.item % n_qt;
-    const int sh = c.item / n_qt;
-    c.head = sh % args.heads;
-    c.slot = sh / args.heads;
-    c.q0 = qt * ATT_BQ;
-    c.doc = args.slot_doc[c.slot];
-    c.first_j = -1;
-    c.last_j = -1;
-    for (int j = 0; j < n_kv; ++j)
-      if (args.tileflag[c.doc * n_kv + j] != 2) { if (c.first_j < 0) c.first_j = j; c.last_j = j; }
-    if (c.first_j < 0) { c.first_j = 0; c.last_j = 0; }   // degenerate: keep one tile so the row sum is defined
-    c.j = c.first_j;
-    c.valid = true;
-  };
-  auto start = [&](AttCursor& c) {
-    c.item = blockIdx.x;
-    c.ii = 0;
-    enter_item(c);
-  };
-  auto advance = [&](AttCursor& c) {                       // next valid (item, tile)
-    while (true) {
-      ++c.j;
-      if (c.j > c.last_j) {
-        c.item += gridDim.x;
-        ++c.ii;
-        enter_item(c);
-        return;
-      }
-      if (args.tileflag[c.doc * n_kv + c.j] != 2) return;
-    }
-  };
+  // constant rows 64..79 of every V^T sub-tile: row 64 = 1.0 (PV then also yields the row sum of P), rest 0
+  for (int i = threadIdx.x; i < ATT_STAGES * 2 * 128; i += blockDim.x) {
+    const int sub = i >> 7, chunk = i & 127;                 // 128 x 16 B chunks = rows 64..79 of one sub-tile
+    uint8_t* base = smem + AttSmem::KV_OFF + (sub >> 1) * AttSmem::KV_STAGE + AttSmem::K_BYTES +
+                    (sub & 1) * AttSmem::VSUB_BYTES + ATT_D * 128;
+    const uint32_t val = (chunk < 8) ? 0x3F803F80u : 0u;     // first 8 chunks = row 64
+    *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(val, val, val, val);
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  const int stride = gridDim.x;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      AttCursor c;
-      start(c);
+      AttCursor c = att_first(total_items, n_qt, stride, args);
       uint32_t t = 0;
       int loaded_ii = -1;
       while (c.valid) {
@@ -186,39 +222,40 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
           mbar_expect_tx(&q_full[qb], AttSmem::Q_BYTES);
           tma_load_2d(smem + AttSmem::Q_OFF + qb * AttSmem::Q_BYTES, &tmap_qk, &q_full[qb], c.head * ATT_D, row0 + c.q0);
           // pull the NEXT item's bias tiles (the only operand that comes from DRAM) into L2 ahead of time
-          const int nitem = c.item + gridDim.x;
+          const int nitem = c.item + stride;
           if (nitem < total_items) {
             const int nsh = nitem / n_qt;
-            const int ndoc = args.slot_doc[nsh / args.heads];
-            const int nrow = (ndoc * args.heads + nsh % args.heads) * S + (nitem % n_qt) * ATT_BQ;
+            const int nrow = (static_cast<int>(c.nmeta >> 16) * args.heads + nsh % args.heads) * S + (nitem % n_qt) * ATT_BQ;
             for (int j = 0; j < n_kv; ++j)
-              if (args.tileflag[ndoc * n_kv + j] != 2) tma_prefetch_2d(&tmap_bias, j * ATT_BKV, nrow);
+              if ((c.nmeta >> j) & 1u) tma_prefetch_2d(&tmap_bias, j * ATT_BKV, nrow);
           }
         }
         const int st = t % ATT_STAGES;
+        const bool trp = args.trace && blockIdx.x == 0 && t < 96;
+        if (trp) args.trace[2048 + t * 4 + 0] = clock64();
         mbar_wait(&kv_empty[st], ((t / ATT_STAGES) & 1) ^ 1);
+        if (trp) args.trace[2048 + t * 4 + 1] = clock64();
         uint8_t* sk = smem + AttSmem::KV_OFF + st * AttSmem::KV_STAGE;
         uint8_t* sv = sk + AttSmem::K_BYTES;
         uint8_t* sb = sv + AttSmem::V_BYTES;
         const int kv0 = c.j * ATT_BKV;
         const int vt_row = (c.slot * args.heads + c.head) * ATT_D;
         const int bias_row = (c.doc * args.heads + c.head) * S + c.q0;
-        mbar_expect_tx(&kv_full[st], AttSmem::KV_STAGE);
+        mbar_expect_tx(&kv_full[st], AttSmem::TX_BYTES);
         tma_load_2d(sk, &tmap_qk, &kv_full[st], args.H + c.head * ATT_D, row0 + kv0);
         tma_load_2d(sv, &tmap_vt, &kv_full[st], kv0, vt_row);
-        tma_load_2d(sv + AttSmem::V_BYTES / 2, &tmap_vt, &kv_full[st], kv0 + 64, vt_row);
+        tma_load_2d(sv + AttSmem::VSUB_BYTES, &tmap_vt, &kv_full[st], kv0 + 64, vt_row);
         tma_load_2d(sb, &tmap_bias, &kv_full[st], kv0, bias_row);
         ++t;
-        advance(c);
+        c = att_next(c, total_items, n_qt, stride, args);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, ATT_BKV);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, ATT_D);
-      AttCursor cs;                                   // cursor of the next S = Q K^T to issue (runs one tile ahead)
-      start(cs);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, ATT_DV);
+      AttCursor cs = att_first(total_items, n_qt, stride, args);   // next S = Q K^T to issue
       uint32_t ts = 0;
       auto issue_s = [&]() {
         const int st = ts % ATT_STAGES;
@@ -234,14 +271,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         umma_commit(&s_full[ts & 1]);
         if (cs.j == cs.last_j) umma_commit(&q_empty[qb]);   // last use of this item's Q
         ++ts;
-        advance(cs);
+        cs = att_next(cs, total_items, n_qt, stride, args);
       };
       if (cs.valid) issue_s();
-      for (uint32_t t = 0; t < ts; ++t) {               // ts grows while tiles remain
+      for (uint32_t t = 0; t < ts; ++t) {               // ts grows while tiles remain (S runs one tile ahead)
         if (cs.valid) issue_s();
         const int st = t % ATT_STAGES;
         const int b = t & 1;
+        const bool trm = args.trace && blockIdx.x == 0 && t < 96;
+        if (trm) args.trace[1024 + t * 4 + 0] = clock64();
         mbar_wait(&p_full[b], (t >> 1) & 1);
+        if (trm) args.trace[1024 + t * 4 + 1] = clock64();
         mbar_wait(&o_empty[b], ((t >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t sp = smem_u32(smem + AttSmem::P_OFF);
@@ -250,11 +290,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         for (int k = 0; k < ATT_BKV / 16; ++k) {
           const int hf = k >> 2, kk = k & 3;
           const uint64_t dp = umma_desc_sw128_kmajor(sp + hf * (AttSmem::P_BYTES / 2)) + 2 * kk;
-          const uint64_t dv = umma_desc_sw128_kmajor(sv + hf * (AttSmem::V_BYTES / 2)) + 2 * kk;
-          umma_bf16_ss(tmem_O + b * ATT_D, dp, dv, idesc_o, k ? 1u : 0u);
+          const uint64_t dv = umma_desc_sw128_kmajor(sv + hf * AttSmem::VSUB_BYTES) + 2 * kk;
+          umma_bf16_ss(tmem_O + b * 128, dp, dv, idesc_o, k ? 1u : 0u);
         }
         umma_commit(&o_full[b]);
         umma_commit(&kv_empty[st]);
+        if (trm) args.trace[1024 + t * 4 + 2] = clock64();
       }
     }
   } else {
@@ -264,33 +305,45 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
     const int r = quarter * 32 + lane;                        // query row within the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     float* xch = reinterpret_cast<float*>(smem + AttSmem::X_OFF);     // [buf][part][row]
-    float* xl = xch + 2 * ATT_NSPLIT * ATT_BQ;                        // [part][row] row-sum exchange
     constexpr int OD = ATT_D / ATT_NSPLIT;                            // 16
     constexpr int KC = ATT_BKV / ATT_NSPLIT;                          // 32
+    constexpr float C0 = 8388736.0f;                                  // 2^23 + 128
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     uint32_t t = 0;
-    AttCursor c;
-    start(c);
+    AttCursor c = att_first(total_items, n_qt, stride, args);
 
     while (c.valid) {
       const int row0 = c.slot * S;
       const int q0 = c.q0, head = c.head, doc = c.doc, my_ii = c.ii;
       const float scale2 = __ldg(args.bias_scale2 + head);
+      const float inv_scale2 = 1.0f / scale2;
       float o_acc[OD];
 #pragma unroll
       for (int i = 0; i < OD; ++i) o_acc[i] = 0.f;
-      float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+      float l_acc = 0.f;
+      // The row reference ("max") is kept as an integer multiple q_ref of the bias quantum scale2, so that for
+      // every tile after the first it rides for free in the FADD that removes the uint8->float magic offset:
+      //   s - ref = ((2^23 + u) - (2^23 + 128 + q_ref)) * scale2 + acc
+      float q_ref = 0.f, alpha_prev = 1.f;
       int nproc = 0;
 
-      auto accumulate = [&](uint32_t tt, float alpha) {         // O_reg = alpha * O_reg + O'[tt]
+      auto accumulate = [&](uint32_t tt, float alpha) {         // O_reg = (O_reg + O'[tt]) * alpha ; same for l
         const int b = tt & 1;
         mbar_wait(&o_full[b], (tt >> 1) & 1);
         tc_fence_after();
         uint32_t v[OD];
-        tmem_ld16(tmem_O + lane_addr + b * ATT_D + part * OD, v);
+        tmem_ld16(tmem_O + lane_addr + b * 128 + part * OD, v);
+        const uint32_t lsum = tmem_ld1(tmem_O + lane_addr + b * 128 + ATT_D);
         tmem_ld_wait();
+        if (__all_sync(0xffffffffu, alpha == 1.0f)) {
 #pragma unroll
-        for (int i = 0; i < OD; ++i) o_acc[i] = fmaf(o_acc[i], alpha, __uint_as_float(v[i]));
+          for (int i = 0; i < OD; ++i) o_acc[i] += __uint_as_float(v[i]);
+          l_acc += __uint_as_float(lsum);
+        } else {
+#pragma unroll
+          for (int i = 0; i < OD; ++i) o_acc[i] = (o_acc[i] + __uint_as_float(v[i])) * alpha;
+          l_acc = (l_acc + __uint_as_float(lsum)) * alpha;
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_empty[b]);
@@ -300,28 +353,38 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
         const int st = t % ATT_STAGES;
         const int b = t & 1;
         const int kv0 = c.j * ATT_BKV;
-        const int flag = args.tileflag[doc * n_kv + c.j];
+        const bool need_mask = (c.partial >> c.j) & 1u;        // padded text keys inside this tile (rare)
+        const bool tail = kv0 + ATT_BKV > S;                   // keys beyond the document (last tile)
         const uint8_t* sb = smem + AttSmem::KV_OFF + st * AttSmem::KV_STAGE + AttSmem::K_BYTES + AttSmem::V_BYTES + r * 128;
         uint8_t* sp = smem + AttSmem::P_OFF + (part >> 1) * (AttSmem::P_BYTES / 2) + r * 128;
+        const bool tr = args.trace && blockIdx.x == 0 && threadIdx.x == 64 && t < 96;
+        if (tr) args.trace[t * 8 + 0] = clock64();
         mbar_wait(&s_full[b], (t >> 1) & 1);         // S_t done  (=> kv_full[st] landed: the MMA waited on it)
         tc_fence_after();
+        if (tr) args.trace[t * 8 + 1] = clock64();
 
-        // ---- s = S + bias (registers, log2 domain), partial row max
         uint32_t v[KC];
         tmem_ld32(tmem_S + lane_addr + b * ATT_BKV + part * KC, v);
         const uint4 ba = *reinterpret_cast<const uint4*>(sb + (((part * 2) ^ sw) << 4));        // keys 32*part .. +15
         const uint4 bb = *reinterpret_cast<const uint4*>(sb + (((part * 2 + 1) ^ sw) << 4));    // keys +16 .. +31
         tmem_ld_wait();
+        // ---- s = S + bias - ref   (log2 domain; ref = 0 for the first tile of an item)
+        const float crow = C0 + q_ref;                // exact: |q_ref| < 2^22 integers
         float sc[KC];
-#define MMEE_BIAS4(W, BASE)                                                                         \
-  sc[BASE + 0] = fmaf(u8_to_centered_float<0>(W), scale2, __uint_as_float(v[BASE + 0]));            \
-  sc[BASE + 1] = fmaf(u8_to_centered_float<1>(W), scale2, __uint_as_float(v[BASE + 1]));            \
-  sc[BASE + 2] = fmaf(u8_to_centered_float<2>(W), scale2, __uint_as_float(v[BASE + 2]));            \
-  sc[BASE + 3] = fmaf(u8_to_centered_float<3>(W), scale2, __uint_as_float(v[BASE + 3]));
+#define MMEE_BIAS4(W, BASE)                                                                  \
+  sc[BASE + 0] = fmaf(u8_magic<0>(W) - crow, scale2, __uint_as_float(v[BASE + 0]));          \
+  sc[BASE + 1] = fmaf(u8_magic<1>(W) - crow, scale2, __uint_as_float(v[BASE + 1]));          \
+  sc[BASE + 2] = fmaf(u8_magic<2>(W) - crow, scale2, __uint_as_float(v[BASE + 2]));          \
+  sc[BASE + 3] = fmaf(u8_magic<3>(W) - crow, scale2, __uint_as_float(v[BASE + 3]));
         MMEE_BIAS4(ba.x, 0) MMEE_BIAS4(ba.y, 4) MMEE_BIAS4(ba.z, 8) MMEE_BIAS4(ba.w, 12)
         MMEE_BIAS4(bb.x, 16) MMEE_BIAS4(bb.y, 20) MMEE_BIAS4(bb.z, 24) MMEE_BIAS4(bb.w, 28)
 #undef MMEE_BIAS4
-        if (flag != 0 || kv0 + ATT_BKV > S) {        // padded keys in this tile and/or keys beyond the document
+        if (tail) {
+#pragma unroll
+          for (int i = 0; i < KC; ++i)
+            if (kv0 + part * KC + i >= S) sc[i] = -INFINITY;
+        }
+        if (need_mask) {                              // padded keys in this tile
           const float* ma = args.maskadd + static_cast<size_t>(doc) * args.kv_pitch + kv0 + part * KC;
 #pragma unroll
           for (int i = 0; i < KC; i += 4) {
@@ -333,60 +396,74 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_const
             if (m4.w < 0.f) sc[i + 3] = -INFINITY;
           }
         }
-        float tmax = sc[0];
+        float pmax = sc[0];
 #pragma unroll
-        for (int i = 1; i < KC; ++i) tmax = fmaxf(tmax, sc[i]);
-        xch[(b * ATT_NSPLIT + part) * ATT_BQ + r] = tmax;
+        for (int i = 1; i < KC; ++i) pmax = fmaxf(pmax, sc[i]);
+        xch[(b * ATT_NSPLIT + part) * ATT_BQ + r] = pmax;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&kv_empty[st]);   // bias tile consumed
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-#pragma unroll
-        for (int pp = 0; pp < ATT_NSPLIT; ++pp) tmax = fmaxf(tmax, xch[(b * ATT_NSPLIT + pp) * ATT_BQ + r]);
+        if (tr) args.trace[t * 8 + 2] = clock64();
 
-        const float m_new = fmaxf(m_run, tmax);
-        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-        const float alpha = fast_exp2(m_run - m_use);     // m_run = -inf -> 0
-
-        // O'[t-1] -> registers.  Its o_full wait also proves P V_{t-1} has finished reading the single P buffer.
-        if (nproc > 0) accumulate(t - 1, alpha_prev);
-        alpha_prev = alpha;
-
-        // ---- p = exp2(s - m), partial row sum, bf16 P -> smem (SW128 K-major A operand)
-        float psum = 0.f;
+        // p = exp2(s - ref) as bf16 into smem (SW128 K-major A operand); the row sum comes out of the PV MMA
+        auto emit_p = [&](auto first_tag, float shift) {
+          constexpr bool kFirst = decltype(first_tag)::value;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float p[8];
+          for (int q = 0; q < 4; ++q) {
+            float p[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            p[e] = fast_exp2(sc[q * 8 + e] - m_use);
-            psum += p[e];
+            for (int e = 0; e < 8; ++e) p[e] = fast_exp2(kFirst ? (sc[q * 8 + e] - shift) : sc[q * 8 + e]);
+            *reinterpret_cast<uint4*>(sp + ((((part & 1) * 4 + q) ^ sw) << 4)) =
+                make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]),
+                           pack_bf16x2(p[6], p[7]));
           }
-          *reinterpret_cast<uint4*>(sp + ((((part & 1) * 4 + q) ^ sw) << 4)) =
-              make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]),
-                         pack_bf16x2(p[6], p[7]));
+        };
+        if (nproc == 0) {
+          // first tile of an item: exact row max before exponentiating
+          asm volatile("bar.sync %0, 128;" ::"r"(quarter + 1) : "memory");   // the 4 warps that share these 32 rows
+          float rmax = pmax;
+#pragma unroll
+          for (int pp = 0; pp < ATT_NSPLIT; ++pp) rmax = fmaxf(rmax, xch[(b * ATT_NSPLIT + pp) * ATT_BQ + r]);
+          q_ref = (rmax == -INFINITY) ? 0.f : rintf(rmax * inv_scale2);
+          emit_p(std::true_type{}, q_ref * scale2);
+        } else {
+          // O'[t-1] -> registers.  Its o_full wait also proves P V_{t-1} has finished reading the single P buffer.
+          accumulate(t - 1, alpha_prev);
+          if (tr) args.trace[t * 8 + 3] = clock64();
+          emit_p(std::false_type{}, 0.f);
         }
-        l_run = l_run * alpha + psum;
-        m_run = m_new;
+        if (tr) args.trace[t * 8 + 4] = clock64();
         fence_proxy_async_smem();                     // P visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[b]);
+        if (tr) args.trace[t * 8 + 5] = clock64();
+
+        // ---- reference for the following tiles
+        alpha_prev = 1.f;
+        if (nproc > 0) {
+          asm volatile("bar.sync %0, 128;" ::"r"(quarter + 1) : "memory");   // the 4 warps that share these 32 rows
+          float rmax = pmax;
+#pragma unroll
+          for (int pp = 0; pp < ATT_NSPLIT; ++pp) rmax = fmaxf(rmax, xch[(b * ATT_NSPLIT + pp) * ATT_BQ + r]);
+          if (rmax > 0.f) {                           // this tile raised the row max: later tiles use the new reference
+            const float dq = ceilf(rmax * inv_scale2);
+            q_ref += dq;
+            alpha_prev = fast_exp2(-dq * scale2);
+            if (rmax > 100.f) *args.err_flag = 1;
+          }
+        }
+        if (tr) args.trace[t * 8 + 6] = clock64();
         ++t;
         ++nproc;
-        advance(c);
+        c = att_next(c, total_items, n_qt, stride, args);
+        if (tr) args.trace[(t - 1) * 8 + 7] = clock64();
       }
-      accumulate(t - 1, alpha_prev);
+      accumulate(t - 1, 1.f);
 
-      // ---- combine the partial row sums, normalise and store ctx[row, head*64 + 16*part .. +15]
-      xl[part * ATT_BQ + r] = l_run;
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      float l_tot = 0.f;
-#pragma unroll
-      for (int pp = 0; pp < ATT_NSPLIT; ++pp) l_tot += xl[pp * ATT_BQ + r];
-      asm volatile("bar.sync 1, 512;" ::: "memory");      // xl may be rewritten by the next item
+      // ---- normalise and store ctx[row, head*64 + 16*part .. +15]
       const int q = q0 + r;
       if (q < S) {
-        const float inv = 1.0f / l_tot;
+        const float inv = 1.0f / l_acc;
         uint4* dst = reinterpret_cast<uint4*>(args.ctx + static_cast<size_t>(row0 + q) * args.H + head * ATT_D + part * OD);
 #pragma unroll
         for (int i = 0; i < OD / 8; ++i)

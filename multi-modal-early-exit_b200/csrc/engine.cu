@@ -149,7 +149,11 @@ struct mmee_engine {
   DevBuf<float> Y, VIS, POOL, Z, T0, T1;
   DevBuf<uint8_t> BIAS;
   DevBuf<float> maskadd, bias_inv_scale, bias_scale2;
-  DevBuf<int> tileflag;
+  DevBuf<int> tileflag, att_err;
+  DevBuf<uint32_t> slot_meta;
+  int meta_stage = -1;
+  DevBuf<long long> att_trace;
+  bool trace_on = false;
   int n_kv_tiles = 6;
   DevBuf<int> posid;
   CUtensorMap t_x[2], t_qk, t_vt, t_bias, t_ctx, t_a1, t_mid, t_patch;
@@ -334,7 +338,7 @@ void finalize(mmee_engine* e) {
         my = fmaxf(my, fabsf(ty[static_cast<size_t>(hh) * d.rel2d_bins + b]));
       }
       float bound = (m1 + mx + my) / sqrtf(static_cast<float>(H / h));
-      if (!(bound > 0.f)) bound = 1.f;
+      if (!(bound > 0.02f)) bound = 0.02f;   // keeps the row reference q_ref = max/scale2 an exact fp32 integer
       const float scale = bound / 127.0f;
       inv[hh] = 1.0f / scale;
       sc2[hh] = scale * 1.4426950408889634f;
@@ -446,6 +450,9 @@ void allocate(mmee_engine* e) {
   e->n_kv_tiles = (S + ATT_BKV - 1) / ATT_BKV;
   e->maskadd.alloc(static_cast<size_t>(B) * e->kv_pitch, true);
   e->tileflag.alloc(static_cast<size_t>(B) * e->n_kv_tiles, true);
+  e->att_err.alloc(1, true);
+  e->slot_meta.alloc(B, true);
+  e->att_trace.alloc(4096, true);
   e->t_ctx = make_tmap_2d_sw128(e->CTX.p, M, H, H, 128);
   e->t_a1 = make_tmap_2d_sw128(e->A1.p, M, H, H, 128);
   e->t_mid = make_tmap_2d_sw128(e->MID.p, M, I, I, 128);
@@ -545,6 +552,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   }
   mark(e, "embed", st);
 
+  e->meta_stage = -1;
   int stage = 0;       // index into n_dev / m_dev
   int cur = 0;         // X buffer holding the current layer input
   int sd = 0;          // slot_doc ping-pong index
@@ -630,10 +638,16 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     launch_gemm<EPI_QKV>(e, e->bn_qkv, e->t_x[cur], w.t_wqkv, ga, st);
     mark(e, "gemm", st);
 
+    if (e->meta_stage != stage) {   // survivors changed since the last layer (or first layer): refresh slot -> (doc, tile flags)
+      slot_meta_kernel<<<(B + 255) / 256, 256, 0, st>>>(e->slot_doc[sd].p, e->tileflag.p, e->n_dev.p + stage, e->slot_meta.p,
+                                                      e->n_kv_tiles);
+      e->launches++;
+      e->meta_stage = stage;
+    }
     AttArgs aa;
-    aa.n_active_dev = e->n_dev.p + stage; aa.slot_doc = e->slot_doc[sd].p; aa.ctx = e->CTX.p; aa.H = H;
-    aa.heads = heads; aa.seq = S; aa.kv_pitch = e->kv_pitch; aa.tileflag = e->tileflag.p; aa.maskadd = e->maskadd.p;
-    aa.bias_scale2 = e->bias_scale2.p;
+    aa.n_active_dev = e->n_dev.p + stage; aa.slot_meta = e->slot_meta.p; aa.ctx = e->CTX.p; aa.H = H;
+    aa.heads = heads; aa.seq = S; aa.kv_pitch = e->kv_pitch; aa.maskadd = e->maskadd.p;
+    aa.bias_scale2 = e->bias_scale2.p; aa.err_flag = e->att_err.p; aa.trace = (e->trace_on && l == 0) ? e->att_trace.p : nullptr;
     {
       static bool configured = false;
       if (!configured) {
@@ -924,6 +938,7 @@ int64_t mmee_debug_read(mmee_engine* e, const char* name, void* host_dst, int64_
     else if (n == "VIS") { src = e->VIS.p; bytes = e->VIS.n * 4; }
     else if (n == "POOL") { src = e->POOL.p; bytes = e->POOL.n * 4; }
     else if (n == "BIAS") { src = e->BIAS.p; bytes = e->BIAS.n; }
+    else if (n == "ATT_TRACE") { src = e->att_trace.p; bytes = e->att_trace.n * 8; }
     else if (n == "BIAS_SCALE2") { src = e->bias_scale2.p; bytes = e->bias_scale2.n * 4; }
     else throw std::runtime_error("unknown buffer " + n);
     if (static_cast<int64_t>(bytes) > capacity_bytes) bytes = static_cast<size_t>(capacity_bytes);
@@ -937,7 +952,8 @@ int64_t mmee_debug_read(mmee_engine* e, const char* name, void* host_dst, int64_
 
 int mmee_set_profiling(mmee_engine* e, int on) {
   if (!e) return -1;
-  e->profiling = on != 0;
+  e->profiling = (on & 1) != 0;
+  e->trace_on = (on & 2) != 0;     // developer trace of the first layer's attention kernel (debug_read "ATT_TRACE")
   return 0;
 }
 
