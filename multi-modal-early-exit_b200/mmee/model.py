@@ -108,10 +108,10 @@ class B200EEForSequenceClassification:
         self._load_weights(state_dict)
 
     # ------------------------------------------------------------------ construction helpers
-    @classmethod
-    def from_reference(cls, model, device: int = 0, max_batch: int = 256):
-        """Build from a constructed reference `LayoutLMv3EEForSequenceClassification` (or anything with the
-        same `.config` / `.state_dict()`), reading HF dims and `config.EE_config`."""
+    @staticmethod
+    def spec_from_reference(model):
+        """(ModelDims, ExitConfig, fp32 CPU state dict) of a constructed reference
+        `LayoutLMv3EEForSequenceClassification` (or anything with the same `.config` / `.state_dict()`)."""
         c = model.config
         dims = ModelDims(hidden=c.hidden_size, layers=c.num_hidden_layers, heads=c.num_attention_heads,
                          inter=c.intermediate_size, image=c.input_size, patch=c.patch_size,
@@ -120,9 +120,15 @@ class B200EEForSequenceClassification:
                          max_2d=c.max_2d_position_embeddings, rel_bins=c.rel_pos_bins, max_rel=c.max_rel_pos,
                          rel2d_bins=c.rel_2d_pos_bins, max_rel2d=c.max_rel_2d_pos, pad_id=c.pad_token_id,
                          ln_eps=c.layer_norm_eps)
-        ee = ExitConfig.from_dict({k: (str(v) if not isinstance(v, (list, tuple, int, float)) else v)
+        ee = ExitConfig.from_dict({k: (v if isinstance(v, (list, tuple, int, float)) else str(v))
                                    for k, v in dict(c.EE_config).items()})
         sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+        return dims, ee, sd
+
+    @classmethod
+    def from_reference(cls, model, device: int = 0, max_batch: int = 256):
+        """Build the engine from a constructed reference model (reads HF dims, `config.EE_config`, weights)."""
+        dims, ee, sd = cls.spec_from_reference(model)
         return cls(dims, ee, sd, device=device, max_batch=max_batch)
 
     def _load_weights(self, sd: Dict[str, torch.Tensor]) -> None:

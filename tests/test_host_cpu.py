@@ -179,3 +179,23 @@ def test_two_rank_gather_equals_single_process(tmp_path):
     world = 2
     mp.spawn(_gather_worker, args=(world, _free_port(), 37, str(tmp_path)), nprocs=world, join=True)
     assert all(open(os.path.join(tmp_path, f"ok{r}")).read() == "1" for r in range(world))
+
+
+@pytest.mark.skipif(not __import__("oracle.reference_harness", fromlist=["x"]).available(), reason="reference tree not present")
+def test_spec_from_reference_model():
+    """from_reference() reads dims, exit config and weights off a constructed reference model."""
+    from mmee.model import B200EEForSequenceClassification
+    from oracle import reference_harness as RH
+
+    dims = ModelDims.tiny(layers=2)
+    ee = ExitConfig.from_dict(dict(exits=["text_visual_concat", 1, 2], encoder_layer_strategy="gate",
+                                   inference_strategy="entropy", global_threshold=0.4))
+    sd = synth.make_state_dict(dims, ee, seed=1)
+    ref = RH.build_reference_model(dims, ee, sd)
+    d2, e2, sd2 = B200EEForSequenceClassification.spec_from_reference(ref)
+    assert d2 == dims
+    assert list(e2.exits) == list(ee.exits) and e2.encoder_layer_strategy == "gate" and e2.inference_strategy == "entropy"
+    assert e2.global_threshold == 0.4
+    for k, v in sd.items():
+        assert torch.equal(sd2[k], v), k
+    assert set(sd2) - set(sd) <= {"layoutlmv3.visual_bbox", "layoutlmv3.embeddings.position_ids"}
