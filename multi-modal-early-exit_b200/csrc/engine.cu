@@ -150,13 +150,13 @@ struct mmee_engine {
   DevBuf<uint8_t> BIAS;
   DevBuf<float> maskadd, bias_inv_scale, bias_scale2;
   DevBuf<int> tileflag, att_err;
-  DevBuf<uint32_t> slot_meta;
+  DevBuf<uint2> slot_meta;
   int meta_stage = -1;
   DevBuf<long long> att_trace;
   bool trace_on = false;
   int n_kv_tiles = 6;
   DevBuf<int> posid;
-  CUtensorMap t_x[2], t_qk, t_vt, t_bias, t_ctx, t_a1, t_mid, t_patch;
+  CUtensorMap t_x[2], t_qk, t_k64, t_vt, t_bias, t_ctx, t_a1, t_mid, t_patch;
 
   // bookkeeping (device)
   DevBuf<int> n_dev, m_dev;                 // [stages]
@@ -446,7 +446,9 @@ void allocate(mmee_engine* e) {
   e->t_x[1] = make_tmap_2d_sw128(e->X[1].p, M, H, H, 128);
   e->t_qk = make_tmap_2d_sw128(e->QK.p, M, 2 * H, 2 * H, 128);
   e->t_vt = make_tmap_2d_sw128(e->VT.p, static_cast<uint64_t>(B) * heads * 64, e->kv_pitch, e->kv_pitch, 64);
-  e->t_bias = make_tmap_2d_u8_sw128(e->BIAS.p, static_cast<uint64_t>(B) * heads * S, e->bias_pitch, e->bias_pitch, 128);
+  e->t_k64 = make_tmap_2d_sw128(e->QK.p, M, 2 * H, 2 * H, ATT_BKV);
+  e->t_bias = make_tmap_2d_u8(e->BIAS.p, static_cast<uint64_t>(B) * heads * S, e->bias_pitch, e->bias_pitch, 128, ATT_BKV);
+  if (e->n_kv_tiles > ATT_MAX_KV_TILES) throw std::runtime_error("too many key tiles");
   e->n_kv_tiles = (S + ATT_BKV - 1) / ATT_BKV;
   e->maskadd.alloc(static_cast<size_t>(B) * e->kv_pitch, true);
   e->tileflag.alloc(static_cast<size_t>(B) * e->n_kv_tiles, true);
@@ -547,7 +549,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     const size_t smem = (static_cast<size_t>(heads) * (d.rel_bins + 2 * d.rel2d_bins) + heads) * 4;
     const int threads = ((e->bias_pitch / 16 + 31) / 32) * 32;
     bias_build_kernel<<<dim3(1, S, B), threads, smem, st>>>(ba);
-    keymask_kernel<<<B, e->kv_pitch, 0, st>>>(mask, e->maskadd.p, e->tileflag.p, T, S, e->kv_pitch, e->n_kv_tiles);
+    keymask_kernel<<<B, e->kv_pitch, 0, st>>>(mask, e->maskadd.p, e->tileflag.p, T, S, e->kv_pitch, e->n_kv_tiles, ATT_BKV);
     e->launches += 2;
   }
   mark(e, "embed", st);
@@ -654,8 +656,8 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
         CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
         configured = true;
       }
-      attention_kernel<<<e->sms, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(
-          e->t_qk, e->t_vt, e->t_bias, aa);
+      attention_kernel<<<e->sms * ATT_CTAS_PER_SM, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(
+          e->t_qk, e->t_k64, e->t_vt, e->t_bias, aa);
       CUDA_OK(cudaGetLastError());
       e->launches++;
     }

@@ -132,22 +132,22 @@ __global__ void bias_build_kernel(BiasArgs a) {
 }
 
 // Key-padding mask (HF:270-272 adds (1-mask)*finfo.min to the scores): maskadd[doc][j] = 0 / -inf and a per
-// (doc, 128-key tile) flag: 0 = no masked key, 1 = some, 2 = every valid key masked (the tile is skipped).
+// (doc, key tile of `tile_keys` keys) flag: 0 = no masked key, 1 = some, 2 = every valid key masked (the tile is skipped).
 // grid B, block = kv_pitch threads (<= 1024)
 __global__ void keymask_kernel(const int64_t* __restrict__ mask, float* __restrict__ maskadd, int* __restrict__ tileflag,
-                               int n_text, int seq, int kv_pitch, int n_tiles) {
-  __shared__ int s_masked[8], s_valid[8];
+                               int n_text, int seq, int kv_pitch, int n_tiles, int tile_keys) {
+  __shared__ int s_masked[32], s_valid[32];
   const int doc = blockIdx.x;
   const int j = threadIdx.x;
-  if (j < 8) { s_masked[j] = 0; s_valid[j] = 0; }
+  if (j < 32) { s_masked[j] = 0; s_valid[j] = 0; }
   __syncthreads();
   if (j < kv_pitch) {
     bool m = (j >= seq);
     if (!m && j < n_text) m = (mask[static_cast<size_t>(doc) * n_text + j] == 0);
     maskadd[static_cast<size_t>(doc) * kv_pitch + j] = m ? -INFINITY : 0.f;
     if (j < seq) {
-      atomicAdd(&s_valid[j >> 7], 1);
-      if (m) atomicAdd(&s_masked[j >> 7], 1);
+      atomicAdd(&s_valid[j / tile_keys], 1);
+      if (m) atomicAdd(&s_masked[j / tile_keys], 1);
     }
   }
   __syncthreads();

@@ -43,17 +43,18 @@ inline CUtensorMap make_tmap_2d_sw128(const void* base, uint64_t rows, uint64_t 
   return m;
 }
 
-// 1-byte elements, row-major [rows, cols] with row pitch `pitch_bytes` (multiple of 16); box = [box_rows, 128 B],
-// SWIZZLE_128B.
-inline CUtensorMap make_tmap_2d_u8_sw128(const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
-                                         uint32_t box_rows) {
+// 1-byte elements, row-major [rows, cols] with row pitch `pitch_bytes` (multiple of 16); box = [box_rows, box_bytes]
+// with box_bytes = 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B).
+inline CUtensorMap make_tmap_2d_u8(const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                                   uint32_t box_rows, uint32_t box_bytes) {
   CUtensorMap m;
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {pitch_bytes};
-  cuuint32_t box[2] = {128, box_rows};
+  cuuint32_t box[2] = {box_bytes, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               box_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(u8) failed: " + std::to_string((int)r));
   return m;
