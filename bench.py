@@ -266,9 +266,16 @@ def main():
     pk = peaks()
     gemm_tf = gemm_flops / (stage["gemm"] / 1000.0) / 1e12 if stage.get("gemm") else None
     attn_tf = attn_flops / (stage["attention"] / 1000.0) / 1e12 if stage.get("attention") else None
+    traffic, traffic_src = None, None
+    tj = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tj) and B == BATCH_PER_GPU:      # ncu --set full capture of the same workload (see profiles/)
+        with open(tj) as f:
+            tr = json.load(f)
+        traffic = tr.get("gemm_mean_dram_bytes_per_launch")
+        traffic_src = f"ncu dram__bytes_read.sum+dram__bytes_write.sum, mean of the 4 GEMM launches of one layer at {tr.get('docs')} docs (profiles/traffic.json, capture {tr.get('capture')})"
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (QKV / out-proj / MLP-up+GELU / MLP-down, tcgen05)",
                 "achieved": gemm_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                "frac": (gemm_tf / pk["tf_sust"]) if gemm_tf else None, "traffic": None,
+                "frac": (gemm_tf / pk["tf_sust"]) if gemm_tf else None, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
                 "attention": {"achieved": attn_tf, "unit": "TFLOP/s", "frac": (attn_tf / pk["tf_sust"]) if attn_tf else None},
                 "stage_ms": stage,
