@@ -152,8 +152,6 @@ struct mmee_engine {
   DevBuf<int> tileflag, att_err;
   DevBuf<uint2> slot_meta;
   int meta_stage = -1;
-  DevBuf<long long> att_trace;
-  bool trace_on = false;
   int n_kv_tiles = 6;
   DevBuf<int> posid;
   CUtensorMap t_x[2], t_qk, t_k64, t_vt, t_bias, t_ctx, t_a1, t_mid, t_patch;
@@ -454,7 +452,6 @@ void allocate(mmee_engine* e) {
   e->tileflag.alloc(static_cast<size_t>(B) * e->n_kv_tiles, true);
   e->att_err.alloc(1, true);
   e->slot_meta.alloc(B, true);
-  e->att_trace.alloc(4096, true);
   e->t_ctx = make_tmap_2d_sw128(e->CTX.p, M, H, H, 128);
   e->t_a1 = make_tmap_2d_sw128(e->A1.p, M, H, H, 128);
   e->t_mid = make_tmap_2d_sw128(e->MID.p, M, I, I, 128);
@@ -649,7 +646,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     AttArgs aa;
     aa.n_active_dev = e->n_dev.p + stage; aa.slot_meta = e->slot_meta.p; aa.ctx = e->CTX.p; aa.H = H;
     aa.heads = heads; aa.seq = S; aa.kv_pitch = e->kv_pitch; aa.maskadd = e->maskadd.p;
-    aa.bias_scale2 = e->bias_scale2.p; aa.err_flag = e->att_err.p; aa.trace = (e->trace_on && l == 0) ? e->att_trace.p : nullptr;
+    aa.bias_scale2 = e->bias_scale2.p; aa.err_flag = e->att_err.p;
     {
       static bool configured = false;
       if (!configured) {
@@ -940,7 +937,6 @@ int64_t mmee_debug_read(mmee_engine* e, const char* name, void* host_dst, int64_
     else if (n == "VIS") { src = e->VIS.p; bytes = e->VIS.n * 4; }
     else if (n == "POOL") { src = e->POOL.p; bytes = e->POOL.n * 4; }
     else if (n == "BIAS") { src = e->BIAS.p; bytes = e->BIAS.n; }
-    else if (n == "ATT_TRACE") { src = e->att_trace.p; bytes = e->att_trace.n * 8; }
     else if (n == "BIAS_SCALE2") { src = e->bias_scale2.p; bytes = e->bias_scale2.n * 4; }
     else throw std::runtime_error("unknown buffer " + n);
     if (static_cast<int64_t>(bytes) > capacity_bytes) bytes = static_cast<size_t>(capacity_bytes);
@@ -955,7 +951,6 @@ int64_t mmee_debug_read(mmee_engine* e, const char* name, void* host_dst, int64_
 int mmee_set_profiling(mmee_engine* e, int on) {
   if (!e) return -1;
   e->profiling = (on & 1) != 0;
-  e->trace_on = (on & 2) != 0;     // developer trace of the first layer's attention kernel (debug_read "ATT_TRACE")
   return 0;
 }
 
