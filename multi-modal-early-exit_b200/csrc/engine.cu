@@ -117,7 +117,7 @@ struct mmee_engine {
   int device = 0;
   int max_batch = 0;
   int H, L, heads, I, T, P, S, K, n_vis, n_patch, kdim_patch;
-  int kv_pitch = 768, bias_pitch = 712;
+  int kv_pitch = 768, bias_pitch = 768;
   int m_max = 0;            // padded row capacity of activation buffers
   int sms = 148;
   int bn_h, bn_qkv, bn_i;   // BLOCK_N per GEMM family
@@ -147,10 +147,12 @@ struct mmee_engine {
   // activations
   DevBuf<__nv_bfloat16> X[2], QK, VT, CTX, A1, MID, PATCH;
   DevBuf<float> Y, VIS, POOL, Z, T0, T1;
-  DevBuf<uint8_t> BIAS;
-  DevBuf<float> maskadd, bias_inv_scale, bias_scale2;
+  DevBuf<__half> BIAS, bias_t2;
+  DevBuf<float> maskadd, bias_t1;
   DevBuf<int> tileflag, att_err;
   DevBuf<uint2> slot_meta;
+  DevBuf<long long> att_trace;
+  bool trace_on = false;
   int meta_stage = -1;
   int n_kv_tiles = 6;
   DevBuf<int> posid;
@@ -323,26 +325,24 @@ void finalize(mmee_engine* e) {
   // Q carries log2(e)/sqrt(d): the attention softmax runs in the log2 domain (exp2 without a per-element multiply)
   const float qscale = 1.4426950408889634f / sqrtf(static_cast<float>(H / h));
   {
-    // per-head linear scale of the uint8 attention bias: the largest |bias| the three tables can produce / 127
+    // attention-bias tables in the log2 domain (bias_build_kernel): T1[b1][head] = W1d * c (fp32),
+    // T2[bx][by][head] = fp16((Wx + Wy) * c), c = log2(e)/sqrt(d)
     const auto& t1 = need(e, p + "encoder.rel_pos_bias.weight", {h, d.rel_bins});
     const auto& tx = need(e, p + "encoder.rel_pos_x_bias.weight", {h, d.rel2d_bins});
     const auto& ty = need(e, p + "encoder.rel_pos_y_bias.weight", {h, d.rel2d_bins});
-    std::vector<float> inv(h), sc2(h);
-    for (int hh = 0; hh < h; ++hh) {
-      float m1 = 0.f, mx = 0.f, my = 0.f;
-      for (int b = 0; b < d.rel_bins; ++b) m1 = fmaxf(m1, fabsf(t1[static_cast<size_t>(hh) * d.rel_bins + b]));
-      for (int b = 0; b < d.rel2d_bins; ++b) {
-        mx = fmaxf(mx, fabsf(tx[static_cast<size_t>(hh) * d.rel2d_bins + b]));
-        my = fmaxf(my, fabsf(ty[static_cast<size_t>(hh) * d.rel2d_bins + b]));
-      }
-      float bound = (m1 + mx + my) / sqrtf(static_cast<float>(H / h));
-      if (!(bound > 0.02f)) bound = 0.02f;   // keeps the row reference q_ref = max/scale2 an exact fp32 integer
-      const float scale = bound / 127.0f;
-      inv[hh] = 1.0f / scale;
-      sc2[hh] = scale * 1.4426950408889634f;
-    }
-    upload_f32(e->bias_inv_scale, inv);
-    upload_f32(e->bias_scale2, sc2);
+    if (h % 2) throw std::runtime_error("attention heads must be even");
+    std::vector<float> T1(static_cast<size_t>(d.rel_bins) * h);
+    for (int b1 = 0; b1 < d.rel_bins; ++b1)
+      for (int hh = 0; hh < h; ++hh) T1[static_cast<size_t>(b1) * h + hh] = t1[static_cast<size_t>(hh) * d.rel_bins + b1] * qscale;
+    std::vector<__half> T2(static_cast<size_t>(d.rel2d_bins) * d.rel2d_bins * h);
+    for (int bx = 0; bx < d.rel2d_bins; ++bx)
+      for (int by = 0; by < d.rel2d_bins; ++by)
+        for (int hh = 0; hh < h; ++hh)
+          T2[(static_cast<size_t>(bx) * d.rel2d_bins + by) * h + hh] = __float2half_rn(
+              (tx[static_cast<size_t>(hh) * d.rel2d_bins + bx] + ty[static_cast<size_t>(hh) * d.rel2d_bins + by]) * qscale);
+    upload_f32(e->bias_t1, T1);
+    e->bias_t2.alloc(T2.size());
+    CUDA_OK(cudaMemcpy(e->bias_t2.p, T2.data(), T2.size() * 2, cudaMemcpyHostToDevice));
   }
   e->layers.resize(e->L);
   for (int i = 0; i < e->L; ++i) {
@@ -437,7 +437,7 @@ void allocate(mmee_engine* e) {
   e->Z.alloc(static_cast<size_t>(B) * H, true);
   e->T0.alloc(static_cast<size_t>(B) * H, true);
   e->T1.alloc(static_cast<size_t>(B) * H, true);
-  e->BIAS.alloc(static_cast<size_t>(B) * heads * S * e->bias_pitch + 64 * 1024, true);
+  e->BIAS.alloc(static_cast<size_t>(B) * heads * S * e->bias_pitch + 64 * 1024, true);   // 12.3 MB / base document
   e->posid.alloc(static_cast<size_t>(B) * e->T);
 
   e->t_x[0] = make_tmap_2d_sw128(e->X[0].p, M, H, H, 128);
@@ -445,13 +445,15 @@ void allocate(mmee_engine* e) {
   e->t_qk = make_tmap_2d_sw128(e->QK.p, M, 2 * H, 2 * H, 128);
   e->t_vt = make_tmap_2d_sw128(e->VT.p, static_cast<uint64_t>(B) * heads * 64, e->kv_pitch, e->kv_pitch, 64);
   e->t_k64 = make_tmap_2d_sw128(e->QK.p, M, 2 * H, 2 * H, ATT_BKV);
-  e->t_bias = make_tmap_2d_u8(e->BIAS.p, static_cast<uint64_t>(B) * heads * S, e->bias_pitch, e->bias_pitch, 128, ATT_BKV);
+  e->t_bias = make_tmap_2d_sw128(e->BIAS.p, static_cast<uint64_t>(B) * heads * S, e->bias_pitch, e->bias_pitch, ATT_BQ,
+                                 CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
   if (e->n_kv_tiles > ATT_MAX_KV_TILES) throw std::runtime_error("too many key tiles");
   e->n_kv_tiles = (S + ATT_BKV - 1) / ATT_BKV;
   e->maskadd.alloc(static_cast<size_t>(B) * e->kv_pitch, true);
   e->tileflag.alloc(static_cast<size_t>(B) * e->n_kv_tiles, true);
   e->att_err.alloc(1, true);
   e->slot_meta.alloc(B, true);
+  e->att_trace.alloc(4096, true);
   e->t_ctx = make_tmap_2d_sw128(e->CTX.p, M, H, H, 128);
   e->t_a1 = make_tmap_2d_sw128(e->A1.p, M, H, H, 128);
   e->t_mid = make_tmap_2d_sw128(e->MID.p, M, I, I, 128);
@@ -537,16 +539,22 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     e->launches++;
   }
   {
-    BiasArgs ba;
-    ba.bbox = bbox; ba.vis_bbox = e->vis_bbox.p; ba.w1d = e->w1d.p; ba.wx = e->wx.p; ba.wy = e->wy.p;
-    ba.inv_scale = e->bias_inv_scale.p;
-    ba.lut1 = e->lut1.p; ba.lut2 = e->lut2.p; ba.lut1_n = static_cast<int>(e->lut1.n); ba.lut2_n = static_cast<int>(e->lut2.n);
-    ba.bins1 = d.rel_bins; ba.bins2 = d.rel2d_bins; ba.heads = heads; ba.n_text = T; ba.seq = S; ba.pitch = e->bias_pitch;
-    ba.scale = 1.0f / sqrtf(static_cast<float>(H / heads)); ba.out = e->BIAS.p;
-    const size_t smem = (static_cast<size_t>(heads) * (d.rel_bins + 2 * d.rel2d_bins) + heads) * 4;
-    const int threads = ((e->bias_pitch / 16 + 31) / 32) * 32;
-    bias_build_kernel<<<dim3(1, S, B), threads, smem, st>>>(ba);
     keymask_kernel<<<B, e->kv_pitch, 0, st>>>(mask, e->maskadd.p, e->tileflag.p, T, S, e->kv_pitch, e->n_kv_tiles, ATT_BKV);
+    BiasArgs ba;
+    ba.bbox = bbox; ba.vis_bbox = e->vis_bbox.p; ba.t1 = e->bias_t1.p; ba.t2 = e->bias_t2.p;
+    ba.lut1 = e->lut1.p; ba.lut2 = e->lut2.p; ba.lut1_n = static_cast<int>(e->lut1.n); ba.lut2_n = static_cast<int>(e->lut2.n);
+    ba.maskadd = e->maskadd.p;
+    ba.bins1 = d.rel_bins; ba.bins2 = d.rel2d_bins; ba.heads = heads; ba.n_text = T; ba.seq = S; ba.pitch = e->bias_pitch;
+    ba.kv_pitch = e->kv_pitch; ba.B = B; ba.out = e->BIAS.p;
+    const size_t smem = bias_build_smem(ba);
+    static bool configured = false;
+    if (!configured) {
+      CUDA_OK(cudaFuncSetAttribute(bias_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    if (smem > 200 * 1024) throw std::runtime_error("relative-position tables do not fit shared memory");
+    bias_build_kernel<<<e->sms, BIAS_THREADS, smem, st>>>(ba);
+    CUDA_OK(cudaGetLastError());
     e->launches += 2;
   }
   mark(e, "embed", st);
@@ -645,16 +653,20 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     }
     AttArgs aa;
     aa.n_active_dev = e->n_dev.p + stage; aa.slot_meta = e->slot_meta.p; aa.ctx = e->CTX.p; aa.H = H;
-    aa.heads = heads; aa.seq = S; aa.kv_pitch = e->kv_pitch; aa.maskadd = e->maskadd.p;
-    aa.bias_scale2 = e->bias_scale2.p; aa.err_flag = e->att_err.p;
+    aa.heads = heads; aa.seq = S; aa.err_flag = e->att_err.p; aa.trace = e->att_trace.p;
     {
       static bool configured = false;
       if (!configured) {
-        CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
+        CUDA_OK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
+        CUDA_OK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
         configured = true;
       }
-      attention_kernel<<<e->sms * ATT_CTAS_PER_SM, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(
-          e->t_qk, e->t_k64, e->t_vt, e->t_bias, aa);
+      if (e->trace_on && l == 0)
+        attention_kernel<true><<<e->sms * ATT_CTAS_PER_SM, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(
+            e->t_qk, e->t_k64, e->t_vt, e->t_bias, aa);
+      else
+        attention_kernel<false><<<e->sms * ATT_CTAS_PER_SM, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(
+            e->t_qk, e->t_k64, e->t_vt, e->t_bias, aa);
       CUDA_OK(cudaGetLastError());
       e->launches++;
     }
@@ -781,7 +793,7 @@ int mmee_create(const mmee_model_desc* desc, int device, int max_batch, mmee_eng
   e->S = e->T + e->n_vis;
   e->kdim_patch = d.channels * d.patch * d.patch;
   e->kv_pitch = ((e->S + 127) / 128) * 128;
-  e->bias_pitch = ((e->S + 15) / 16) * 16;
+  e->bias_pitch = ((e->S + ATT_BKV - 1) / ATT_BKV) * ATT_BKV;   // whole key tiles: the pitch padding carries the -60000 mask
   if (e->kv_pitch > 1024) throw std::runtime_error("sequence too long for keymask_kernel");
   e->sms = prop.multiProcessorCount;
   e->bn_h = pick_bn(e->H); e->bn_qkv = pick_bn(e->H) ; e->bn_i = pick_bn(e->I);
@@ -936,8 +948,8 @@ int64_t mmee_debug_read(mmee_engine* e, const char* name, void* host_dst, int64_
     else if (n == "Y") { src = e->Y.p; bytes = e->Y.n * 4; }
     else if (n == "VIS") { src = e->VIS.p; bytes = e->VIS.n * 4; }
     else if (n == "POOL") { src = e->POOL.p; bytes = e->POOL.n * 4; }
-    else if (n == "BIAS") { src = e->BIAS.p; bytes = e->BIAS.n; }
-    else if (n == "BIAS_SCALE2") { src = e->bias_scale2.p; bytes = e->bias_scale2.n * 4; }
+    else if (n == "ATT_TRACE") { src = e->att_trace.p; bytes = e->att_trace.n * 8; }
+    else if (n == "BIAS") { src = e->BIAS.p; bytes = e->BIAS.n * 2; }
     else throw std::runtime_error("unknown buffer " + n);
     if (static_cast<int64_t>(bytes) > capacity_bytes) bytes = static_cast<size_t>(capacity_bytes);
     CUDA_OK(cudaMemcpy(host_dst, src, bytes, cudaMemcpyDeviceToHost));
@@ -951,6 +963,7 @@ int64_t mmee_debug_read(mmee_engine* e, const char* name, void* host_dst, int64_
 int mmee_set_profiling(mmee_engine* e, int on) {
   if (!e) return -1;
   e->profiling = (on & 1) != 0;
+  e->trace_on = (on & 2) != 0;     // developer trace of the first layer's attention kernel (debug_read "ATT_TRACE")
   return 0;
 }
 

@@ -47,87 +47,124 @@ __global__ void ln_rows_kernel(const float* __restrict__ Y, __nv_bfloat16* __res
 
 // ------------------------------------------------------------------ attention bias
 // The additive attention bias (rel_pos + rel_2d_pos)/sqrt(d) is layer-invariant (the reference builds it once per
-// forward, EE/models/LayoutLMv3.py:170-179).  It is materialised once per forward as uint8 with a per-head linear
-// scale:  bias = (u - 128) * scale_h,  scale_h = (max|W1d[h]| + max|Wx[h]| + max|Wy[h]|) / sqrt(d) / 127, so the
-// quantisation step is <= 0.8% of the largest bias the tables can produce (error far below the bf16 rounding of
-// the scores it is added to).  6 MB per base document instead of 24 MB (fp32) x 2 tensors in the reference.
+// forward, EE/models/LayoutLMv3.py:170-179; HF:393-458).  It is materialised once per forward as fp16 in the log2
+// domain, bias16[doc][head][i][j] = (W1d[b1] + (Wx[bx] + Wy[by])) * log2(e)/sqrt(d), with -60000 on padded keys
+// (attention_mask == 0, HF:270-272) and on the pitch padding j >= seq, so the attention kernel can ADD it on the
+// tensor core (S += bias16 x I, see attention.cuh) and needs no separate key mask.  12.3 MB per base document
+// instead of 2 x 24 MB fp32 in the reference.
+//
+// Persistent kernel, one CTA per SM: the 2-D table T2[bx][by][head] = fp16((Wx + Wy) * c) (98 KB for base, built at
+// weight load) and T1[b1][head] = W1d * c (fp32) live in shared memory for the whole launch, so each (i, j) pair
+// costs one bucket computation for all heads and one T1 + one T2 lookup per head PAIR.
 struct BiasArgs {
   const int64_t* bbox;       // [B, n_text, 4]
   const int* vis_bbox;       // [n_vis, 4]
-  const float* w1d;          // [heads, bins1]   (rel_pos_bias.weight)
-  const float* wx;           // [heads, bins2]
-  const float* wy;           // [heads, bins2]
-  const float* inv_scale;    // [heads]  1 / scale_h
+  const float* t1;           // [bins1][heads]            W1d * log2(e)/sqrt(d)
+  const __half* t2;          // [bins2*bins2][heads]      (Wx + Wy) * log2(e)/sqrt(d)
   const uint8_t* lut1;       // |rel| -> bucket offset, 1-D   (size lut1_n)
   const uint8_t* lut2;       // 2-D
+  const float* maskadd;      // [B][kv_pitch] 0 / -inf per key (padding, j >= seq)
   int lut1_n, lut2_n;
   int bins1, bins2;          // rel_pos_bins, rel_2d_pos_bins
-  int heads, n_text, seq, pitch;
-  float scale;               // 1/sqrt(d)
-  uint8_t* out;              // [B][heads][seq][pitch]
+  int heads, n_text, seq, pitch, kv_pitch, B;
+  __half* out;               // [B][heads][seq][pitch]
 };
 
-// grid (1, seq, B), block >= pitch/16 threads; thread = 16 consecutive keys j of query row i; loops over heads.
-__global__ void bias_build_kernel(BiasArgs a) {
-  extern __shared__ float s_tab[];       // w1d | wx | wy | inv_scale
-  const int n1 = a.heads * a.bins1, n2 = a.heads * a.bins2;
-  for (int i = threadIdx.x; i < n1; i += blockDim.x) s_tab[i] = a.w1d[i];
-  for (int i = threadIdx.x; i < n2; i += blockDim.x) { s_tab[n1 + i] = a.wx[i]; s_tab[n1 + n2 + i] = a.wy[i]; }
-  for (int i = threadIdx.x; i < a.heads; i += blockDim.x) s_tab[n1 + 2 * n2 + i] = a.inv_scale[i];
-  __syncthreads();
-  const int j0 = threadIdx.x * 16;
-  const int i = blockIdx.y;
-  const int doc = blockIdx.z;
-  if (j0 >= a.pitch) return;
-  auto coords = [&](int t, int& pos, int& x0, int& y1) {
-    if (t < a.n_text) {
-      const int64_t* bb = a.bbox + (static_cast<size_t>(doc) * a.n_text + t) * 4;
-      pos = t; x0 = static_cast<int>(bb[0]); y1 = static_cast<int>(bb[3]);
-    } else {
-      const int p = t - a.n_text;
-      pos = p; x0 = a.vis_bbox[p * 4 + 0]; y1 = a.vis_bbox[p * 4 + 3];
-    }
-  };
-  auto bucket = [](int rel, const uint8_t* lut, int lut_n, int bins) {
-    const int n = min(abs(rel), lut_n - 1);
-    return (rel > 0 ? (bins >> 1) : 0) + lut[n];
-  };
-  int pi, xi, yi;
-  coords(i, pi, xi, yi);
-  uint32_t idx[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const int j = j0 + k;
-    if (j < a.seq) {
-      int pj, xj, yj;
-      coords(j, pj, xj, yj);
-      const int b1 = bucket(pj - pi, a.lut1, a.lut1_n, a.bins1);
-      const int bx = bucket(xj - xi, a.lut2, a.lut2_n, a.bins2);
-      const int by = bucket(yj - yi, a.lut2, a.lut2_n, a.bins2);
-      idx[k] = static_cast<uint32_t>(b1) | (static_cast<uint32_t>(bx) << 8) | (static_cast<uint32_t>(by) << 16);
-    } else {
-      idx[k] = 0xFFFFFFFFu;              // pitch padding
-    }
-  }
-  uint8_t* out = a.out + ((static_cast<size_t>(doc) * a.heads) * a.seq + i) * a.pitch + j0;
-  const size_t head_stride = static_cast<size_t>(a.seq) * a.pitch;
-  for (int h = 0; h < a.heads; ++h) {
-    const float inv = s_tab[n1 + 2 * n2 + h];
-    uint32_t packed[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      uint32_t u = 128u;
-      if (idx[k] != 0xFFFFFFFFu) {
-        // reference association: rel_pos + (rel_x + rel_y), then / sqrt(d)
-        const float v = (s_tab[h * a.bins1 + (idx[k] & 0xFF)] +
-                         (s_tab[n1 + h * a.bins2 + ((idx[k] >> 8) & 0xFF)] +
-                          s_tab[n1 + n2 + h * a.bins2 + ((idx[k] >> 16) & 0xFF)])) * a.scale;
-        const int q = __float2int_rn(v * inv) + 128;
-        u = static_cast<uint32_t>(min(max(q, 1), 255));
+constexpr int BIAS_THREADS = 768;
+constexpr float BIAS_MASKED = -60000.0f;   // finite (0 * x stays 0 in the identity MMA) and exp2() of it is 0
+
+inline size_t bias_build_smem(const BiasArgs& a) {
+  return static_cast<size_t>(a.bins2) * a.bins2 * a.heads * 2 + static_cast<size_t>(a.bins1) * a.heads * 4 + a.lut1_n +
+         a.lut2_n + static_cast<size_t>(a.pitch) * 16 + 64;
+}
+
+// thread = 8 consecutive keys j of one query row i; a pass covers blockDim / (pitch/8) rows of one document.
+__global__ void __launch_bounds__(BIAS_THREADS, 1) bias_build_kernel(BiasArgs a) {
+  extern __shared__ __align__(16) uint8_t bsm[];
+  const int n_t2 = a.bins2 * a.bins2 * a.heads;
+  __half* s_t2 = reinterpret_cast<__half*>(bsm);
+  float* s_t1 = reinterpret_cast<float*>(bsm + static_cast<size_t>(n_t2) * 2);
+  int* s_pos = reinterpret_cast<int*>(s_t1 + a.bins1 * a.heads);      // [pitch] each
+  int* s_x = s_pos + a.pitch;
+  int* s_y = s_x + a.pitch;
+  int* s_m = s_y + a.pitch;                                           // 1 = masked key
+  uint8_t* s_l1 = reinterpret_cast<uint8_t*>(s_m + a.pitch);
+  uint8_t* s_l2 = s_l1 + a.lut1_n;
+  for (int i = threadIdx.x; i < n_t2 / 8; i += blockDim.x)
+    reinterpret_cast<uint4*>(s_t2)[i] = __ldg(reinterpret_cast<const uint4*>(a.t2) + i);
+  for (int i = threadIdx.x; i < a.bins1 * a.heads; i += blockDim.x) s_t1[i] = a.t1[i];
+  for (int i = threadIdx.x; i < a.lut1_n; i += blockDim.x) s_l1[i] = a.lut1[i];
+  for (int i = threadIdx.x; i < a.lut2_n; i += blockDim.x) s_l2[i] = a.lut2[i];
+
+  const int chunks = a.pitch >> 3;                      // threads per row
+  const int rows_pp = blockDim.x / chunks;              // rows per pass
+  const int passes = (a.seq + rows_pp - 1) / rows_pp;   // per document
+  const int units = a.B * passes;
+  const int u_lo = static_cast<int>(static_cast<long long>(units) * blockIdx.x / gridDim.x);
+  const int u_hi = static_cast<int>(static_cast<long long>(units) * (blockIdx.x + 1) / gridDim.x);
+  const int rl = threadIdx.x / chunks;                  // row within the pass
+  const int j0 = (threadIdx.x - rl * chunks) * 8;
+  const bool active = rl < rows_pp;
+  const int half1 = a.bins1 >> 1, half2 = a.bins2 >> 1;
+  int cur_doc = -1;
+  for (int u = u_lo; u < u_hi; ++u) {
+    const int doc = u / passes;
+    const int i = (u - doc * passes) * rows_pp + rl;
+    if (doc != cur_doc) {                               // (re)load this document's key coordinates
+      __syncthreads();
+      for (int t = threadIdx.x; t < a.pitch; t += blockDim.x) {
+        int pos = 0, x0 = 0, y1 = 0, m = 1;
+        if (t < a.seq) {
+          if (t < a.n_text) {
+            const int64_t* bb = a.bbox + (static_cast<size_t>(doc) * a.n_text + t) * 4;
+            pos = t; x0 = static_cast<int>(bb[0]); y1 = static_cast<int>(bb[3]);
+          } else {
+            const int p = t - a.n_text;
+            pos = p; x0 = a.vis_bbox[p * 4 + 0]; y1 = a.vis_bbox[p * 4 + 3];
+          }
+          m = a.maskadd[static_cast<size_t>(doc) * a.kv_pitch + t] < 0.f ? 1 : 0;
+        }
+        s_pos[t] = pos; s_x[t] = x0; s_y[t] = y1; s_m[t] = m;
       }
-      packed[k >> 2] |= u << ((k & 3) * 8);
+      cur_doc = doc;
+      __syncthreads();
     }
-    *reinterpret_cast<uint4*>(out + h * head_stride) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    if (!active || i >= a.seq) continue;
+    const int pi = s_pos[i], xi = s_x[i], yi = s_y[i];
+    uint32_t i1[8], i2[8];
+    uint32_t mbits = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = j0 + k;
+      const int r1 = s_pos[j] - pi, rx = s_x[j] - xi, ry = s_y[j] - yi;
+      const int b1 = (r1 > 0 ? half1 : 0) + s_l1[min(abs(r1), a.lut1_n - 1)];
+      const int bx = (rx > 0 ? half2 : 0) + s_l2[min(abs(rx), a.lut2_n - 1)];
+      const int by = (ry > 0 ? half2 : 0) + s_l2[min(abs(ry), a.lut2_n - 1)];
+      i1[k] = static_cast<uint32_t>(b1 * a.heads);
+      i2[k] = static_cast<uint32_t>((bx * a.bins2 + by) * a.heads);
+      mbits |= static_cast<uint32_t>(s_m[j]) << k;
+    }
+    __half* out = a.out + ((static_cast<size_t>(doc) * a.heads) * a.seq + i) * a.pitch + j0;
+    const size_t head_stride = static_cast<size_t>(a.seq) * a.pitch;
+    for (int h = 0; h < a.heads; h += 2) {
+      float v0[8], v1[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float2 t1 = *reinterpret_cast<const float2*>(s_t1 + i1[k] + h);
+        const float2 t2 = __half22float2(*reinterpret_cast<const __half2*>(s_t2 + i2[k] + h));
+        const bool m = (mbits >> k) & 1u;
+        v0[k] = m ? BIAS_MASKED : t1.x + t2.x;
+        v1[k] = m ? BIAS_MASKED : t1.y + t2.y;
+      }
+      auto pack = [](float lo, float hi) {
+        __half2 t = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&t);
+      };
+      *reinterpret_cast<uint4*>(out + h * head_stride) =
+          make_uint4(pack(v0[0], v0[1]), pack(v0[2], v0[3]), pack(v0[4], v0[5]), pack(v0[6], v0[7]));
+      *reinterpret_cast<uint4*>(out + (h + 1) * head_stride) =
+          make_uint4(pack(v1[0], v1[1]), pack(v1[2], v1[3]), pack(v1[4], v1[5]), pack(v1[6], v1[7]));
+    }
   }
 }
 

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmee.so")
+LIB_PATH = os.environ.get("MMEE_LIB", os.path.join(_HERE, "libmmee.so"))   # MMEE_LIB: developer override for A/B runs
 MMEE_MAX_EXITS = 64
 
 EXPORTED_SYMBOLS = [

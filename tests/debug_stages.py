@@ -56,14 +56,13 @@ def main():
     X0 = bf16_to_f32(model.debug_read("X0", np.uint16, n * S * H)).reshape(n, S, H)
     rep("X0 text", X0[:, :T], x0[:, :T].numpy())
     rep("X0 visual", X0[:, T:], x0[:, T:].numpy())
-    pitch = ((S + 15) // 16) * 16
+    pitch = ((S + 63) // 64) * 64
     LOG2E = 1.4426950408889634
-    B_ = model.debug_read("BIAS", np.uint8, n * h * S * pitch).reshape(n, h, S, pitch)
-    sc2 = model.debug_read("BIAS_SCALE2", np.float32, h)
-    want_b = (bias / 8.0).numpy()
-    got_b = (B_[..., :S].astype(np.float32) - 128.0) * (sc2 / LOG2E)[None, :, None, None]
-    rep("bias(u8)", got_b, want_b)
-    print("bias quantisation step per head", sc2 / LOG2E)
+    B_ = model.debug_read("BIAS", np.float16, n * h * S * pitch).reshape(n, h, S, pitch).astype(np.float32)
+    want_b = (bias / 8.0).numpy() * LOG2E
+    keep = (mask.numpy() > 0)[:, None, None, :] & np.ones_like(want_b, dtype=bool)
+    rep("bias(fp16, log2 domain, unmasked keys)", np.where(keep, B_[..., :S], 0), np.where(keep, want_b, 0))
+    print("bias on masked / padded keys: max", np.where(keep, -1e9, B_[..., :S]).max(), "pitch pad max", B_[..., S:].max())
     QK = bf16_to_f32(model.debug_read("QK", np.uint16, n * S * 2 * H)).reshape(n, S, 2 * H)
     q = parts["q"].transpose(1, 2).reshape(n, S, H).numpy() / 8.0 * LOG2E
     k = parts["k"].transpose(1, 2).reshape(n, S, H).numpy()
