@@ -67,6 +67,86 @@ __device__ __forceinline__ void warp_layernorm(float (&v)[NV], int H, const floa
   }
 }
 
+// LayerNorm of a row held as NV4 float4 per lane (columns 4*(lane + 32*i) .. +3); fp32 two-pass.
+template <int NV4>
+__device__ __forceinline__ void warp_layernorm4(float4 (&v)[NV4], int H, const float* __restrict__ w,
+                                                const float* __restrict__ b, float eps, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / H + eps);
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int c = 4 * (lane + 32 * i);
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c));
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(b + c));
+    v[i].x = (v[i].x - mean) * rstd * w4.x + b4.x;
+    v[i].y = (v[i].y - mean) * rstd * w4.y + b4.y;
+    v[i].z = (v[i].z - mean) * rstd * w4.z + b4.z;
+    v[i].w = (v[i].w - mean) * rstd * w4.w + b4.w;
+  }
+}
+
+// one warp per text token; X row = doc*seq + t.  Vectorised variant: H = 128*NV4 and the six spatial segments
+// (4 x coord + 2 x shape) are multiples of 4 columns, so every lane gathers whole float4s (base: 6 per table).
+template <int NV4>
+__global__ void text_embed_vec_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ bbox,
+                                      const int* __restrict__ posid, EmbedWeights W, __nv_bfloat16* __restrict__ X,
+                                      int n_docs, int n_text, int seq, int H, int coord, int shape, float eps) {
+  const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= n_docs * n_text) return;
+  const int lane = threadIdx.x & 31;
+  const int doc = tok / n_text, t = tok - doc * n_text;
+  const int64_t id = ids[tok];
+  const int pos = posid[tok];
+  const longlong2 b01 = __ldg(reinterpret_cast<const longlong2*>(bbox + static_cast<size_t>(tok) * 4));
+  const longlong2 b23 = __ldg(reinterpret_cast<const longlong2*>(bbox + static_cast<size_t>(tok) * 4) + 1);
+  const int x0 = static_cast<int>(b01.x), y0 = static_cast<int>(b01.y), x1 = static_cast<int>(b23.x),
+            y1 = static_cast<int>(b23.y);
+  const int hh = min(max(y1 - y0, 0), 1023), ww = min(max(x1 - x0, 0), 1023);
+  const float* wrow = W.word + static_cast<size_t>(id) * H;
+  const float* prow = W.pos + static_cast<size_t>(pos) * H;
+  float4 wv[NV4], pv[NV4], sv[NV4], tv[NV4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {                       // all gathers in flight before the first use
+    const int c = 4 * (lane + 32 * i);
+    wv[i] = __ldg(reinterpret_cast<const float4*>(wrow + c));
+    pv[i] = __ldg(reinterpret_cast<const float4*>(prow + c));
+    tv[i] = __ldg(reinterpret_cast<const float4*>(W.type0 + c));
+    const float* sp;
+    if (c < coord) sp = W.x_emb + static_cast<size_t>(x0) * coord + c;
+    else if (c < 2 * coord) sp = W.y_emb + static_cast<size_t>(y0) * coord + (c - coord);
+    else if (c < 3 * coord) sp = W.x_emb + static_cast<size_t>(x1) * coord + (c - 2 * coord);
+    else if (c < 4 * coord) sp = W.y_emb + static_cast<size_t>(y1) * coord + (c - 3 * coord);
+    else if (c < 4 * coord + shape) sp = W.h_emb + static_cast<size_t>(hh) * shape + (c - 4 * coord);
+    else sp = W.w_emb + static_cast<size_t>(ww) * shape + (c - 4 * coord - shape);
+    sv[i] = __ldg(reinterpret_cast<const float4*>(sp));
+  }
+  float4 v[NV4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    // same association as the reference: ((word + type) + pos) + spatial
+    v[i].x = ((wv[i].x + tv[i].x) + pv[i].x) + sv[i].x;
+    v[i].y = ((wv[i].y + tv[i].y) + pv[i].y) + sv[i].y;
+    v[i].z = ((wv[i].z + tv[i].z) + pv[i].z) + sv[i].z;
+    v[i].w = ((wv[i].w + tv[i].w) + pv[i].w) + sv[i].w;
+  }
+  warp_layernorm4<NV4>(v, H, W.ln_emb_w, W.ln_emb_b, eps, lane);
+  warp_layernorm4<NV4>(v, H, W.ln_model_w, W.ln_model_b, eps, lane);
+  __nv_bfloat16* out = X + (static_cast<size_t>(doc) * seq + t) * H;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i)
+    *reinterpret_cast<uint2*>(out + 4 * (lane + 32 * i)) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+}
+
+// generic (scalar) variant for shapes the vectorised kernel does not cover (e.g. large: coord 171 / shape 170)
 // one warp per text token; X row = doc*seq + t
 template <int NV>
 __global__ void text_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ bbox,

@@ -263,12 +263,29 @@ void launch_gemm_t(mmee_engine* e, const CUtensorMap& ta, const CUtensorMap& tb,
   e->launches++;
 }
 
+// BLOCK_N = 256 shapes run on the CTA-pair (cta_group::2) kernel; its weight tensor maps use 128-row boxes
+// (each CTA of the pair stages half of the 256 output columns), see wbox().
+template <int EPI>
+void launch_gemm_pair(mmee_engine* e, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t st) {
+  auto kern = gemm_tc_pair_kernel<EPI>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmPairSmem::DYN_BYTES));
+    configured = true;
+  }
+  kern<<<e->sms & ~1, GEMM_THREADS, GemmPairSmem::DYN_BYTES, st>>>(ta, tb, a);
+  CUDA_OK(cudaGetLastError());
+  e->launches++;
+}
+
 template <int EPI>
 void launch_gemm(mmee_engine* e, int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a,
                  cudaStream_t st) {
-  if (bn == 256) launch_gemm_t<256, EPI>(e, ta, tb, a, st);
+  if (bn == 256) launch_gemm_pair<EPI>(e, ta, tb, a, st);
   else launch_gemm_t<128, EPI>(e, ta, tb, a, st);
 }
+
+int wbox(int bn) { return bn == 256 ? 128 : bn; }   // weight TMA box rows for a GEMM family with BLOCK_N = bn
 
 int pick_bn(int n) { return (n % 256 == 0) ? 256 : 128; }
 
@@ -373,12 +390,12 @@ void finalize(mmee_engine* e) {
     upload_f32(w.bo2, need(e, lp + "output.dense.bias", {H}));
     upload_f32(w.ln2_w, need(e, lp + "output.LayerNorm.weight", {H}));
     upload_f32(w.ln2_b, need(e, lp + "output.LayerNorm.bias", {H}));
-    w.t_wqkv = make_tmap_2d_sw128(w.wqkv.p, 3 * H, H, H, e->bn_qkv);
-    w.t_wo = make_tmap_2d_sw128(w.wo.p, H, H, H, e->bn_h);
-    w.t_wi = make_tmap_2d_sw128(w.wi.p, I, H, H, e->bn_i);
-    w.t_wo2 = make_tmap_2d_sw128(w.wo2.p, H, I, I, e->bn_h);
+    w.t_wqkv = make_tmap_2d_sw128(w.wqkv.p, 3 * H, H, H, wbox(e->bn_qkv));
+    w.t_wo = make_tmap_2d_sw128(w.wo.p, H, H, H, wbox(e->bn_h));
+    w.t_wi = make_tmap_2d_sw128(w.wi.p, I, H, H, wbox(e->bn_i));
+    w.t_wo2 = make_tmap_2d_sw128(w.wo2.p, H, I, I, wbox(e->bn_h));
   }
-  e->t_patch_w = make_tmap_2d_sw128(e->patch_w.p, H, e->kdim_patch, e->kdim_patch, e->bn_h);
+  e->t_patch_w = make_tmap_2d_sw128(e->patch_w.p, H, e->kdim_patch, e->kdim_patch, wbox(e->bn_h));
 
   const int n_head_out = d.head_kind == 0 ? d.n_labels : 2;
   e->exit_heads.resize(d.n_exits);
@@ -421,7 +438,7 @@ void finalize(mmee_engine* e) {
 
 void allocate(mmee_engine* e) {
   const int B = e->max_batch, S = e->S, H = e->H, I = e->I, heads = e->heads;
-  e->m_max = ((B * S + 127) / 128) * 128 + 128;
+  e->m_max = ((B * S + 255) / 256) * 256 + 128;
   const size_t M = e->m_max;
   for (int i = 0; i < 2; ++i) e->X[i].alloc(M * H, true);
   e->QK.alloc(M * 2 * H, true);
@@ -430,7 +447,7 @@ void allocate(mmee_engine* e) {
   e->A1.alloc(M * H, true);
   e->MID.alloc(M * I, true);
   e->Y.alloc(M * H, true);
-  const size_t mp = (static_cast<size_t>(B) * e->n_patch + 127) / 128 * 128 + 128;
+  const size_t mp = (static_cast<size_t>(B) * e->n_patch + 255) / 256 * 256 + 128;
   e->PATCH.alloc(mp * e->kdim_patch, true);
   e->VIS.alloc(static_cast<size_t>(B) * e->n_vis * H, true);
   e->POOL.alloc(static_cast<size_t>(B) * H, true);
@@ -518,10 +535,29 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
 
   posid_kernel<<<(B + 7) / 8, 256, 0, st>>>(ids, e->posid.p, B, T, d.pad_id);
   e->launches++;
-  launch_nv(H, [&](auto nv) {
-    text_embed_kernel<decltype(nv)::value><<<(B * T + 7) / 8, 256, 0, st>>>(
-        ids, bbox, e->posid.p, ew, e->X[0].p, B, T, S, H, d.coord, d.shape, d.ln_eps);
-  });
+  if (H % 128 == 0 && d.coord % 4 == 0 && d.shape % 4 == 0 && H / 128 <= 8) {
+    auto go = [&](auto nv4) {
+      text_embed_vec_kernel<decltype(nv4)::value><<<(B * T + 7) / 8, 256, 0, st>>>(
+          ids, bbox, e->posid.p, ew, e->X[0].p, B, T, S, H, d.coord, d.shape, d.ln_eps);
+    };
+    switch (H / 128) {
+      case 1: go(std::integral_constant<int, 1>{}); break;
+      case 2: go(std::integral_constant<int, 2>{}); break;
+      case 4: go(std::integral_constant<int, 4>{}); break;
+      case 6: go(std::integral_constant<int, 6>{}); break;
+      case 8: go(std::integral_constant<int, 8>{}); break;
+      default:
+        launch_nv(H, [&](auto nv) {
+          text_embed_kernel<decltype(nv)::value><<<(B * T + 7) / 8, 256, 0, st>>>(
+              ids, bbox, e->posid.p, ew, e->X[0].p, B, T, S, H, d.coord, d.shape, d.ln_eps);
+        });
+    }
+  } else {
+    launch_nv(H, [&](auto nv) {
+      text_embed_kernel<decltype(nv)::value><<<(B * T + 7) / 8, 256, 0, st>>>(
+          ids, bbox, e->posid.p, ew, e->X[0].p, B, T, S, H, d.coord, d.shape, d.ln_eps);
+    });
+  }
   e->launches++;
   {
     const size_t total = static_cast<size_t>(B) * e->n_patch * e->kdim_patch / 4;

@@ -81,6 +81,111 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return x * phi;
 }
 
+// Epilogue of one 128-row x BLOCK_N accumulator for one epilogue warp (TMEM lane quarter `quarter`, column half
+// `half`): TMEM -> registers -> (+bias, activation) -> per-warp swizzled smem transpose -> coalesced global stores.
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, int m0, int n0, uint32_t tmem_acc,
+                                                   uint8_t* stg, int quarter, int half, int lane) {
+      const int row_base = m0 + quarter * 32;     // first row of this warp's 32-row slab
+      const int row = row_base + lane;
+      const bool row_ok = row < M;
+      const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
+
+#pragma unroll 1
+      for (int c = half * (BLOCK_N / 2); c < (half + 1) * (BLOCK_N / 2); c += 32) {
+        const int n = n0 + c;
+        uint2 rs[8];
+        if constexpr (EPI == EPI_RESID_F32) {       // residual loads first: independent of the accumulator
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int grow = row_base + (lane >> 3) + 4 * i;
+            rs[i] = (grow < M) ? __ldg(reinterpret_cast<const uint2*>(args.resid + static_cast<size_t>(grow) * args.N + n + (lane & 7) * 4))
+                               : make_uint2(0u, 0u);
+          }
+        }
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        float bv[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + n) + q);
+          bv[q * 4 + 0] = b4.x; bv[q * 4 + 1] = b4.y; bv[q * 4 + 2] = b4.z; bv[q * 4 + 3] = b4.w;
+        }
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bv[j];
+
+        if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_QKV) {
+          bool transposed_v = false;
+          if constexpr (EPI == EPI_QKV) transposed_v = (n >= args.qk_cols);
+          if (!transposed_v) {
+            // bf16 row slab: 64 B per row; thread = row writes 4 x 16 B chunks (chunk ^ ((row>>1)&3): conflict-free)
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float g[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) g[j] = (EPI == EPI_GELU_BF16) ? gelu_erf_fast(f[q * 8 + j]) : f[q * 8 + j];
+              *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
+                             pack_bf16x2(g[6], g[7]));
+            }
+            __syncwarp();
+            // 4 lanes cover one row's 64 B; 8 rows per store instruction
+            __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(args.out);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = (lane >> 2) + 8 * i, q = lane & 3;
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
+              if (row_base + r < M)
+                *reinterpret_cast<uint4*>(outp + static_cast<size_t>(row_base + r) * args.ld_out + n + q * 8) = val;
+            }
+          } else if (row_ok) {
+            // V is stored transposed per (doc, head): vt[d][token] so that P*V takes a K-major B operand.
+            const int doc = row / args.seq;
+            const int tok = row - doc * args.seq;
+            const int nv = n - args.qk_cols;        // 32-aligned => one head per chunk
+            const int head = nv >> 6;
+            const int d0 = nv & 63;
+            __nv_bfloat16* dst = args.vt +
+                (static_cast<size_t>(doc * args.heads + head) * 64 + d0) * args.kv_pitch + tok;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * args.kv_pitch] = __float2bfloat16_rn(f[j]);
+          }
+        } else {
+          // fp32 row slab: 128 B per row; thread = row writes 8 x 16 B chunks (chunk ^ (row&7): conflict-free)
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                make_float4(f[q * 4 + 0], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+          __syncwarp();
+          // 8 lanes cover one row's 128 B; 4 rows per store instruction; residual / pos-embed added here (coalesced)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = (lane >> 3) + 4 * i, q = lane & 7;
+            float4 val = *reinterpret_cast<const float4*>(stg + r * 128 + ((q ^ (r & 7)) << 4));
+            const int grow = row_base + r;
+            if (grow < M) {
+              if constexpr (EPI == EPI_RESID_F32) {
+                const float2 r0 = unpack_bf16x2(rs[i].x), r1 = unpack_bf16x2(rs[i].y);
+                val.x += r0.x; val.y += r0.y; val.z += r1.x; val.w += r1.y;
+                *reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(grow) * args.ld_out + n + q * 4) = val;
+              } else {   // EPI_PATCH
+                const int doc = grow / args.n_patch;
+                const int p = grow - doc * args.n_patch;
+                const float4 pe = __ldg(reinterpret_cast<const float4*>(args.pos + static_cast<size_t>(1 + p) * args.N + n + q * 4));
+                val.x += pe.x; val.y += pe.y; val.z += pe.z; val.w += pe.w;
+                *reinterpret_cast<float4*>(static_cast<float*>(args.out) +
+                    (static_cast<size_t>(doc) * args.n_vis + 1 + p) * args.ld_out + n + q * 4) = val;
+              }
+            }
+          }
+        }
+      }
+}
+
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -202,104 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row_base = m0 + quarter * 32;     // first row of this warp's 32-row slab
-      const int row = row_base + lane;
-      const bool row_ok = row < M;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-
-#pragma unroll 1
-      for (int c = half * (BLOCK_N / 2); c < (half + 1) * (BLOCK_N / 2); c += 32) {
-        const int n = n0 + c;
-        uint2 rs[8];
-        if constexpr (EPI == EPI_RESID_F32) {       // residual loads first: independent of the accumulator
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int grow = row_base + (lane >> 3) + 4 * i;
-            rs[i] = (grow < M) ? __ldg(reinterpret_cast<const uint2*>(args.resid + static_cast<size_t>(grow) * args.N + n + (lane & 7) * 4))
-                               : make_uint2(0u, 0u);
-          }
-        }
-        uint32_t v[32];
-        tmem_ld32(taddr + c, v);
-        float bv[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + n) + q);
-          bv[q * 4 + 0] = b4.x; bv[q * 4 + 1] = b4.y; bv[q * 4 + 2] = b4.z; bv[q * 4 + 3] = b4.w;
-        }
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bv[j];
-
-        if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_QKV) {
-          bool transposed_v = false;
-          if constexpr (EPI == EPI_QKV) transposed_v = (n >= args.qk_cols);
-          if (!transposed_v) {
-            // bf16 row slab: 64 B per row; thread = row writes 4 x 16 B chunks (chunk ^ ((row>>1)&3): conflict-free)
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float g[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) g[j] = (EPI == EPI_GELU_BF16) ? gelu_erf_fast(f[q * 8 + j]) : f[q * 8 + j];
-              *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
-                  make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
-                             pack_bf16x2(g[6], g[7]));
-            }
-            __syncwarp();
-            // 4 lanes cover one row's 64 B; 8 rows per store instruction
-            __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(args.out);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = (lane >> 2) + 8 * i, q = lane & 3;
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
-              if (row_base + r < M)
-                *reinterpret_cast<uint4*>(outp + static_cast<size_t>(row_base + r) * args.ld_out + n + q * 8) = val;
-            }
-          } else if (row_ok) {
-            // V is stored transposed per (doc, head): vt[d][token] so that P*V takes a K-major B operand.
-            const int doc = row / args.seq;
-            const int tok = row - doc * args.seq;
-            const int nv = n - args.qk_cols;        // 32-aligned => one head per chunk
-            const int head = nv >> 6;
-            const int d0 = nv & 63;
-            __nv_bfloat16* dst = args.vt +
-                (static_cast<size_t>(doc * args.heads + head) * 64 + d0) * args.kv_pitch + tok;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * args.kv_pitch] = __float2bfloat16_rn(f[j]);
-          }
-        } else {
-          // fp32 row slab: 128 B per row; thread = row writes 8 x 16 B chunks (chunk ^ (row&7): conflict-free)
-          __syncwarp();
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-                make_float4(f[q * 4 + 0], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
-          __syncwarp();
-          // 8 lanes cover one row's 128 B; 4 rows per store instruction; residual / pos-embed added here (coalesced)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = (lane >> 3) + 4 * i, q = lane & 7;
-            float4 val = *reinterpret_cast<const float4*>(stg + r * 128 + ((q ^ (r & 7)) << 4));
-            const int grow = row_base + r;
-            if (grow < M) {
-              if constexpr (EPI == EPI_RESID_F32) {
-                const float2 r0 = unpack_bf16x2(rs[i].x), r1 = unpack_bf16x2(rs[i].y);
-                val.x += r0.x; val.y += r0.y; val.z += r1.x; val.w += r1.y;
-                *reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(grow) * args.ld_out + n + q * 4) = val;
-              } else {   // EPI_PATCH
-                const int doc = grow / args.n_patch;
-                const int p = grow - doc * args.n_patch;
-                const float4 pe = __ldg(reinterpret_cast<const float4*>(args.pos + static_cast<size_t>(1 + p) * args.N + n + q * 4));
-                val.x += pe.x; val.y += pe.y; val.z += pe.z; val.w += pe.w;
-                *reinterpret_cast<float4*>(static_cast<float*>(args.out) +
-                    (static_cast<size_t>(doc) * args.n_vis + 1 + p) * args.ld_out + n + q * 4) = val;
-              }
-            }
-          }
-        }
-      }
+      gemm_epilogue_warp<BLOCK_N, EPI>(args, M, m0, n0, tmem_base + acc * BLOCK_N, stg, quarter, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -312,6 +320,146 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile.  Each CTA stages
+// its own 128 rows of A and HALF of the weight tile (128 of the 256 output columns); the pair's tensor cores read
+// both halves, so every k-block moves 32 KB per SM through L2 instead of 48 KB (the single-CTA kernel is bound by
+// L2 -> SM operand traffic at these shapes, see profiles/).  The leader (cluster rank 0) issues every MMA; its
+// tcgen05.commit is multicast to the stage / accumulator barriers of both CTAs; both CTAs' epilogue warps release
+// the accumulator on the leader's barrier.  Epilogue as above, each CTA for its own 128 rows.
+struct GemmPairSmem {
+  static constexpr int STAGES = 5;
+  static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;       // 16 KB
+  static constexpr int B_BYTES = 128 * GEMM_BLOCK_K * 2;                // 16 KB: this CTA's half of the 256 columns
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STG_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = STG_OFF + GEMM_EPI_WARPS * 4096;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL;                               // dynamic smem base is 1024 B aligned
+};
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmArgs args) {
+  using SM = GemmPairSmem;
+  constexpr int STAGES = SM::STAGES;
+  constexpr int BLOCK_N = 256;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sb = smem_u32(smem);
+  if (sb & 1023u) __trap();
+  const uint32_t full_bar = sb + SM::BAR_OFF;                  // [STAGES]  (used in the leader only)
+  const uint32_t empty_bar = full_bar + STAGES * 8;            // [STAGES]  local to each CTA
+  const uint32_t tmem_full = empty_bar + STAGES * 8;           // [2]       local to each CTA
+  const uint32_t tmem_empty = tmem_full + 2 * 8;               // [2]       (used in the leader only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int M = args.m_dev ? *args.m_dev : args.m_static;
+  const int m_blocks = (M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);      // 256-row tiles
+  const int n_blocks = args.N / BLOCK_N;
+  const int k_blocks = args.K / GEMM_BLOCK_K;
+  const int total_tiles = m_blocks * n_blocks;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(bars + i, 1);                       // full: the leader's expect_tx arrival
+      mbar_init(bars + STAGES + i, 1);              // empty: multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bars + 2 * STAGES + i, 1);                          // tmem_full: multicast commit
+      mbar_init(bars + 2 * STAGES + 2 + i, 2 * GEMM_EPI_WARPS);     // tmem_empty: epilogue warps of both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_pair<512>(tmem_base_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        const int m0 = (tile / n_blocks) * 2 * GEMM_BLOCK_M + static_cast<int>(rank) * GEMM_BLOCK_M;
+        const int n0 = (tile % n_blocks) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar + stage * 8, phase ^ 1);
+          const uint32_t sa = sb + stage * SM::STAGE_BYTES;
+          if (leader) mbar_expect_tx(full_bar + stage * 8, 2 * SM::STAGE_BYTES);   // both CTAs' bytes land on it
+          tma_load_2d_pair(sa, &tmap_a, full_bar + stage * 8, kb * GEMM_BLOCK_K, m0);
+          tma_load_2d_pair(sa + SM::A_BYTES, &tmap_b, full_bar + stage * 8, kb * GEMM_BLOCK_K, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        mbar_wait(tmem_empty + acc * 8, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar + stage * 8, phase);
+          tc_fence_after();
+          const uint32_t sa = sb + stage * SM::STAGE_BYTES;
+          const uint64_t da = umma_desc_sw128_kmajor(sa);
+          const uint64_t db = umma_desc_sw128_kmajor(sa + SM::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
+            umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit_pair(empty_bar + stage * 8);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(tmem_full + acc * 8);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (2..9), both CTAs
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    uint8_t* stg = smem + SM::STG_OFF + (warp - 2) * 4096;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+      const int m0 = (tile / n_blocks) * 2 * GEMM_BLOCK_M + static_cast<int>(rank) * GEMM_BLOCK_M;
+      const int n0 = (tile % n_blocks) * BLOCK_N;
+      mbar_wait(tmem_full + acc * 8, acc_phase);
+      tc_fence_after();
+      gemm_epilogue_warp<BLOCK_N, EPI>(args, M, m0, n0, tmem_base + acc * BLOCK_N, stg, quarter, half, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tmem_empty + acc * 8, 0);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair<512>(tmem_base);
   }
 }
 

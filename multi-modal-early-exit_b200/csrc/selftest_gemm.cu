@@ -43,8 +43,15 @@ __global__ void ref_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, const f
   C[(size_t)m * N + n] = acc + bias[n];
 }
 
+static bool g_pair = false;      // use the CTA-pair kernel (BN must be 256; tb then has 128-row boxes)
 template <int BN, int EPI>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int sms, cudaStream_t st = 0) {
+  if (g_pair && BN == 256) {
+    auto kp = gemm_tc_pair_kernel<EPI>;
+    CK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmPairSmem::DYN_BYTES));
+    kp<<<sms & ~1, GEMM_THREADS, GemmPairSmem::DYN_BYTES, st>>>(ta, tb, a);
+    return;
+  }
   auto kern = gemm_tc_kernel<BN, EPI>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::DYN_BYTES));
   kern<<<sms, GEMM_THREADS, GemmSmem<BN>::DYN_BYTES, st>>>(ta, tb, a);
@@ -54,7 +61,7 @@ static double gelu_ref(double x) { return 0.5 * x * (1.0 + erf(x / sqrt(2.0))); 
 
 template <int BN, int EPI>
 static int run_case(const char* name, int M, int N, int K, int sms, bool timing) {
-  int Mmax = ((M + 127) / 128) * 128 + 128;
+  int Mmax = ((M + 255) / 256) * 256 + 128;
   __nv_bfloat16 *A, *W, *R, *O16;
   float *bias, *Cref, *O32;
   CK(cudaMalloc(&A, (size_t)Mmax * K * 2));
@@ -74,7 +81,7 @@ static int run_case(const char* name, int M, int N, int K, int sms, bool timing)
   CK(cudaMemset(O16, 0xFF, (size_t)Mmax * N * 2));
   CK(cudaMemset(O32, 0xFF, (size_t)Mmax * N * 4));
   CUtensorMap ta = make_tmap_2d_sw128(A, Mmax, K, K, 128);
-  CUtensorMap tb = make_tmap_2d_sw128(W, N, K, K, BN);
+  CUtensorMap tb = make_tmap_2d_sw128(W, N, K, K, (g_pair && BN == 256) ? 128 : BN);
   GemmArgs a{};
   a.m_dev = m_dev; a.m_static = M; a.N = N; a.K = K; a.bias = bias; a.ld_out = N; a.resid = R;
   a.out = (EPI == EPI_RESID_F32) ? (void*)O32 : (void*)O16;
@@ -141,7 +148,15 @@ int main(int argc, char** argv) {
   bad += run_case<256, EPI_GELU_BF16>("gelu bn256", 2127, 3072, 768, sms, false);
   bad += run_case<256, EPI_RESID_F32>("resid bn256", 2127, 768, 3072, sms, false);
   bad += run_case<128, EPI_RESID_F32>("resid bn128", 1418, 128, 256, sms, false);
-  if (argc > 1) {
+  g_pair = true;
+  printf("-- CTA-pair (cta_group::2) kernel\n");
+  bad += run_case<256, EPI_BIAS_BF16>("pair bias", 2127, 2304, 768, sms, false);
+  bad += run_case<256, EPI_GELU_BF16>("pair gelu", 2127, 3072, 768, sms, false);
+  bad += run_case<256, EPI_RESID_F32>("pair resid", 2127, 768, 3072, sms, false);
+  bad += run_case<256, EPI_RESID_F32>("pair resid small", 100, 768, 768, sms, false);
+  for (int pass = 0; pass < 2 && argc > 1; ++pass) {
+    g_pair = pass == 1;
+    printf(g_pair ? "-- timing, CTA-pair kernel\n" : "-- timing, single-CTA kernel\n");
     int M = 256 * 709;
     bad += run_case<256, EPI_BIAS_BF16>("T qkv", M, 2304, 768, sms, true);
     bad += run_case<256, EPI_GELU_BF16>("T mlp-up gelu", M, 3072, 768, sms, true);
