@@ -122,6 +122,10 @@ struct mmee_engine {
   int sms = 148;
   int bn_h, bn_qkv, bn_i;   // BLOCK_N per GEMM family
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;       // host path: pixel upload overlaps text embedding + bias build
+  cudaEvent_t px_ready = nullptr;           // recorded on copy_stream after the pixel copy
+  cudaEvent_t fwd_start = nullptr;
+  bool px_async = false;                    // forward_device must wait for px_ready before touching pixels
   bool finalized = false;
   int64_t launches = 0;
   bool profiling = false;
@@ -162,6 +166,7 @@ struct mmee_engine {
   DevBuf<int> n_dev, m_dev;                 // [stages]
   DevBuf<int> slot_doc[2], slot_src;        // ping-pong slot->doc; new->old slot map
   DevBuf<int> slot_fire, out_exit;
+  DevBuf<unsigned int> exit_tickets;        // exit_fused_kernel: per-group tickets + groups-done counter
   DevBuf<float> slot_logits, slot_head, slot_crit, out_logits, out_crit, all_logits, all_head, all_crit;
   DevBuf<unsigned long long> hist;
   DevBuf<long long> hist64;
@@ -178,6 +183,9 @@ struct mmee_engine {
     if (pin_out) cudaFreeHost(pin_out);
     for (auto& e : ev) cudaEventDestroy(e.second);
     if (stream) cudaStreamDestroy(stream);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (px_ready) cudaEventDestroy(px_ready);
+    if (fwd_start) cudaEventDestroy(fwd_start);
   }
 };
 
@@ -483,6 +491,7 @@ void allocate(mmee_engine* e) {
   e->slot_doc[1].alloc(B);
   e->slot_src.alloc(B);
   e->slot_fire.alloc(B);
+  e->exit_tickets.alloc((B + EXF_DOCS - 1) / EXF_DOCS + 1, true);
   e->out_exit.alloc(B);
   const int K = e->K, E1 = e->d.n_exits + 1;
   e->slot_logits.alloc(static_cast<size_t>(B) * K);
@@ -559,21 +568,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     });
   }
   e->launches++;
-  {
-    const size_t total = static_cast<size_t>(B) * e->n_patch * e->kdim_patch / 4;
-    im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(px, e->PATCH.p, B, d.image, d.patch,
-                                                                              d.channels);
-    e->launches++;
-    GemmArgs ga{};
-    ga.m_dev = nullptr; ga.m_static = B * e->n_patch; ga.N = H; ga.K = e->kdim_patch; ga.bias = e->patch_b.p;
-    ga.out = e->VIS.p; ga.ld_out = H; ga.pos = e->pos_embed.p; ga.n_patch = e->n_patch; ga.n_vis = e->n_vis;
-    launch_gemm<EPI_PATCH>(e, e->bn_h, e->t_patch, e->t_patch_w, ga, st);
-    launch_nv(H, [&](auto nv) {
-      visual_ln_kernel<decltype(nv)::value><<<(B * e->n_vis + 7) / 8, 256, 0, st>>>(
-          e->VIS.p, ew, e->X[0].p, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps);
-    });
-    e->launches++;
-  }
+  // pixel-independent work first: on the host path the pixel upload (96 % of the input bytes) overlaps it
   {
     keymask_kernel<<<B, e->kv_pitch, 0, st>>>(mask, e->maskadd.p, e->tileflag.p, T, S, e->kv_pitch, e->n_kv_tiles, ATT_BKV);
     BiasArgs ba;
@@ -593,6 +588,22 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     CUDA_OK(cudaGetLastError());
     e->launches += 2;
   }
+  {
+    const size_t total = static_cast<size_t>(B) * e->n_patch * e->kdim_patch / 4;
+    if (e->px_async) CUDA_OK(cudaStreamWaitEvent(st, e->px_ready, 0));
+    im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(px, e->PATCH.p, B, d.image, d.patch,
+                                                                              d.channels);
+    e->launches++;
+    GemmArgs ga{};
+    ga.m_dev = nullptr; ga.m_static = B * e->n_patch; ga.N = H; ga.K = e->kdim_patch; ga.bias = e->patch_b.p;
+    ga.out = e->VIS.p; ga.ld_out = H; ga.pos = e->pos_embed.p; ga.n_patch = e->n_patch; ga.n_vis = e->n_vis;
+    launch_gemm<EPI_PATCH>(e, e->bn_h, e->t_patch, e->t_patch_w, ga, st);
+    launch_nv(H, [&](auto nv) {
+      visual_ln_kernel<decltype(nv)::value><<<(B * e->n_vis + 7) / 8, 256, 0, st>>>(
+          e->VIS.p, ew, e->X[0].p, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps);
+    });
+    e->launches++;
+  }
   mark(e, "embed", st);
 
   e->meta_stage = -1;
@@ -603,47 +614,39 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
 
   auto run_exit = [&](const float* rows, size_t row_stride, const float* ln_w, const float* ln_b,
                       const HeadW& head, bool is_final, const int* rows_slot_src) {
-    const int* nact = e->n_dev.p + stage;
-    ExitRowsArgs ra{};
-    ra.rows = rows; ra.row_stride = row_stride; ra.slot_src = rows_slot_src; ra.ln_w = ln_w; ra.ln_b = ln_b;
-    ra.ln_eps = d.ln_eps; ra.H = H; ra.n_active_dev = nact; ra.Z = e->Z.p;
-    exit_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(ra);
-    e->launches++;
+    // one fused launch: CLS rows (+LN) -> dense/tanh -> out_proj, temperature, criterion, threshold -> compaction
     const bool use_cls = gate && !is_final;               // class logits = classifier(CLS_j) ("gated logits")
     const bool need_head = !use_cls || want_all;          // the 2-way gate output is only an API output
-    ExitDenseArgs da{};
-    da.Z = e->Z.p; da.H = H; da.n_active_dev = nact;
+    ExitFusedArgs xa{};
+    xa.rows = rows; xa.row_stride = row_stride; xa.slot_src = rows_slot_src; xa.ln_w = ln_w; xa.ln_b = ln_b;
+    xa.ln_eps = d.ln_eps; xa.H = H; xa.n_active_dev = e->n_dev.p + stage;
     int jobs = 0;
-    const float* in_head = e->Z.p;
-    const float* in_cls = e->Z.p;
-    if (need_head && head.two_layer) {
-      da.w[jobs] = head.dense_w.p; da.b[jobs] = head.dense_b.p; da.T[jobs] = e->T0.p; in_head = e->T0.p; ++jobs;
+    xa.head_src = -1; xa.cls_src = -1;
+    if (need_head) {
+      if (head.two_layer) {
+        xa.w[jobs] = head.dense_w.p; xa.b[jobs] = head.dense_b.p; xa.T[jobs] = e->T0.p; xa.head_src = jobs; ++jobs;
+      } else {
+        xa.head_src = 2;
+      }
     }
     if (use_cls) {
-      da.w[jobs] = e->classifier.dense_w.p; da.b[jobs] = e->classifier.dense_b.p; da.T[jobs] = e->T1.p;
-      in_cls = e->T1.p; ++jobs;
+      xa.w[jobs] = e->classifier.dense_w.p; xa.b[jobs] = e->classifier.dense_b.p; xa.T[jobs] = e->T1.p; xa.cls_src = jobs; ++jobs;
     }
-    if (jobs) {
-      exit_dense_kernel<<<dim3(H / EXD_FEATS, (B + EXD_DOCS - 1) / EXD_DOCS, jobs), 256, 0, st>>>(da);
-      e->launches++;
-    }
-    ExitOutArgs xa{};
-    xa.in_head = in_head; xa.in_cls = in_cls;
+    xa.jobs = jobs;
     xa.head = head.view();
     if (!need_head) xa.head.out_w = nullptr;
     xa.cls = e->classifier.view();
     xa.gate_mode = use_cls ? 1 : 0;
-    xa.H = H; xa.n_labels = K;
+    xa.n_labels = K;
     xa.criterion = pol->criterion;
     const float Te = pol->temperatures ? pol->temperatures[exit_no] : 1.f;
     xa.inv_temp = 1.0f / Te;
     xa.threshold = is_final ? 0.f : pol->thresholds[exit_no];
     xa.force = is_final ? 1 : 0;
-    xa.n_active_dev = nact;
     xa.slot_logits = e->slot_logits.p; xa.slot_head = e->slot_head.p; xa.slot_crit = e->slot_crit.p;
     xa.slot_fire = e->slot_fire.p;
-    exit_out_kernel<<<(B + 7) / 8, 256, 0, st>>>(xa);
-    CompactArgs ca{};
+    xa.group_ticket = e->exit_tickets.p; xa.groups_done = e->exit_tickets.p + (e->max_batch + EXF_DOCS - 1) / EXF_DOCS;
+    CompactArgs& ca = xa.compact;
     ca.n_active_dev = e->n_dev.p + stage; ca.n_next_dev = e->n_dev.p + stage + 1; ca.m_next_dev = e->m_dev.p + stage + 1;
     ca.seq = S; ca.slot_doc = e->slot_doc[sd].p; ca.next_slot_doc = e->slot_doc[sd ^ 1].p;
     ca.next_slot_src = e->slot_src.p; ca.slot_fire = e->slot_fire.p; ca.slot_logits = e->slot_logits.p;
@@ -653,8 +656,16 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     ca.out_logits = e->out_logits.p; ca.out_crit = e->out_crit.p; ca.out_exit = e->out_exit.p;
     ca.all_logits = want_all ? e->all_logits.p : nullptr; ca.all_head = want_all ? e->all_head.p : nullptr;
     ca.all_crit = want_all ? e->all_crit.p : nullptr; ca.B = B; ca.n_head_max = K; ca.hist = e->hist.p;
-    compact_kernel<<<1, 1024, 0, st>>>(ca);
-    e->launches += 2;
+    const size_t smem = exit_fused_smem(H);
+    static bool configured = false;
+    if (!configured) {
+      CUDA_OK(cudaFuncSetAttribute(exit_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      configured = true;
+    }
+    const dim3 grid(jobs ? H / EXF_FEATS : 1, (B + EXF_DOCS - 1) / EXF_DOCS, jobs ? jobs : 1);
+    exit_fused_kernel<<<grid, EXF_THREADS, smem, st>>>(xa);
+    CUDA_OK(cudaGetLastError());
+    e->launches++;
     stage += 1; sd ^= 1; exit_no += 1;
   };
 
@@ -754,13 +765,16 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   // ---- results (device -> caller's device buffers)
   hist_to_i64_kernel<<<1, 64, 0, st>>>(e->hist.p, e->hist64.p, E1);
   e->launches++;
-  CUDA_OK(cudaMemcpyAsync(out->logits, e->out_logits.p, static_cast<size_t>(B) * K * 4, cudaMemcpyDeviceToDevice, st));
-  CUDA_OK(cudaMemcpyAsync(out->exit_index, e->out_exit.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, st));
-  if (out->criterion) CUDA_OK(cudaMemcpyAsync(out->criterion, e->out_crit.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, st));
-  if (out->all_exit_logits) CUDA_OK(cudaMemcpyAsync(out->all_exit_logits, e->all_logits.p, static_cast<size_t>(E1) * B * K * 4, cudaMemcpyDeviceToDevice, st));
-  if (out->all_head_logits) CUDA_OK(cudaMemcpyAsync(out->all_head_logits, e->all_head.p, static_cast<size_t>(E1) * B * K * 4, cudaMemcpyDeviceToDevice, st));
-  if (out->all_criteria) CUDA_OK(cudaMemcpyAsync(out->all_criteria, e->all_crit.p, static_cast<size_t>(E1) * B * 4, cudaMemcpyDeviceToDevice, st));
-  if (out->exit_hist) CUDA_OK(cudaMemcpyAsync(out->exit_hist, e->hist64.p, static_cast<size_t>(E1) * 8, cudaMemcpyDeviceToDevice, st));
+  auto d2d = [&](void* dst, const void* src, size_t bytes) {     // the host path hands in the engine's own buffers
+    if (dst && dst != src) CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+  };
+  d2d(out->logits, e->out_logits.p, static_cast<size_t>(B) * K * 4);
+  d2d(out->exit_index, e->out_exit.p, static_cast<size_t>(B) * 4);
+  d2d(out->criterion, e->out_crit.p, static_cast<size_t>(B) * 4);
+  d2d(out->all_exit_logits, e->all_logits.p, static_cast<size_t>(E1) * B * K * 4);
+  d2d(out->all_head_logits, e->all_head.p, static_cast<size_t>(E1) * B * K * 4);
+  d2d(out->all_criteria, e->all_crit.p, static_cast<size_t>(E1) * B * 4);
+  d2d(out->exit_hist, e->hist64.p, static_cast<size_t>(E1) * 8);
   mark(e, "end", st);
 }
 
@@ -836,6 +850,9 @@ int mmee_create(const mmee_model_desc* desc, int device, int max_batch, mmee_eng
   if ((2 * e->H) % e->bn_qkv) e->bn_qkv = 128;
   try {
     CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&e->px_ready, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&e->fwd_start, cudaEventDisableTiming));
     allocate(e);
   } catch (...) {
     delete e;
@@ -924,23 +941,29 @@ int mmee_forward(mmee_engine* e, int B, const int64_t* input_ids, const int64_t*
     e->in_px.alloc(mb * e->d.channels * e->d.image * e->d.image);
   }
   cudaStream_t st = e->stream;
+  // pixels go up on a second stream and are first needed by im2col, after text embedding and bias build
+  CUDA_OK(cudaEventRecord(e->fwd_start, st));
+  CUDA_OK(cudaStreamWaitEvent(e->copy_stream, e->fwd_start, 0));       // previous forward has released in_px
+  CUDA_OK(cudaMemcpyAsync(e->in_px.p, pixel_values, n_px * 4, cudaMemcpyHostToDevice, e->copy_stream));
+  CUDA_OK(cudaEventRecord(e->px_ready, e->copy_stream));
   CUDA_OK(cudaMemcpyAsync(e->in_ids.p, input_ids, n_ids * 8, cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemcpyAsync(e->in_bbox.p, bbox, n_ids * 32, cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemcpyAsync(e->in_mask.p, attention_mask, n_ids * 8, cudaMemcpyHostToDevice, st));
-  CUDA_OK(cudaMemcpyAsync(e->in_px.p, pixel_values, n_px * 4, cudaMemcpyHostToDevice, st));
+  e->px_async = true;
   // run with outputs in the engine's own device buffers, then copy what was asked for to the host
   mmee_outputs dv{};
-  dv.logits = e->out_logits.p;       // forward_device copies onto itself harmlessly for these two: use scratch instead
-  DevBuf<float> d_logits, d_crit;
-  DevBuf<int32_t> d_exit;
-  DevBuf<int64_t> d_hist;
-  d_logits.alloc(static_cast<size_t>(B) * K); d_crit.alloc(B); d_exit.alloc(B); d_hist.alloc(E1);
-  dv.logits = d_logits.p; dv.exit_index = d_exit.p; dv.criterion = d_crit.p; dv.exit_hist = reinterpret_cast<int64_t*>(d_hist.p);
-  DevBuf<float> d_all, d_allh, d_allc;
-  if (out->all_exit_logits) { d_all.alloc(static_cast<size_t>(E1) * B * K); dv.all_exit_logits = d_all.p; }
-  if (out->all_head_logits) { d_allh.alloc(static_cast<size_t>(E1) * B * K); dv.all_head_logits = d_allh.p; }
-  if (out->all_criteria) { d_allc.alloc(static_cast<size_t>(E1) * B); dv.all_criteria = d_allc.p; }
-  forward_device(e, B, e->in_ids.p, e->in_bbox.p, e->in_mask.p, e->in_px.p, policy, &dv, st);
+  dv.logits = e->out_logits.p; dv.exit_index = e->out_exit.p; dv.criterion = e->out_crit.p;
+  dv.exit_hist = reinterpret_cast<int64_t*>(e->hist64.p);
+  if (out->all_exit_logits) dv.all_exit_logits = e->all_logits.p;
+  if (out->all_head_logits) dv.all_head_logits = e->all_head.p;
+  if (out->all_criteria) dv.all_criteria = e->all_crit.p;
+  try {
+    forward_device(e, B, e->in_ids.p, e->in_bbox.p, e->in_mask.p, e->in_px.p, policy, &dv, st);
+  } catch (...) {
+    e->px_async = false;
+    throw;
+  }
+  e->px_async = false;
   CUDA_OK(cudaMemcpyAsync(out->logits, dv.logits, static_cast<size_t>(B) * K * 4, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaMemcpyAsync(out->exit_index, dv.exit_index, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, st));
   if (out->criterion) CUDA_OK(cudaMemcpyAsync(out->criterion, dv.criterion, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, st));

@@ -5,11 +5,11 @@
 //                      post-LN write goes straight to the survivor's new slot).  HF:300-304, 509-513.
 //   bias_build_kernel: (rel_pos + rel_2d_pos)/sqrt(d) + key mask, once per forward, reused by every layer
 //                      (EE/models/LayoutLMv3.py:170-179; HF:393-458; mask HF:270-272).
-//   exit_head_kernel : CLS row -> [LN] -> dense/tanh/out_proj (EE/models/LayoutLMv3.py:86-93, 226-227; gate mode
+//   exit_fused_kernel: CLS row -> [LN] -> dense/tanh/out_proj (EE/models/LayoutLMv3.py:86-93, 226-227; gate mode
 //                      also classifier(CLS) :768) -> logits/T -> max-softmax | entropy (EE_modules.py:149-160)
-//                      -> strict threshold test (EE_modules.py:139-143, policy.py:33).
-//   compact_kernel   : block prefix-sum over the fire flags -> survivor list for the next layer, results of
-//                      leaving documents scattered to their original document index; no host round-trip.
+//                      -> strict threshold test (EE_modules.py:139-143, policy.py:33) -> block prefix-sum over
+//                      the fire flags -> survivor list for the next layer, results of leaving documents scattered
+//                      to their original document index; one launch per exit, no host round-trip.
 #pragma once
 #include "embed.cuh"
 #include "ptx.cuh"
@@ -200,118 +200,6 @@ struct HeadWeights {
   int n_out;
 };
 
-// (1) gather the exit input rows of the active slots (+ LayerNorm): Z[slot][H] fp32.  One warp per slot.
-struct ExitRowsArgs {
-  const float* rows;        // fp32 rows; row of slot s starts at rows + src(s) * row_stride
-  size_t row_stride;        // in floats
-  const int* slot_src;      // optional: rows not yet compacted -> src(s) = slot_src[s]
-  const float* ln_w;        // nullptr -> no LayerNorm (mean-pooled embedding exit)
-  const float* ln_b;
-  float ln_eps;
-  int H;
-  const int* n_active_dev;
-  float* Z;                 // [n, H]
-};
-
-__global__ void exit_rows_kernel(ExitRowsArgs a) {
-  const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (slot >= *a.n_active_dev) return;
-  const int lane = threadIdx.x & 31;
-  const int H = a.H;
-  const int src = a.slot_src ? a.slot_src[slot] : slot;
-  const float* r = a.rows + static_cast<size_t>(src) * a.row_stride;
-  float* z = a.Z + static_cast<size_t>(slot) * H;
-  if (!a.ln_w) {
-    for (int c = lane; c < H; c += 32) z[c] = r[c];
-    return;
-  }
-  float s = 0.f;
-  for (int c = lane; c < H; c += 32) s += r[c];
-  const float mean = warp_sum(s) / H;
-  float q = 0.f;
-  for (int c = lane; c < H; c += 32) { const float d = r[c] - mean; q += d * d; }
-  const float rstd = rsqrtf(warp_sum(q) / H + a.ln_eps);
-  for (int c = lane; c < H; c += 32) z[c] = (r[c] - mean) * rstd * __ldg(a.ln_w + c) + __ldg(a.ln_b + c);
-}
-
-// (2) T[w][slot][j] = tanh(sum_k W_w[j,k] Z[slot][k] + b_w[j]) for up to two heads w (exit head, classifier).
-// fp32 SIMT tile: 32 slots x 64 features per CTA, K staged through shared memory in chunks of 32.
-struct ExitDenseArgs {
-  const float* Z;           // [n, H]
-  const float* w[2];        // [H, H] each
-  const float* b[2];
-  float* T[2];              // [n, H] each
-  int H;
-  const int* n_active_dev;
-};
-
-constexpr int EXD_DOCS = 32, EXD_FEATS = 64, EXD_K = 32;
-
-__global__ void __launch_bounds__(256) exit_dense_kernel(ExitDenseArgs a) {
-  __shared__ float sZ[EXD_DOCS][EXD_K + 1];
-  __shared__ float sW[EXD_FEATS][EXD_K + 1];
-  const int n = *a.n_active_dev;
-  const int d0 = blockIdx.y * EXD_DOCS;
-  if (d0 >= n) return;
-  const int f0 = blockIdx.x * EXD_FEATS;
-  const int which = blockIdx.z;
-  const float* __restrict__ W = a.w[which];
-  const int H = a.H;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // 4 features x 2 slots per thread
-  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  for (int k0 = 0; k0 < H; k0 += EXD_K) {
-    for (int i = threadIdx.x; i < EXD_DOCS * EXD_K; i += 256) {
-      const int d = i >> 5, k = i & 31;
-      sZ[d][k] = (d0 + d < n) ? a.Z[static_cast<size_t>(d0 + d) * H + k0 + k] : 0.f;
-    }
-    for (int i = threadIdx.x; i < EXD_FEATS * EXD_K; i += 256) {
-      const int f = i >> 5, k = i & 31;
-      sW[f][k] = __ldg(W + static_cast<size_t>(f0 + f) * H + k0 + k);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < EXD_K; ++k) {
-      const float z0 = sZ[ty * 2][k], z1 = sZ[ty * 2 + 1][k];
-#pragma unroll
-      for (int f = 0; f < 4; ++f) {
-        const float w = sW[tx * 4 + f][k];
-        acc[0][f] = fmaf(w, z0, acc[0][f]);
-        acc[1][f] = fmaf(w, z1, acc[1][f]);
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int dd = 0; dd < 2; ++dd) {
-    const int d = d0 + ty * 2 + dd;
-    if (d >= n) continue;
-#pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      const int j = f0 + tx * 4 + f;
-      a.T[which][static_cast<size_t>(d) * H + j] = tanhf(acc[dd][f] + __ldg(a.b[which] + j));
-    }
-  }
-}
-
-// (3) out_proj + temperature + criterion + strict threshold test.  One warp per slot.
-struct ExitOutArgs {
-  const float* in_head;     // [n, H] input of the exit head's out_proj (tanh(dense) or Z for 1-layer heads)
-  const float* in_cls;      // [n, H] input of the classifier's out_proj (gate mode), else unused
-  HeadWeights head;         // ramp: class logits; gate: 2-way gate logits (skipped when head.out_w == nullptr)
-  HeadWeights cls;          // gate mode: the final classifier ("gated logits", EE/models/LayoutLMv3.py:768)
-  int gate_mode;
-  int H, n_labels;
-  int criterion;            // 0 max_confidence (fire if >), 1 entropy (fire if <)
-  float inv_temp;           // 1/T_e
-  float threshold;
-  int force;                // final classifier: always fires
-  const int* n_active_dev;
-  float* slot_logits;       // [n, n_labels]  class logits of this exit
-  float* slot_head;         // [n, head.n_out] raw head output (gate logits in gate mode)
-  float* slot_crit;         // [n]
-  int* slot_fire;           // [n]
-};
-
 __device__ __forceinline__ float warp_dot(const float* __restrict__ w, const float* __restrict__ x, int H, int lane) {
   float acc = 0.f;
   for (int k = lane * 4; k < H; k += 128) {
@@ -323,50 +211,6 @@ __device__ __forceinline__ float warp_dot(const float* __restrict__ w, const flo
     acc = fmaf(w4.w, x4.w, acc);
   }
   return warp_sum(acc);
-}
-
-__global__ void exit_out_kernel(ExitOutArgs a) {
-  const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (slot >= *a.n_active_dev) return;
-  const int lane = threadIdx.x & 31;
-  const int H = a.H, K = a.n_labels;
-  float head_val = 0.f;                 // lane j holds head logit j
-  if (a.head.out_w) {
-    const float* x = a.in_head + static_cast<size_t>(slot) * H;
-    for (int j = 0; j < a.head.n_out; ++j) {
-      const float v = warp_dot(a.head.out_w + static_cast<size_t>(j) * H, x, H, lane) + __ldg(a.head.out_b + j);
-      if (lane == j) head_val = v;
-    }
-    if (lane < a.head.n_out) a.slot_head[static_cast<size_t>(slot) * a.head.n_out + lane] = head_val;
-  }
-  float raw = head_val;                 // class logit of lane k
-  if (a.gate_mode) {
-    raw = 0.f;
-    const float* x = a.in_cls + static_cast<size_t>(slot) * H;
-    for (int j = 0; j < K; ++j) {
-      const float v = warp_dot(a.cls.out_w + static_cast<size_t>(j) * H, x, H, lane) + __ldg(a.cls.out_b + j);
-      if (lane == j) raw = v;
-    }
-  }
-  if (lane < K) a.slot_logits[static_cast<size_t>(slot) * K + lane] = raw;
-  const float z = raw * a.inv_temp;
-  const float zmax = warp_max(lane < K ? z : -INFINITY);
-  const float e = (lane < K) ? expf(z - zmax) : 0.f;
-  const float A = warp_sum(e);
-  float crit;
-  if (a.criterion == 0) {
-    crit = 1.0f / A;                    // max softmax = exp(0) / sum_k exp(z_k - z_max)
-  } else {
-    // entropy of EE/models/EE_modules.py:149-154, log(sum e^z) - sum z e^z / sum e^z, evaluated max-shifted
-    // (identical in exact arithmetic, finite for any temperature).
-    const float Bz = warp_sum((lane < K) ? (z - zmax) * e : 0.f);
-    crit = logf(A) - Bz / A;
-  }
-  if (lane == 0) {
-    a.slot_crit[slot] = crit;
-    const bool fire = a.force || (a.criterion == 0 ? (crit > a.threshold) : (crit < a.threshold));
-    a.slot_fire[slot] = fire ? 1 : 0;
-  }
 }
 
 // ------------------------------------------------------------------ compaction
@@ -396,47 +240,88 @@ struct CompactArgs {
   unsigned long long* hist;    // [E+1]
 };
 
-// single CTA of 1024 threads; handles any n via a chunked scan.
-__global__ void __launch_bounds__(1024) compact_kernel(CompactArgs a) {
-  __shared__ int s_warp[32];
-  __shared__ int s_total;
-  __shared__ int s_base;
-  __shared__ int s_fired;
+// ------------------------------------------------------------------ fused exit stage (one launch per exit)
+// exit_fused_kernel: CLS rows + LayerNorm, dense + tanh, out_proj + criterion + threshold, and the survivor compaction
+// in ONE launch.  CTA (fb, g, job): documents 16g..16g+15 of the active slots, dense features
+// 32fb..32fb+31 of head `job`:
+//   1. LayerNorm of the group's CLS rows into shared memory (fp32, two-pass; redundant per feature block: cheap);
+//   2. warp = 4 features x 16 documents: W rows streamed from L2 (float4), Z from smem, fp32 FMA, butterfly
+//      reduction over the K-split lanes, T = tanh(. + b) to global scratch;
+//   3. the LAST CTA of a group to finish (atomic ticket) runs out_proj / temperature / criterion / strict threshold
+//      for its 16 documents 
+//   4. the LAST group to finish runs the prefix-sum compaction over all active slots (compact logic).
+// No host round-trip and no extra launches: ~4x fewer launches and no exposed load latency between the stages.
+struct ExitFusedArgs {
+  // (1) rows
+  const float* rows;        // fp32 rows; row of slot s starts at rows + src(s) * row_stride
+  size_t row_stride;
+  const int* slot_src;      // optional gather map (rows not yet compacted)
+  const float* ln_w;        // nullptr -> no LayerNorm (mean-pooled embedding exit)
+  const float* ln_b;
+  float ln_eps;
+  int H;
+  const int* n_active_dev;
+  // (2) dense jobs
+  int jobs;                 // 0..2
+  const float* w[2];        // [H, H]
+  const float* b[2];
+  float* T[2];              // [maxB, H] scratch
+  // (3) heads: input of each out_proj: 0 / 1 = T[0] / T[1], 2 = the normalised rows themselves, -1 = head unused
+  int head_src, cls_src;
+  HeadWeights head, cls;
+  int gate_mode, n_labels, criterion;
+  float inv_temp, threshold;
+  int force;
+  float* slot_logits; float* slot_head; float* slot_crit; int* slot_fire;
+  // tickets (zero on entry, reset by the last arriver)
+  unsigned int* group_ticket;   // [ceil(maxB/16)]
+  unsigned int* groups_done;    // [1]
+  // (4)
+  CompactArgs compact;
+};
+
+constexpr int EXF_DOCS = 16, EXF_FEATS = 32, EXF_THREADS = 256;
+
+inline size_t exit_fused_smem(int H) { return static_cast<size_t>(2) * EXF_DOCS * H * sizeof(float) + 64; }
+
+// block-wide compaction (any blockDim that is a multiple of 32, <= 1024); loads of this launch's results bypass L1
+__device__ __forceinline__ void compact_block(const CompactArgs& a, int* s_warp, int* s_misc) {
+  int& s_total = s_misc[0];
+  int& s_base = s_misc[1];
+  int& s_fired = s_misc[2];
   const int n = *a.n_active_dev;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   if (threadIdx.x == 0) { s_base = 0; s_fired = 0; }
   __syncthreads();
-  for (int start = 0; start < n; start += 1024) {
+  for (int start = 0; start < n; start += blockDim.x) {
     const int s = start + threadIdx.x;
     const bool valid = s < n;
     int doc = -1, fire = 0, first = 0;
     if (valid) {
       doc = a.slot_doc[s];
-      fire = a.slot_fire[s];
-      // record per-exit outputs for every active document
+      fire = __ldcg(a.slot_fire + s);
       if (a.all_logits)
         for (int k = 0; k < a.K; ++k)
-          a.all_logits[(static_cast<size_t>(a.exit_index) * a.B + doc) * a.K + k] = a.slot_logits[static_cast<size_t>(s) * a.K + k];
+          a.all_logits[(static_cast<size_t>(a.exit_index) * a.B + doc) * a.K + k] = __ldcg(a.slot_logits + static_cast<size_t>(s) * a.K + k);
       if (a.all_head)
         for (int k = 0; k < a.n_head; ++k)
-          a.all_head[(static_cast<size_t>(a.exit_index) * a.B + doc) * a.n_head_max + k] = a.slot_head[static_cast<size_t>(s) * a.n_head + k];
-      if (a.all_crit) a.all_crit[static_cast<size_t>(a.exit_index) * a.B + doc] = a.slot_crit[s];
+          a.all_head[(static_cast<size_t>(a.exit_index) * a.B + doc) * a.n_head_max + k] = __ldcg(a.slot_head + static_cast<size_t>(s) * a.n_head + k);
+      if (a.all_crit) a.all_crit[static_cast<size_t>(a.exit_index) * a.B + doc] = __ldcg(a.slot_crit + s);
       first = fire && (a.out_exit[doc] < 0);
       if (first) {
         a.out_exit[doc] = a.exit_index;
-        a.out_crit[doc] = a.slot_crit[s];
-        for (int k = 0; k < a.K; ++k) a.out_logits[static_cast<size_t>(doc) * a.K + k] = a.slot_logits[static_cast<size_t>(s) * a.K + k];
+        a.out_crit[doc] = __ldcg(a.slot_crit + s);
+        for (int k = 0; k < a.K; ++k) a.out_logits[static_cast<size_t>(doc) * a.K + k] = __ldcg(a.slot_logits + static_cast<size_t>(s) * a.K + k);
       }
     }
     const int stay = valid && !(a.leave && fire);
-    // block-wide exclusive scan of `stay`
     const unsigned ball = __ballot_sync(0xffffffffu, stay);
     const int wprefix = __popc(ball & ((1u << lane) - 1));
     const unsigned fball = __ballot_sync(0xffffffffu, first);
     if (lane == 0) { s_warp[warp] = __popc(ball); if (fball) atomicAdd(&s_fired, __popc(fball)); }
     __syncthreads();
     if (warp == 0) {
-      const int v = s_warp[lane];
+      const int v = (lane < nwarps) ? s_warp[lane] : 0;
       int incl = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -458,6 +343,198 @@ __global__ void __launch_bounds__(1024) compact_kernel(CompactArgs a) {
     *a.m_next_dev = s_base * a.seq;
     if (s_fired) atomicAdd(a.hist + a.exit_index, static_cast<unsigned long long>(s_fired));
   }
+}
+
+__global__ void __launch_bounds__(EXF_THREADS) exit_fused_kernel(ExitFusedArgs a) {
+  extern __shared__ __align__(16) float exf_smem[];
+  __shared__ int s_warp[32];
+  __shared__ int s_misc[4];
+  __shared__ unsigned int s_ticket;
+  const int H = a.H;
+  float* sZ = exf_smem;                         // [16][H] normalised rows; later the head's out_proj input
+  float* sX = exf_smem + EXF_DOCS * H;          // [16][H] the classifier's out_proj input (gate mode)
+  const int n = *a.n_active_dev;
+  const int n_groups = (n + EXF_DOCS - 1) / EXF_DOCS;
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (n == 0) {                                 // nobody left: still publish the (empty) survivor list
+    if (blockIdx.x == 0 && g == 0 && blockIdx.z == 0) compact_block(a.compact, s_warp, s_misc);
+    return;
+  }
+  if (g >= n_groups) return;
+  const int d0 = g * EXF_DOCS;
+
+  // ---- (1) rows of this group -> sZ (LayerNorm unless this is the pooled embedding exit)
+  for (int dd = warp; dd < EXF_DOCS; dd += EXF_THREADS / 32) {
+    const int slot = d0 + dd;
+    float* z = sZ + dd * H;
+    if (slot >= n) {
+      for (int c = lane * 4; c < H; c += 128) *reinterpret_cast<float4*>(z + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    const int src = a.slot_src ? a.slot_src[slot] : slot;
+    const float* r = a.rows + static_cast<size_t>(src) * a.row_stride;
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      v[i] = (c < H) ? *reinterpret_cast<const float4*>(r + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (a.ln_w) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      const float mean = warp_sum(s) / H;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if ((lane + 32 * i) * 4 < H) {
+          const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+          q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(q) / H + a.ln_eps);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (c < H) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.ln_w + c));
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.ln_b + c));
+          v[i].x = (v[i].x - mean) * rstd * w4.x + b4.x;
+          v[i].y = (v[i].y - mean) * rstd * w4.y + b4.y;
+          v[i].z = (v[i].z - mean) * rstd * w4.z + b4.z;
+          v[i].w = (v[i].w - mean) * rstd * w4.w + b4.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      if (c < H) *reinterpret_cast<float4*>(z + c) = v[i];
+    }
+  }
+  __syncthreads();
+
+  // ---- (2) dense + tanh: warp = 4 features x 16 documents, lanes split K
+  if (a.jobs > 0) {
+    const int job = blockIdx.z;
+    const int f0 = blockIdx.x * EXF_FEATS + warp * 4;
+    const float* __restrict__ W = a.w[job] + static_cast<size_t>(f0) * H;
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    for (int k = lane * 4; k < H; k += 128) {
+      float4 w4[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) w4[f] = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(f) * H + k));
+#pragma unroll
+      for (int d = 0; d < EXF_DOCS; ++d) {
+        const float4 z4 = *reinterpret_cast<const float4*>(sZ + d * H + k);
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          float t = acc[f * 16 + d];
+          t = fmaf(w4[f].x, z4.x, t); t = fmaf(w4[f].y, z4.y, t); t = fmaf(w4[f].z, z4.z, t); t = fmaf(w4[f].w, z4.w, t);
+          acc[f * 16 + d] = t;
+        }
+      }
+    }
+    // butterfly reduction over the 32 K-split lanes: halves the live values per step; lane ends with indices 2*lane, 2*lane+1
+#pragma unroll
+    for (int off = 16, cnt = 64; off >= 1; off >>= 1, cnt >>= 1) {
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int j = 0; j < cnt / 2; ++j) {
+        const float send = up ? acc[j] : acc[j + cnt / 2];
+        const float keep = up ? acc[j + cnt / 2] : acc[j];
+        acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int idx = 2 * lane + j, f = idx >> 4, d = idx & 15;
+      if (d0 + d < n)
+        a.T[job][static_cast<size_t>(d0 + d) * H + f0 + f] = tanhf(acc[j] + __ldg(a.b[job] + f0 + f));
+    }
+  }
+
+  // ---- ticket: the last CTA of this group continues with the heads
+  __threadfence();
+  __syncthreads();
+  const unsigned int per_group = gridDim.x * gridDim.z;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(a.group_ticket + g, 1u);
+  __syncthreads();
+  if (s_ticket != per_group - 1) return;
+  if (threadIdx.x == 0) a.group_ticket[g] = 0u;            // ready for the next exit
+  __threadfence();
+
+  // ---- (3) out_proj inputs into shared memory (T rows were written by other SMs: bypass L1)
+  const int K = a.n_labels;
+  if (a.head_src == 0 || a.head_src == 1) {
+    const float* Tsrc = a.T[a.head_src];
+    for (int i = threadIdx.x; i < EXF_DOCS * H / 4; i += EXF_THREADS) {
+      const int d = (i * 4) / H;
+      reinterpret_cast<float4*>(sZ)[i] = (d0 + d < n) ? __ldcg(reinterpret_cast<const float4*>(Tsrc + static_cast<size_t>(d0) * H) + i)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (a.gate_mode) {
+    const float* Tsrc = a.T[a.cls_src];
+    for (int i = threadIdx.x; i < EXF_DOCS * H / 4; i += EXF_THREADS) {
+      const int d = (i * 4) / H;
+      reinterpret_cast<float4*>(sX)[i] = (d0 + d < n) ? __ldcg(reinterpret_cast<const float4*>(Tsrc + static_cast<size_t>(d0) * H) + i)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __syncthreads();
+  for (int dd = warp; dd < EXF_DOCS; dd += EXF_THREADS / 32) {
+    const int slot = d0 + dd;
+    if (slot >= n) continue;
+    float head_val = 0.f;                 // lane j holds head logit j
+    if (a.head_src >= 0 && a.head.out_w) {
+      const float* x = sZ + dd * H;
+      for (int j = 0; j < a.head.n_out; ++j) {
+        const float v = warp_dot(a.head.out_w + static_cast<size_t>(j) * H, x, H, lane) + __ldg(a.head.out_b + j);
+        if (lane == j) head_val = v;
+      }
+      if (lane < a.head.n_out) a.slot_head[static_cast<size_t>(slot) * a.head.n_out + lane] = head_val;
+    }
+    float raw = head_val;                 // class logit of lane k
+    if (a.gate_mode) {
+      raw = 0.f;
+      const float* x = sX + dd * H;
+      for (int j = 0; j < K; ++j) {
+        const float v = warp_dot(a.cls.out_w + static_cast<size_t>(j) * H, x, H, lane) + __ldg(a.cls.out_b + j);
+        if (lane == j) raw = v;
+      }
+    }
+    if (lane < K) a.slot_logits[static_cast<size_t>(slot) * K + lane] = raw;
+    const float z = raw * a.inv_temp;
+    const float zmax = warp_max(lane < K ? z : -INFINITY);
+    const float ex = (lane < K) ? expf(z - zmax) : 0.f;
+    const float A = warp_sum(ex);
+    float crit;
+    if (a.criterion == 0) {
+      crit = 1.0f / A;
+    } else {
+      const float Bz = warp_sum((lane < K) ? (z - zmax) * ex : 0.f);
+      crit = logf(A) - Bz / A;
+    }
+    if (lane == 0) {
+      a.slot_crit[slot] = crit;
+      const bool fire = a.force || (a.criterion == 0 ? (crit > a.threshold) : (crit < a.threshold));
+      a.slot_fire[slot] = fire ? 1 : 0;
+    }
+  }
+
+  // ---- (4) the last group to finish compacts
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(a.groups_done, 1u);
+  __syncthreads();
+  if (s_ticket != static_cast<unsigned int>(n_groups) - 1) return;
+  if (threadIdx.x == 0) *a.groups_done = 0u;
+  __threadfence();
+  compact_block(a.compact, s_warp, s_misc);
 }
 
 }  // namespace mmee
