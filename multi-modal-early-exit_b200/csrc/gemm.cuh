@@ -64,20 +64,22 @@ struct GemmSmem {
 };
 
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  // x * Phi(x), Phi(x) = 1 - 0.5*erfc(x/sqrt2), erfc by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7 before the
-  // approximate MUFU ops): matches torch's exact-erf GELU (activations.py "gelu" -> nn.functional.gelu) far
-  // inside the bf16 rounding of the output.  2 MUFU (rcp, ex2) + ~12 FMA-pipe ops.
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  float ex;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(z * z * -1.4426950408889634f));
-  const float half_erfc = 0.5f * poly * t * ex;                 // 0.5 * erfc(|x|/sqrt2)
-  const float phi = (x >= 0.f) ? (1.0f - half_erfc) : half_erfc;
+  // x * Phi(x) with Phi(x) = 1 - 0.5*erfc(x/sqrt2) for x >= 0 and 0.5*erfc(|x|/sqrt2) for x < 0.
+  // 0.5*erfc(z) = 2^q(z), q a degree-6 minimax fit of log2(0.5*erfc(z)) on z in [0, 4.3] (|abs err| < 4.2e-7 on
+  // 0.5*erfc, fitted offline; beyond z = 4.3 erfc < 2e-9 and the clamp keeps it there): matches torch's exact-erf
+  // GELU (activations.py "gelu" -> nn.functional.gelu) to 2.3e-7 absolute, far inside the bf16 rounding of the
+  // output.  1 MUFU (ex2) + 11 FMA/ALU-pipe ops (the A&S 7.1.26 form needed 2 MUFU + ~15).
+  const float z = fminf(fabsf(x) * 0.70710678118654752f, 4.3f);
+  float q = 2.699725252e-04f;
+  q = fmaf(q, z, -4.347565948e-03f);
+  q = fmaf(q, z, 3.221176717e-02f);
+  q = fmaf(q, z, -1.508187237e-01f);
+  q = fmaf(q, z, -9.177533792e-01f);
+  q = fmaf(q, z, -1.627978526e+00f);
+  q = fmaf(q, z, -9.999988147e-01f);
+  float h;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(q));        // 0.5 * erfc(|x|/sqrt2)
+  const float phi = (x >= 0.f) ? (1.0f - h) : h;
   return x * phi;
 }
 
