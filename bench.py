@@ -273,7 +273,7 @@ def main():
             tr = json.load(f)
         traffic = tr.get("gemm_mean_dram_bytes_per_launch")
         traffic_src = f"ncu dram__bytes_read.sum+dram__bytes_write.sum, mean of the 4 GEMM launches of one layer at {tr.get('docs')} docs (profiles/traffic.json, capture {tr.get('capture')})"
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (QKV / out-proj / MLP-up+GELU / MLP-down, tcgen05)",
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_pair_kernel (QKV / out-proj / MLP-up+GELU / MLP-down; tcgen05 cta_group::2)",
                 "achieved": gemm_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                 "frac": (gemm_tf / pk["tf_sust"]) if gemm_tf else None, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
@@ -297,7 +297,7 @@ def main():
                        "criterion": kind, "threshold": thr, "calibrated_confidence_level": args.threshold,
                        "temperatures": [round(float(t), 5) for t in temps],
                        "exit_hist_rank0": hist.tolist(), "mean_exit_layer_rank0": mean_depth,
-                       "l2_policy": "working set (attention-bias 3.1 GB + activations 2.6 GB per step) exceeds the 126 MB L2"},
+                       "l2_policy": "working set (fp16 attention bias 3.1 GB + activations 2.6 GB per layer) exceeds the 126 MB L2"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
         }

@@ -100,6 +100,24 @@ double mmee_last_stage_ms(mmee_engine* e, const char* stage);
  * to host memory (synchronises the device). Returns bytes copied or < 0. */
 int64_t mmee_debug_read(mmee_engine* e, const char* name, void* host_dst, int64_t capacity_bytes);
 
+/* Post-hoc exit policy over stored per-exit logits: the device replacement of the per-sample double loop of
+ * Policy.max_confidence_global_thresholding_policy / accuracy_calibration_heuristic (EE/policy.py:12-53, 55-111)
+ * and of the threshold sweeps that re-run it once per threshold (EE/eval.py:227-274 full_test_iteration,
+ * EE/thresh.py:106-132).  All buffers in HOST memory; fp64 like the reference (scipy softmax on the f64 store).
+ *   logits       f64 [E1, N, K]   per-exit logits incl. the final classifier (EE/utils.py:160-193 `logits_store`)
+ *   temperatures f64 [E1] or NULL logits[e] / T_e before the criterion (EE/generic_scaling.py:54-61)
+ *   criterion    0 max softmax, exit iff > thr (EE/policy.py:33) ; 1 entropy, exit iff < thr (EE_modules.py:142)
+ *   thresholds   f64 [n_thr, E1]  one row per sweep point (a global threshold = a constant row; the last column
+ *                                 is ignored: the final classifier always fires, EE/policy.py:40-45)
+ *   labels       i64 [N] or NULL  enables correct_out
+ * Outputs: exits_out i32 [n_thr, N] (`exits_store`), crit_out f64 [E1, N] (nullable), hist_out i64 [n_thr, E1]
+ * (nullable; exit_distribution * N), correct_out i64 [n_thr] (nullable; samples whose arg-max class at the exit
+ * taken equals the label). */
+int  mmee_policy_scan(int device, int n_exits_plus1, int64_t n_samples, int n_labels, const double* logits,
+                      const double* temperatures, int criterion, const double* thresholds, int n_thr,
+                      const int64_t* labels, int32_t* exits_out, double* crit_out, int64_t* hist_out,
+                      int64_t* correct_out);
+
 const char* mmee_last_error(void);
 const char* mmee_version(void);
 

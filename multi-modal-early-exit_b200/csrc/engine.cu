@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -18,6 +19,7 @@
 #include "embed.cuh"
 #include "gemm.cuh"
 #include "norm_exit.cuh"
+#include "policy.cuh"
 #include "tmap.h"
 
 using namespace mmee;
@@ -150,6 +152,8 @@ struct mmee_engine {
 
   // activations
   DevBuf<__nv_bfloat16> X[2], QK, VT, CTX, A1, MID, PATCH;
+  DevBuf<__nv_bfloat16> Xlo[2], A1lo;       // low parts of the split-bf16 residual stream (precise_residual)
+  bool precise_residual = true;
   DevBuf<float> Y, VIS, POOL, Z, T0, T1;
   DevBuf<__half> BIAS, bias_t2;
   DevBuf<float> maskadd, bias_t1;
@@ -453,6 +457,9 @@ void allocate(mmee_engine* e) {
   e->VT.alloc(static_cast<size_t>(B) * heads * 64 * e->kv_pitch, true);
   e->CTX.alloc(M * H, true);
   e->A1.alloc(M * H, true);
+  if (e->precise_residual) {
+    e->Xlo[0].alloc(M * H, true); e->Xlo[1].alloc(M * H, true); e->A1lo.alloc(M * H, true);
+  }
   e->MID.alloc(M * I, true);
   e->Y.alloc(M * H, true);
   const size_t mp = (static_cast<size_t>(B) * e->n_patch + 255) / 256 * 256 + 128;
@@ -611,6 +618,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   int cur = 0;         // X buffer holding the current layer input
   int sd = 0;          // slot_doc ping-pong index
   int exit_no = 0;     // next exit to evaluate
+  bool x_lo_valid = false;   // X[cur] has a low part (false for the embedding output: a single bf16 rounding)
 
   auto run_exit = [&](const float* rows, size_t row_stride, const float* ln_w, const float* ln_b,
                       const HeadW& head, bool is_final, const int* rows_slot_src) {
@@ -721,10 +729,11 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
 
     ga = GemmArgs{};
     ga.m_dev = mdev; ga.N = H; ga.K = H; ga.bias = w.bo.p; ga.out = e->Y.p; ga.ld_out = H; ga.resid = e->X[cur].p;
+    ga.resid_lo = x_lo_valid ? e->Xlo[cur].p : nullptr;
     launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_ctx, w.t_wo, ga, st);
     mark(e, "gemm", st);
     launch_nv(H, [&](auto nv) {
-      ln_rows_kernel<decltype(nv)::value><<<(B * S + 7) / 8, 256, 0, st>>>(e->Y.p, e->A1.p, w.ln1_w.p, w.ln1_b.p,
+      ln_rows_kernel<decltype(nv)::value><<<(B * S + 7) / 8, 256, 0, st>>>(e->Y.p, e->A1.p, e->A1lo.p, w.ln1_w.p, w.ln1_b.p,
                                                                           d.ln_eps, H, S, mdev, nullptr);
     });
     e->launches++;
@@ -735,6 +744,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     launch_gemm<EPI_GELU_BF16>(e, e->bn_i, e->t_a1, w.t_wi, ga, st);
     ga = GemmArgs{};
     ga.m_dev = mdev; ga.N = H; ga.K = I; ga.bias = w.bo2.p; ga.out = e->Y.p; ga.ld_out = H; ga.resid = e->A1.p;
+    ga.resid_lo = e->A1lo.p;
     launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_mid, w.t_wo2, ga, st);
     mark(e, "gemm", st);
 
@@ -749,10 +759,11 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     if (!last) {
       launch_nv(H, [&](auto nv) {
         ln_rows_kernel<decltype(nv)::value><<<(B * S + 7) / 8, 256, 0, st>>>(
-            e->Y.p, e->X[cur ^ 1].p, w.ln2_w.p, w.ln2_b.p, d.ln_eps, H, S, e->m_dev.p + stage, ln_src);
+            e->Y.p, e->X[cur ^ 1].p, e->Xlo[cur ^ 1].p, w.ln2_w.p, w.ln2_b.p, d.ln_eps, H, S, e->m_dev.p + stage, ln_src);
       });
       e->launches++;
       cur ^= 1;
+      x_lo_valid = e->precise_residual;
       mark(e, "norm", st);
     } else {
       // final classifier on the CLS row of the last layer (EE/models/LayoutLMv3.py:730-731); rows still live in
@@ -846,6 +857,7 @@ int mmee_create(const mmee_model_desc* desc, int device, int max_batch, mmee_eng
   e->bias_pitch = ((e->S + ATT_BKV - 1) / ATT_BKV) * ATT_BKV;   // whole key tiles: the pitch padding carries the -60000 mask
   if (e->kv_pitch > 1024) throw std::runtime_error("sequence too long for keymask_kernel");
   e->sms = prop.multiProcessorCount;
+  if (const char* pr = getenv("MMEE_PRECISE_RESIDUAL")) e->precise_residual = pr[0] != '0';   // developer A/B switch
   e->bn_h = pick_bn(e->H); e->bn_qkv = pick_bn(e->H) ; e->bn_i = pick_bn(e->I);
   if ((2 * e->H) % e->bn_qkv) e->bn_qkv = 128;
   try {
@@ -941,14 +953,15 @@ int mmee_forward(mmee_engine* e, int B, const int64_t* input_ids, const int64_t*
     e->in_px.alloc(mb * e->d.channels * e->d.image * e->d.image);
   }
   cudaStream_t st = e->stream;
-  // pixels go up on a second stream and are first needed by im2col, after text embedding and bias build
+  // small inputs first (one H2D copy engine serves both streams in issue order); the pixels (96 % of the bytes) go up
+  // on a second stream and are first needed by im2col, after text embedding and bias build
+  CUDA_OK(cudaMemcpyAsync(e->in_ids.p, input_ids, n_ids * 8, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->in_bbox.p, bbox, n_ids * 32, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->in_mask.p, attention_mask, n_ids * 8, cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaEventRecord(e->fwd_start, st));
   CUDA_OK(cudaStreamWaitEvent(e->copy_stream, e->fwd_start, 0));       // previous forward has released in_px
   CUDA_OK(cudaMemcpyAsync(e->in_px.p, pixel_values, n_px * 4, cudaMemcpyHostToDevice, e->copy_stream));
   CUDA_OK(cudaEventRecord(e->px_ready, e->copy_stream));
-  CUDA_OK(cudaMemcpyAsync(e->in_ids.p, input_ids, n_ids * 8, cudaMemcpyHostToDevice, st));
-  CUDA_OK(cudaMemcpyAsync(e->in_bbox.p, bbox, n_ids * 32, cudaMemcpyHostToDevice, st));
-  CUDA_OK(cudaMemcpyAsync(e->in_mask.p, attention_mask, n_ids * 8, cudaMemcpyHostToDevice, st));
   e->px_async = true;
   // run with outputs in the engine's own device buffers, then copy what was asked for to the host
   mmee_outputs dv{};
@@ -1017,6 +1030,53 @@ int64_t mmee_debug_read(mmee_engine* e, const char* name, void* host_dst, int64_
     g_err = ex.what();
     return -1;
   }
+}
+
+int mmee_policy_scan(int device, int n_exits_plus1, int64_t n_samples, int n_labels, const double* logits,
+                     const double* temperatures, int criterion, const double* thresholds, int n_thr,
+                     const int64_t* labels, int32_t* exits_out, double* crit_out, int64_t* hist_out,
+                     int64_t* correct_out) {
+  MMEE_TRY
+  const int E1 = n_exits_plus1, K = n_labels;
+  const int64_t N = n_samples;
+  if (!logits || !thresholds || !exits_out) throw std::runtime_error("null argument");
+  if (E1 < 1 || N < 1 || K < 1 || n_thr < 1) throw std::runtime_error("bad shape");
+  if (criterion != 0 && criterion != 1) throw std::runtime_error("criterion must be 0 (max_confidence) or 1 (entropy)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw std::runtime_error("no CUDA device: libmmee has no CPU fallback");
+  CUDA_OK(cudaSetDevice(device));
+  const size_t n_log = static_cast<size_t>(E1) * N * K, n_en = static_cast<size_t>(E1) * N;
+  DevBuf<double> d_logits, d_temps, d_thr, d_crit;
+  DevBuf<int> d_arg;
+  DevBuf<int32_t> d_exits;
+  DevBuf<int64_t> d_labels;
+  DevBuf<unsigned long long> d_hist, d_correct;
+  d_logits.alloc(n_log); d_crit.alloc(n_en); d_arg.alloc(n_en);
+  d_thr.alloc(static_cast<size_t>(n_thr) * E1); d_exits.alloc(static_cast<size_t>(n_thr) * N);
+  d_hist.alloc(static_cast<size_t>(n_thr) * E1, true); d_correct.alloc(n_thr, true);
+  CUDA_OK(cudaMemcpy(d_logits.p, logits, n_log * 8, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d_thr.p, thresholds, static_cast<size_t>(n_thr) * E1 * 8, cudaMemcpyHostToDevice));
+  if (temperatures) {
+    d_temps.alloc(E1);
+    CUDA_OK(cudaMemcpy(d_temps.p, temperatures, static_cast<size_t>(E1) * 8, cudaMemcpyHostToDevice));
+  }
+  if (labels) {
+    d_labels.alloc(N);
+    CUDA_OK(cudaMemcpy(d_labels.p, labels, static_cast<size_t>(N) * 8, cudaMemcpyHostToDevice));
+  }
+  policy_crit_kernel<<<static_cast<unsigned>((n_en + 255) / 256), 256>>>(d_logits.p, d_temps.p, E1, N, K, criterion,
+                                                                          d_crit.p, d_arg.p);
+  CUDA_OK(cudaGetLastError());
+  policy_scan_kernel<<<dim3(static_cast<unsigned>((N + 255) / 256), n_thr), 256, (E1 + 1) * sizeof(unsigned int)>>>(
+      d_crit.p, d_arg.p, d_thr.p, d_labels.p, E1, N, criterion, d_exits.p, d_hist.p, d_correct.p);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpy(exits_out, d_exits.p, static_cast<size_t>(n_thr) * N * 4, cudaMemcpyDeviceToHost));
+  if (crit_out) CUDA_OK(cudaMemcpy(crit_out, d_crit.p, n_en * 8, cudaMemcpyDeviceToHost));
+  if (hist_out) CUDA_OK(cudaMemcpy(hist_out, d_hist.p, static_cast<size_t>(n_thr) * E1 * 8, cudaMemcpyDeviceToHost));
+  if (correct_out) CUDA_OK(cudaMemcpy(correct_out, d_correct.p, static_cast<size_t>(n_thr) * 8, cudaMemcpyDeviceToHost));
+  return 0;
+  MMEE_CATCH
 }
 
 int mmee_set_profiling(mmee_engine* e, int on) {

@@ -27,7 +27,7 @@ constexpr int GEMM_THREADS = 64 + GEMM_EPI_WARPS * 32;
 enum GemmEpilogue : int {
   EPI_BIAS_BF16 = 0,   // out_bf16[m, n] = acc + bias[n]
   EPI_GELU_BF16 = 1,   // out_bf16[m, n] = gelu_erf(acc + bias[n])
-  EPI_RESID_F32 = 2,   // out_f32 [m, n] = acc + bias[n] + resid_bf16[m, n]
+  EPI_RESID_F32 = 2,   // out_f32 [m, n] = acc + bias[n] + resid_bf16[m, n] (+ resid_lo_bf16[m, n])
   EPI_QKV = 3,         // n < qk_cols: qk_bf16[m, n];  else V^T: vt[doc][head][d][kv_pitch]
   EPI_PATCH = 4,       // patch-embed rows (doc*n_patch + p): out_f32[(doc*n_vis + 1 + p), n] = acc + bias + pos[1+p, n]
 };
@@ -40,6 +40,7 @@ struct GemmArgs {
   void* out;               // bf16 or f32 [*, ld_out]
   int ld_out;
   const __nv_bfloat16* resid;   // EPI_RESID_F32: [*, N]
+  const __nv_bfloat16* resid_lo;   // optional low part of a split-bf16 residual (resid + resid_lo = 16-bit mantissa), or nullptr
   // EPI_QKV
   __nv_bfloat16* vt;       // [docs][heads][64][kv_pitch]
   int qk_cols;             // 2*H
@@ -96,13 +97,14 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
 #pragma unroll 1
       for (int c = half * (BLOCK_N / 2); c < (half + 1) * (BLOCK_N / 2); c += 32) {
         const int n = n0 + c;
-        uint2 rs[8];
+        uint2 rs[8], rl[8];
         if constexpr (EPI == EPI_RESID_F32) {       // residual loads first: independent of the accumulator
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int grow = row_base + (lane >> 3) + 4 * i;
-            rs[i] = (grow < M) ? __ldg(reinterpret_cast<const uint2*>(args.resid + static_cast<size_t>(grow) * args.N + n + (lane & 7) * 4))
-                               : make_uint2(0u, 0u);
+            const size_t off = static_cast<size_t>(grow) * args.N + n + (lane & 7) * 4;
+            rs[i] = (grow < M) ? __ldg(reinterpret_cast<const uint2*>(args.resid + off)) : make_uint2(0u, 0u);
+            rl[i] = (grow < M && args.resid_lo) ? __ldg(reinterpret_cast<const uint2*>(args.resid_lo + off)) : make_uint2(0u, 0u);
           }
         }
         uint32_t v[32];
@@ -172,7 +174,8 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
             if (grow < M) {
               if constexpr (EPI == EPI_RESID_F32) {
                 const float2 r0 = unpack_bf16x2(rs[i].x), r1 = unpack_bf16x2(rs[i].y);
-                val.x += r0.x; val.y += r0.y; val.z += r1.x; val.w += r1.y;
+                const float2 l0 = unpack_bf16x2(rl[i].x), l1 = unpack_bf16x2(rl[i].y);
+                val.x += r0.x + l0.x; val.y += r0.y + l0.y; val.z += r1.x + l1.x; val.w += r1.y + l1.y;
                 *reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(grow) * args.ld_out + n + q * 4) = val;
               } else {   // EPI_PATCH
                 const int doc = grow / args.n_patch;

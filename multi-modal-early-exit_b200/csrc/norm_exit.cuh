@@ -16,10 +16,12 @@
 
 namespace mmee {
 
-// one warp per destination row; rows >= *m_dst_dev are skipped.
+// one warp per destination row; rows >= *m_dst_dev are skipped.  Xlo (optional): low part of the split-bf16 residual
+// stream, Xlo = bf16(v - bf16(v)): the next residual add reads X + Xlo (16-bit mantissa) while the GEMMs read X.
 template <int NV>
 __global__ void ln_rows_kernel(const float* __restrict__ Y, __nv_bfloat16* __restrict__ X,
-                               const float* __restrict__ w, const float* __restrict__ b, float eps, int H, int seq,
+                               __nv_bfloat16* __restrict__ Xlo, const float* __restrict__ w,
+                               const float* __restrict__ b, float eps, int H, int seq,
                                const int* __restrict__ m_dst_dev, const int* __restrict__ slot_src) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= *m_dst_dev) return;
@@ -38,10 +40,15 @@ __global__ void ln_rows_kernel(const float* __restrict__ Y, __nv_bfloat16* __res
   }
   warp_layernorm<NV>(v, H, w, b, eps, lane);
   __nv_bfloat16* out = X + static_cast<size_t>(row) * H;
+  __nv_bfloat16* out_lo = Xlo ? Xlo + static_cast<size_t>(row) * H : nullptr;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = lane + 32 * i;
-    if (c < H) out[c] = __float2bfloat16_rn(v[i]);
+    if (c < H) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v[i]);
+      out[c] = hi;
+      if (out_lo) out_lo[c] = __float2bfloat16_rn(v[i] - __bfloat162float(hi));
+    }
   }
 }
 

@@ -16,7 +16,7 @@ EXPORTED_SYMBOLS = [
     "mmee_create", "mmee_destroy", "mmee_set_weight", "mmee_set_bucket_lut", "mmee_get_bucket_lut",
     "mmee_finalize_weights", "mmee_forward", "mmee_forward_device", "mmee_last_launch_count",
     "mmee_set_profiling", "mmee_collect_profile", "mmee_last_stage_ms", "mmee_debug_read", "mmee_last_error",
-    "mmee_version",
+    "mmee_version", "mmee_policy_scan",
 ]
 
 
@@ -88,6 +88,9 @@ def load() -> C.CDLL:
     lib.mmee_debug_read.restype = C.c_int64
     lib.mmee_last_stage_ms.argtypes = [C.c_void_p, C.c_char_p]
     lib.mmee_last_stage_ms.restype = C.c_double
+    lib.mmee_policy_scan.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mmee_policy_scan.restype = C.c_int
     lib.mmee_last_error.argtypes = []
     lib.mmee_last_error.restype = C.c_char_p
     lib.mmee_version.argtypes = []

@@ -10,7 +10,7 @@ CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launch_$TAG.log 2>&1
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 50 -c 4 -f -o gpurun_out/gemm_$TAG $CMD > gpurun_out/ncu_gemm_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_tc_pair -s 50 -c 4 -f -o gpurun_out/gemm_$TAG $CMD > gpurun_out/ncu_gemm_$TAG.log 2>&1
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 12 -c 1 -f -o gpurun_out/att_$TAG $CMD > gpurun_out/ncu_att_$TAG.log 2>&1
 echo done

@@ -43,6 +43,9 @@ CASES = {
                                        encoder_layer_strategy="gate", inference_strategy="entropy"), 4, 0, 5, True),
     "large4_ramp_conf": ("large", {"layers": 4}, dict(exits=["text_visual_concat", 2, 4],
                                                      encoder_layer_strategy="ramp", inference_strategy="max_confidence"), 2, 0, 6, True),
+    # BASELINE.json configs[3]: LayoutLMv3-large, all 24 layers, ramps every 2 layers
+    "large24_ramp2": ("large", {}, dict(exits=["text_visual_concat"] + list(range(2, 25, 2)),
+                                        encoder_layer_strategy="ramp", inference_strategy="max_confidence"), 2, 0, 7, True),
 }
 
 

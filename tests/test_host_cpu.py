@@ -199,3 +199,22 @@ def test_spec_from_reference_model():
     for k, v in sd.items():
         assert torch.equal(sd2[k], v), k
     assert set(sd2) - set(sd) <= {"layoutlmv3.visual_bbox", "layoutlmv3.embeddings.position_ids"}
+
+
+def test_policy_host_logic_and_loud_failure():
+    """Host side of mmee.policy: per-exit thresholds of accuracy_calibration_heuristic (EE/policy.py:68-79) and
+    argument checks; the scan itself has no CPU fallback."""
+    from mmee.policy import Policy, heuristic_thresholds, policy_scan
+
+    cm = {"accuracy": [0.5, 0.7, 0.9], "ece": [0.2, 0.1, 0.05]}
+    thr = heuristic_thresholds(cm, 0.1, 3)
+    metrics = np.array([1 - 0.5 / 0.2, 1 - 0.7 / 0.1, 1 - 0.9 / 0.05])
+    want = (metrics - (metrics.min() - 0.1)) / ((metrics.max() + 0.1) - (metrics.min() - 0.1))
+    assert np.allclose(thr, want) and (thr > 0).all() and (thr < 1).all()
+    with pytest.raises(ValueError):
+        policy_scan(np.zeros((3, 4)), 0.5)
+    with pytest.raises(ValueError):
+        policy_scan(np.zeros((3, 4, 5)), np.zeros((2, 4)))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CUDA device|libmmee"):
+            Policy(np.zeros((3, 4, 5)), {"exit_threshold": 0.5}).max_confidence_global_thresholding_policy()

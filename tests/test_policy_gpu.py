@@ -1,0 +1,92 @@
+"""GPU parity tests of the post-hoc exit policy (`mmee.policy`, C ABI `mmee_policy_scan`) against the oracle
+policy port and the reference `Policy` results stored in the golden fixtures.  Exit indices are integers: the bar
+is bit-exact for every sample whose criterion margin to its threshold exceeds 1e-12 (fp64 arithmetic on both
+sides; the device exp() may differ from numpy's in the last ulp)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import ALL_CASES, load_case
+from mmee.policy import Policy, heuristic_thresholds, policy_scan
+from oracle import policy_port
+
+pytestmark = pytest.mark.gpu
+MARGIN = 1e-12
+
+
+def _decisive(crit, thr_row, kind="max_confidence"):
+    return np.abs(crit[:-1] - np.asarray(thr_row)[:-1, None]).min(axis=0) > MARGIN if crit.shape[0] > 1 \
+        else np.ones(crit.shape[1], bool)
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_policy_matches_reference_golden(name):
+    """Same call shape as EE/eval.py:91-98; results equal the reference Policy's stored in the golden."""
+    g, *_ = load_case(name)
+    lg = g["exit_logits"].astype(np.float64)
+    for tag, l in (("raw", lg), ("cal", policy_port.temperature_scale(lg, g["temps"]))):
+        for thr in (0.1, 0.5, 0.7, 0.9):
+            ex, pred, dist = Policy(logits=l, config={"exit_threshold": thr, "device": "cpu"}
+                                    ).max_confidence_global_thresholding_policy()
+            assert ex.dtype == np.int32 and isinstance(pred, torch.Tensor) and pred.dtype == torch.float64
+            assert np.array_equal(ex, g[f"policy_{tag}_{thr}_exits"])
+            assert np.array_equal(pred.numpy(), g[f"policy_{tag}_{thr}_pred"])
+            assert abs(sum(dist.values()) - 1.0) < 1e-12 and set(dist) == set(range(l.shape[0]))
+
+
+def test_sweep_equals_oracle_loop_full_size():
+    """RVL-CDIP-test-sized store (40k samples, 14 exits, 16 classes), the 0.5..0.99 sweep of BASELINE config 3."""
+    rng = np.random.default_rng(3)
+    E1, N, K = 14, 40000, 16
+    lg = rng.normal(size=(E1, N, K)) * np.linspace(0.5, 4.0, E1)[:, None, None]
+    labels = rng.integers(0, K, size=N)
+    temps = np.linspace(1.5, 0.7, E1)
+    thrs = np.arange(0.5, 1.0, 0.01)
+    res = Policy(lg, {"device": "cpu"}).sweep(thrs, temperatures=temps, labels=labels)
+    cal = policy_port.temperature_scale(lg, temps)
+    crit = policy_port.criterion(cal, "max_confidence")
+    assert np.abs(res.criteria - crit).max() < 1e-13
+    prev = None
+    for t, thr in enumerate(thrs):
+        want, _, _ = policy_port.exit_policy_vectorised(cal, thr, "max_confidence")
+        ok = _decisive(crit, np.full(E1, thr))
+        assert np.array_equal(res.exits[t][ok], want[ok]) and ok.mean() > 0.999
+        assert res.hist[t].sum() == N and np.array_equal(np.bincount(res.exits[t], minlength=E1), res.hist[t])
+        assert res.correct[t] == int((cal[res.exits[t], np.arange(N)].argmax(-1) == labels).sum())
+        if prev is not None:
+            assert (res.exits[t] >= prev).all()          # exit depth is monotone in the threshold
+        prev = res.exits[t]
+    assert np.allclose(res.mean_exit, res.exits.mean(1))
+
+
+def test_entropy_and_per_exit_thresholds_and_edges():
+    rng = np.random.default_rng(0)
+    lg = rng.normal(size=(5, 777, 16)) * 3
+    thr = np.array([0.5, 1.0, 1.5, 2.0, 0.0])
+    res = policy_scan(lg, thr, "entropy")
+    want, pred, crit = policy_port.exit_policy_vectorised(lg, thr, "entropy")
+    ok = _decisive(crit, thr)
+    assert np.array_equal(res.exits[0][ok], want[ok])
+    assert np.abs(res.criteria - crit).max() < 1e-12
+    # strict comparisons: threshold 1.0 never fires, threshold 0.0 always fires at exit 0
+    ex, pred, dist = Policy(lg, {"exit_threshold": 1.0, "device": "cpu"}).max_confidence_global_thresholding_policy()
+    assert (ex == 4).all() and dist[4] == 1.0 and np.array_equal(pred.numpy(), lg[4])
+    ex, pred, _ = Policy(lg, {"exit_threshold": 0.0, "device": "cpu"}).max_confidence_global_thresholding_policy()
+    assert (ex == 0).all() and np.array_equal(pred.numpy(), lg[0])
+    # a single exit (E+1 == 1) and a single sample
+    ex, _, _ = Policy(lg[:1, :1], {"exit_threshold": 0.99, "device": "cpu"}).max_confidence_global_thresholding_policy()
+    assert ex.tolist() == [0]
+
+
+def test_accuracy_calibration_heuristic_matches_loop():
+    rng = np.random.default_rng(5)
+    lg = rng.normal(size=(6, 500, 16)) * 2.5
+    cm = {"accuracy": [0.5, 0.6, 0.7, 0.75, 0.8, 0.85], "ece": [0.2, 0.15, 0.12, 0.1, 0.08, 0.05],
+          "average_confidence": [0.6] * 6}
+    cfg = {"calibration_metrics": cm, "epsilon": 0.1, "device": "cpu"}
+    ex, pred, dist = Policy(lg, cfg).accuracy_calibration_heuristic()
+    thr = heuristic_thresholds(cm, 0.1, 6)
+    want, wpred, _ = policy_port.exit_policy(lg, thr, "max_confidence")
+    assert np.array_equal(ex, want) and np.array_equal(pred.numpy(), wpred)
+    with pytest.raises(Exception, match="calibration_metrics"):
+        Policy(lg, {"epsilon": 0.1}).accuracy_calibration_heuristic()
