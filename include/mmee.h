@@ -20,6 +20,10 @@ extern "C" {
 #endif
 
 #define MMEE_MAX_EXITS 64
+/* embedding-level exits in exit_after_layer (EE/models/LayoutLMv3.py:465-483, 519-534, 581-606) */
+#define MMEE_EXIT_VISION_AVG (-2)   /* mean of the visual embeddings */
+#define MMEE_EXIT_TEXT_AVG   (-1)   /* mean of the text embeddings */
+#define MMEE_EXIT_CONCAT       0    /* mean of the fused [text | visual] embeddings */
 
 typedef struct mmee_engine mmee_engine;
 
@@ -36,7 +40,8 @@ typedef struct {
   int pad_id;
   float ln_eps, vis_ln_eps;
   int n_exits;                             /* E early exits, final classifier not counted */
-  int exit_after_layer[MMEE_MAX_EXITS];    /* ascending; 0 = text_visual_concat (embedding-level), 1..layers */
+  int exit_after_layer[MMEE_MAX_EXITS];    /* ascending; -2 / -1 / 0 = vision_avg / text_avg / text_visual_concat
+                                              (embedding-level, see above), 1..layers = after that encoder layer */
   int head_kind;                           /* 0 ramp (EarlyExitHead.RAMP), 1 gate (EarlyExitHead.GATE) */
   int head_layers;                         /* exit_head_num_layers: 1 | 2 */
 } mmee_model_desc;

@@ -99,7 +99,8 @@ __device__ __forceinline__ void warp_layernorm4(float4 (&v)[NV4], int H, const f
 template <int NV4>
 __global__ void text_embed_vec_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ bbox,
                                       const int* __restrict__ posid, EmbedWeights W, __nv_bfloat16* __restrict__ X,
-                                      int n_docs, int n_text, int seq, int H, int coord, int shape, float eps) {
+                                      float* __restrict__ pre, int n_docs, int n_text, int seq, int H, int coord,
+                                      int shape, float eps) {
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= n_docs * n_text) return;
   const int lane = threadIdx.x & 31;
@@ -139,6 +140,10 @@ __global__ void text_embed_vec_kernel(const int64_t* __restrict__ ids, const int
     v[i].w = ((wv[i].w + tv[i].w) + pv[i].w) + sv[i].w;
   }
   warp_layernorm4<NV4>(v, H, W.ln_emb_w, W.ln_emb_b, eps, lane);
+  if (pre) {                                            // text embeddings before the model LayerNorm (text_avg exit)
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) *reinterpret_cast<float4*>(pre + static_cast<size_t>(tok) * H + 4 * (lane + 32 * i)) = v[i];
+  }
   warp_layernorm4<NV4>(v, H, W.ln_model_w, W.ln_model_b, eps, lane);
   __nv_bfloat16* out = X + (static_cast<size_t>(doc) * seq + t) * H;
 #pragma unroll
@@ -151,7 +156,8 @@ __global__ void text_embed_vec_kernel(const int64_t* __restrict__ ids, const int
 template <int NV>
 __global__ void text_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ bbox,
                                   const int* __restrict__ posid, EmbedWeights W, __nv_bfloat16* __restrict__ X,
-                                  int n_docs, int n_text, int seq, int H, int coord, int shape, float eps) {
+                                  float* __restrict__ pre, int n_docs, int n_text, int seq, int H, int coord, int shape,
+                                  float eps) {
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= n_docs * n_text) return;
   const int lane = threadIdx.x & 31;
@@ -185,6 +191,10 @@ __global__ void text_embed_kernel(const int64_t* __restrict__ ids, const int64_t
     v[i] = e;
   }
   warp_layernorm<NV>(v, H, W.ln_emb_w, W.ln_emb_b, eps, lane);
+  if (pre) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) if (lane + 32 * i < H) pre[static_cast<size_t>(tok) * H + lane + 32 * i] = v[i];
+  }
   warp_layernorm<NV>(v, H, W.ln_model_w, W.ln_model_b, eps, lane);
   __nv_bfloat16* out = X + (static_cast<size_t>(doc) * seq + t) * H;
 #pragma unroll
@@ -217,8 +227,9 @@ __global__ void im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __res
 
 // one warp per visual token (doc, p); VIS rows 1..n_patch hold conv + bias + pos_embed (written by the patch GEMM)
 template <int NV>
-__global__ void visual_ln_kernel(const float* __restrict__ VIS, EmbedWeights W, __nv_bfloat16* __restrict__ X,
-                                 int n_docs, int n_vis, int n_text, int seq, int H, float eps_vis, float eps) {
+__global__ void visual_ln_kernel(float* __restrict__ VIS, EmbedWeights W, __nv_bfloat16* __restrict__ X,
+                                 int write_pre, int n_docs, int n_vis, int n_text, int seq, int H, float eps_vis,
+                                 float eps) {
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= n_docs * n_vis) return;
   const int lane = threadIdx.x & 31;
@@ -233,6 +244,10 @@ __global__ void visual_ln_kernel(const float* __restrict__ VIS, EmbedWeights W, 
     v[i] = e;
   }
   warp_layernorm<NV>(v, H, W.ln_vis_w, W.ln_vis_b, eps_vis, lane);
+  if (write_pre) {                                      // visual embeddings after `norm` (vision_avg exit), in place
+#pragma unroll
+    for (int i = 0; i < NV; ++i) if (lane + 32 * i < H) VIS[(static_cast<size_t>(doc) * n_vis + p) * H + lane + 32 * i] = v[i];
+  }
   warp_layernorm<NV>(v, H, W.ln_model_w, W.ln_model_b, eps, lane);
   __nv_bfloat16* out = X + (static_cast<size_t>(doc) * seq + n_text + p) * H;
 #pragma unroll
@@ -258,6 +273,25 @@ __global__ void meanpool_kernel(const __nv_bfloat16* __restrict__ X, float* __re
 #pragma unroll
     for (int i = 0; i < 8; ++i) tot += part[i][threadIdx.x];
     pool[static_cast<size_t>(doc) * H + c] = tot / seq;
+  }
+}
+
+// fp32 variant: pool[doc][c] = mean_t src[(doc*rows + t)][c]  (vision_avg / text_avg exits, EE/models/LayoutLMv3.py:466, 520)
+__global__ void meanpool_f32_kernel(const float* __restrict__ src, float* __restrict__ pool, int rows, int H) {
+  __shared__ float part[8][33];
+  const int doc = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int w = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < H)
+    for (int t = w; t < rows; t += 8) s += src[(static_cast<size_t>(doc) * rows + t) * H + c];
+  part[w][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (w == 0 && c < H) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += part[i][threadIdx.x];
+    pool[static_cast<size_t>(doc) * H + c] = tot / rows;
   }
 }
 

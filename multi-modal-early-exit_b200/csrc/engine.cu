@@ -154,7 +154,8 @@ struct mmee_engine {
   DevBuf<__nv_bfloat16> X[2], QK, VT, CTX, A1, MID, PATCH;
   DevBuf<__nv_bfloat16> Xlo[2], A1lo;       // low parts of the split-bf16 residual stream (precise_residual)
   bool precise_residual = true;
-  DevBuf<float> Y, VIS, POOL, Z, T0, T1;
+  DevBuf<float> Y, VIS, POOL, POOLV, POOLT, TXT, Z, T0, T1;
+  bool has_vision_exit = false, has_text_exit = false;
   DevBuf<__half> BIAS, bias_t2;
   DevBuf<float> maskadd, bias_t1;
   DevBuf<int> tileflag, att_err;
@@ -413,7 +414,9 @@ void finalize(mmee_engine* e) {
   e->exit_heads.resize(d.n_exits);
   int k_enc = 0;
   for (int x = 0; x < d.n_exits; ++x) {
-    if (d.exit_after_layer[x] == 0) load_head(e, e->exit_heads[x], p + "concat_exit_embeddings", n_head_out);
+    if (d.exit_after_layer[x] == MMEE_EXIT_VISION_AVG) load_head(e, e->exit_heads[x], p + "vision_exit_embeddings", n_head_out);
+    else if (d.exit_after_layer[x] == MMEE_EXIT_TEXT_AVG) load_head(e, e->exit_heads[x], p + "text_exit_embeddings", n_head_out);
+    else if (d.exit_after_layer[x] == 0) load_head(e, e->exit_heads[x], p + "concat_exit_embeddings", n_head_out);
     else load_head(e, e->exit_heads[x], p + "encoder.early_exits." + std::to_string(k_enc++), n_head_out);
   }
   load_head(e, e->classifier, "classifier", d.n_labels);
@@ -466,6 +469,15 @@ void allocate(mmee_engine* e) {
   e->PATCH.alloc(mp * e->kdim_patch, true);
   e->VIS.alloc(static_cast<size_t>(B) * e->n_vis * H, true);
   e->POOL.alloc(static_cast<size_t>(B) * H, true);
+  for (int x = 0; x < e->d.n_exits; ++x) {
+    if (e->d.exit_after_layer[x] == MMEE_EXIT_VISION_AVG) e->has_vision_exit = true;
+    if (e->d.exit_after_layer[x] == MMEE_EXIT_TEXT_AVG) e->has_text_exit = true;
+  }
+  if (e->has_vision_exit) e->POOLV.alloc(static_cast<size_t>(B) * H, true);
+  if (e->has_text_exit) {
+    e->POOLT.alloc(static_cast<size_t>(B) * H, true);
+    e->TXT.alloc(static_cast<size_t>(B) * e->T * H, true);
+  }
   e->Z.alloc(static_cast<size_t>(B) * H, true);
   e->T0.alloc(static_cast<size_t>(B) * H, true);
   e->T1.alloc(static_cast<size_t>(B) * H, true);
@@ -554,7 +566,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   if (H % 128 == 0 && d.coord % 4 == 0 && d.shape % 4 == 0 && H / 128 <= 8) {
     auto go = [&](auto nv4) {
       text_embed_vec_kernel<decltype(nv4)::value><<<(B * T + 7) / 8, 256, 0, st>>>(
-          ids, bbox, e->posid.p, ew, e->X[0].p, B, T, S, H, d.coord, d.shape, d.ln_eps);
+          ids, bbox, e->posid.p, ew, e->X[0].p, e->TXT.p, B, T, S, H, d.coord, d.shape, d.ln_eps);
     };
     switch (H / 128) {
       case 1: go(std::integral_constant<int, 1>{}); break;
@@ -565,13 +577,13 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
       default:
         launch_nv(H, [&](auto nv) {
           text_embed_kernel<decltype(nv)::value><<<(B * T + 7) / 8, 256, 0, st>>>(
-              ids, bbox, e->posid.p, ew, e->X[0].p, B, T, S, H, d.coord, d.shape, d.ln_eps);
+              ids, bbox, e->posid.p, ew, e->X[0].p, e->TXT.p, B, T, S, H, d.coord, d.shape, d.ln_eps);
         });
     }
   } else {
     launch_nv(H, [&](auto nv) {
       text_embed_kernel<decltype(nv)::value><<<(B * T + 7) / 8, 256, 0, st>>>(
-          ids, bbox, e->posid.p, ew, e->X[0].p, B, T, S, H, d.coord, d.shape, d.ln_eps);
+          ids, bbox, e->posid.p, ew, e->X[0].p, e->TXT.p, B, T, S, H, d.coord, d.shape, d.ln_eps);
     });
   }
   e->launches++;
@@ -607,7 +619,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     launch_gemm<EPI_PATCH>(e, e->bn_h, e->t_patch, e->t_patch_w, ga, st);
     launch_nv(H, [&](auto nv) {
       visual_ln_kernel<decltype(nv)::value><<<(B * e->n_vis + 7) / 8, 256, 0, st>>>(
-          e->VIS.p, ew, e->X[0].p, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps);
+          e->VIS.p, ew, e->X[0].p, e->has_vision_exit ? 1 : 0, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps);
     });
     e->launches++;
   }
@@ -677,13 +689,32 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     stage += 1; sd ^= 1; exit_no += 1;
   };
 
-  // ---- embedding-level exit (text_visual_concat): mean over the 709 fused tokens
-  if (E > 0 && d.exit_after_layer[0] == 0) {
-    meanpool_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->X[cur].p, e->POOL.p, S, H);
+  // ---- embedding-level exits, in the reference's order (EE/models/LayoutLMv3.py:465-483 vision_avg: mean of the
+  // visual embeddings after `norm`; :519-534 text_avg: mean of the text embeddings, pads included; :581-606
+  // text_visual_concat: mean over the 709 fused tokens after the model LayerNorm).  The pooled rows are indexed by
+  // document, so each exit reads them through the slot -> document map of the survivors so far.
+  bool any_embedding_exit = false;
+  while (exit_no < E && d.exit_after_layer[exit_no] <= 0) {
+    const int code = d.exit_after_layer[exit_no];
+    const float* pool;
+    if (code == MMEE_EXIT_VISION_AVG) {
+      meanpool_f32_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->VIS.p, e->POOLV.p, e->n_vis, H);
+      pool = e->POOLV.p;
+    } else if (code == MMEE_EXIT_TEXT_AVG) {
+      meanpool_f32_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->TXT.p, e->POOLT.p, T, H);
+      pool = e->POOLT.p;
+    } else {
+      meanpool_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->X[cur].p, e->POOL.p, S, H);
+      pool = e->POOL.p;
+    }
     e->launches++;
-    run_exit(e->POOL.p, H, nullptr, nullptr, e->exit_heads[0], false, nullptr);
-    if (leave) {
-      gather_slots_kernel<<<dim3(32, B), 256, 0, st>>>(e->X[cur].p, e->X[cur ^ 1].p, e->slot_src.p, e->n_dev.p + stage, S, H);
+    const int* doc_map = e->slot_doc[sd].p;
+    run_exit(pool, H, nullptr, nullptr, e->exit_heads[exit_no], false, doc_map);
+    any_embedding_exit = true;
+  }
+  if (any_embedding_exit) {
+    if (leave) {   // X is still in document order: move the survivors' rows to their slots
+      gather_slots_kernel<<<dim3(32, B), 256, 0, st>>>(e->X[cur].p, e->X[cur ^ 1].p, e->slot_doc[sd].p, e->n_dev.p + stage, S, H);
       e->launches++;
       cur ^= 1;
     }
@@ -839,7 +870,7 @@ int mmee_create(const mmee_model_desc* desc, int device, int max_batch, mmee_eng
   if (d.n_labels > 32 || d.n_labels < 2) throw std::runtime_error("n_labels must be in [2, 32]");
   if (d.n_exits < 0 || d.n_exits > MMEE_MAX_EXITS) throw std::runtime_error("bad n_exits");
   for (int i = 0; i < d.n_exits; ++i) {
-    if (d.exit_after_layer[i] < 0 || d.exit_after_layer[i] > d.layers) throw std::runtime_error("exit layer out of range");
+    if (d.exit_after_layer[i] < MMEE_EXIT_VISION_AVG || d.exit_after_layer[i] > d.layers) throw std::runtime_error("exit layer out of range");
     if (i && d.exit_after_layer[i] <= d.exit_after_layer[i - 1]) throw std::runtime_error("exits must be ascending");
   }
   if ((d.channels * d.patch * d.patch) % 64) throw std::runtime_error("patch K dim must be a multiple of 64");

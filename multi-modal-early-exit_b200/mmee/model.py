@@ -76,6 +76,9 @@ def bucket_lut(num_buckets: int, max_distance: int, n: int = 1024) -> np.ndarray
     return torch.where(is_small, rel, large).to(torch.uint8).numpy()
 
 
+EMBEDDING_EXIT_CODES = {"vision_avg": -2, "text_avg": -1, "text_visual_concat": 0}   # include/mmee.h MMEE_EXIT_*
+
+
 class B200EEForSequenceClassification:
     def __init__(self, dims: ModelDims, ee: Union[ExitConfig, dict], state_dict: Dict[str, torch.Tensor],
                  device: int = 0, max_batch: int = 256):
@@ -83,12 +86,14 @@ class B200EEForSequenceClassification:
             ee = ExitConfig.from_dict(ee)
         dims.check()
         for x in ee.exits:
-            if isinstance(x, str) and x != "text_visual_concat":
-                raise NotImplementedError(f"embedding-level exit {x!r} is not built yet (SURVEY.md §8f row 3)")
+            if isinstance(x, str) and x not in EMBEDDING_EXIT_CODES:
+                raise NotImplementedError(f"unknown embedding-level exit {x!r}")
         self.dims, self.ee = dims, ee
         self.device_index = device
         self.max_batch = max_batch
-        self.exit_layers = ([0] if ee.has_concat_exit else []) + sorted(ee.encoder_exit_layers)
+        # reference order: vision_avg, text_avg, text_visual_concat, then the encoder layers (EE/models/LayoutLMv3.py:465-606)
+        self.exit_layers = sorted(EMBEDDING_EXIT_CODES[x] for x in ee.exits if isinstance(x, str)) \
+            + sorted(ee.encoder_exit_layers)
         self.n_exits = len(self.exit_layers)
         self._lib = _lib.load()
         d = _lib.ModelDesc()

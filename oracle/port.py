@@ -167,7 +167,10 @@ def forward(sd, dims, ee, docs, keep_hidden: bool = False) -> Dict[str, torch.Te
     logits, or classifier(CLS_j) "gated logits" in gate mode :764-782; final classifier last),
     head_logits [E,B,K|2] (raw head outputs, = exit_states[j][0]), cls_rows [E+1,B,H]."""
     sd = {k: v.float() for k, v in sd.items()}
-    x = fused_embeddings(sd, dims, docs)
+    tvis = visual_embeddings(sd, dims, docs["pixel_values"])
+    ttxt = text_embeddings(sd, dims, docs["input_ids"], docs["bbox"])
+    x = _ln(torch.cat([ttxt, tvis], dim=1), sd["layoutlmv3.LayerNorm.weight"], sd["layoutlmv3.LayerNorm.bias"],
+            dims.ln_eps)                                     # == fused_embeddings
     B = x.shape[0]
     mask = torch.cat([docs["attention_mask"].to(torch.float32), torch.ones(B, dims.n_vis)], dim=1)
     ext = (1.0 - mask)[:, None, None, :] * torch.finfo(torch.float32).min   # modeling_utils get_extended_attention_mask
@@ -176,6 +179,14 @@ def forward(sd, dims, ee, docs, keep_hidden: bool = False) -> Dict[str, torch.Te
     rows: List[torch.Tensor] = []
     heads: List[torch.Tensor] = []
     hidden = [x] if keep_hidden else None
+    if "vision_avg" in ee.exits:
+        z = tvis.mean(1)                                    # :465-468: mean of the visual embeddings (after `norm`)
+        rows.append(z)
+        heads.append(exit_head(sd, "layoutlmv3.vision_exit_embeddings", z))
+    if "text_avg" in ee.exits:
+        z = ttxt.mean(1)                                    # :519-521: mean of the text embeddings (pads included)
+        rows.append(z)
+        heads.append(exit_head(sd, "layoutlmv3.text_exit_embeddings", z))
     if ee.has_concat_exit:
         z = x.mean(1)                                       # :582 (pads included)
         rows.append(z)

@@ -43,6 +43,11 @@ CASES = {
                                        encoder_layer_strategy="gate", inference_strategy="entropy"), 4, 0, 5, True),
     "large4_ramp_conf": ("large", {"layers": 4}, dict(exits=["text_visual_concat", 2, 4],
                                                      encoder_layer_strategy="ramp", inference_strategy="max_confidence"), 2, 0, 6, True),
+    # all three embedding-level exits (EE/models/LayoutLMv3.py:465-483, 519-534, 581-606), ramp and gate
+    "tiny_modality_ramp": ("tiny", {}, dict(exits=["vision_avg", "text_avg", "text_visual_concat", 1, 3],
+                                            encoder_layer_strategy="ramp", inference_strategy="max_confidence"), 5, 2, 8, True),
+    "tiny_modality_gate": ("tiny", {}, dict(exits=["vision_avg", "text_avg", "text_visual_concat", 2],
+                                            encoder_layer_strategy="gate", inference_strategy="entropy"), 5, 4, 9, True),
     # BASELINE.json configs[3]: LayoutLMv3-large, all 24 layers, ramps every 2 layers
     "large24_ramp2": ("large", {}, dict(exits=["text_visual_concat"] + list(range(2, 25, 2)),
                                         encoder_layer_strategy="ramp", inference_strategy="max_confidence"), 2, 0, 7, True),

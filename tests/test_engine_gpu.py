@@ -90,7 +90,8 @@ def test_early_exit_matches_reference_policy(name):
     print(f"{name}: exit-layer agreement with the reference policy {agree}/{total}")
 
 
-@pytest.mark.parametrize("name", ["tiny_ramp_conf", "tiny_gate_ent", "base_gate_ent"])
+@pytest.mark.parametrize("name", ["tiny_ramp_conf", "tiny_gate_ent", "base_gate_ent", "tiny_modality_ramp",
+                                  "tiny_modality_gate"])
 @pytest.mark.parametrize("criterion", ["max_confidence", "entropy"])
 def test_early_exit_equals_dense_posthoc(name, criterion):
     """Real compaction == post-hoc policy on the engine's own dense logits, bit-exact (per-document
@@ -220,3 +221,45 @@ def test_full_size_batch_properties():
         assert a.exits_store.mean() >= prev_mean
         prev_mean = a.exits_store.mean()
     model.close()
+
+
+def test_get_logits_store_matches_reference_layout(tmp_path):
+    """the batched logits-store loop writes what EE/utils.py:125-271 writes (names, keys, dtypes,
+    which logits per exit) and the post-hoc Policy on that store equals the engine's on-device early exit."""
+    import json
+    import os
+
+    from mmee.pipeline import get_logits
+    from mmee.policy import Policy
+
+    for name in ("tiny_ramp_conf", "tiny_gate_ent"):
+        model, g, dims, ee, sd, docs = _engine(name)
+        n = docs["input_ids"].shape[0]
+        docs = dict(docs)
+        docs["labels"] = torch.arange(n) % dims.n_labels
+        loader = [{k: v[i:i + 4] for k, v in docs.items()} for i in range(0, n, 4)]       # batches of 4 (last: 2)
+        cfg = {"checkpoint": f"org/{name}", "test_dataset": "synthetic/rvl", "downsampling": 0, "labelset": "test",
+               "results_root": str(tmp_path), "exit_threshold": 0.5, "device": "cpu"}
+        logits, refs, _ = get_logits(model, cfg, loader)
+        assert logits.dtype == np.float64 and logits.shape == g["exit_logits"].shape
+        assert np.abs(logits - g["exit_logits"]).max() <= LOGIT_TOL                   # the reference's stored logits
+        assert np.array_equal(refs, docs["labels"].numpy())
+        out = os.path.join(str(tmp_path), "results", f"{name}-rvl")
+        assert sorted(os.listdir(out)) == ["config.json", "exit_logits-test.npz", "references-test.npz"]
+        assert np.array_equal(np.load(os.path.join(out, "exit_logits-test.npz"))["arr_0"], logits)
+        saved = json.load(open(os.path.join(out, "config.json")))
+        assert "exit_threshold" not in saved and saved["checkpoint"] == f"org/{name}"
+        again, refs2, _ = get_logits(model, cfg, loader)                              # cache short-cut
+        assert np.array_equal(again, logits) and np.array_equal(refs2, refs)
+        # post-hoc policy on the store == real early exit on the device (raw logits, max-confidence)
+        ex, pred, _ = Policy(logits=logits, config=cfg).max_confidence_global_thresholding_policy()
+        res = model.infer(**_cuda({k: v for k, v in docs.items()}), exit_threshold=0.5, criterion="max_confidence")
+        crit = policy_port_criterion(logits)
+        decisive = np.abs(crit[:-1] - 0.5).min(axis=0) > 1e-4
+        assert np.array_equal(res.exits_store[decisive], ex[decisive])
+
+
+def policy_port_criterion(logits):
+    from oracle import policy_port
+
+    return policy_port.criterion(logits, "max_confidence")
