@@ -561,6 +561,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   ew.ln_model_w = e->ln_model_w.p; ew.ln_model_b = e->ln_model_b.p; ew.ln_vis_w = e->ln_vis_w.p;
   ew.ln_vis_b = e->ln_vis_b.p; ew.cls_token = e->cls_token.p; ew.pos_embed = e->pos_embed.p;
 
+  if (T > 0) {   // image-only engines (n_text = 0, BASELINE config 5) have no text tokens
   posid_kernel<<<(B + 7) / 8, 256, 0, st>>>(ids, e->posid.p, B, T, d.pad_id);
   e->launches++;
   if (H % 128 == 0 && d.coord % 4 == 0 && d.shape % 4 == 0 && H / 128 <= 8) {
@@ -587,6 +588,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     });
   }
   e->launches++;
+  }
   // pixel-independent work first: on the host path the pixel upload (96 % of the input bytes) overlaps it
   {
     keymask_kernel<<<B, e->kv_pitch, 0, st>>>(mask, e->maskadd.p, e->tileflag.p, T, S, e->kv_pitch, e->n_kv_tiles, ATT_BKV);

@@ -171,8 +171,13 @@ class B200EEForSequenceClassification:
     # ------------------------------------------------------------------ engine call
     def _run(self, input_ids, attention_mask, bbox, pixel_values, criterion: str, mode: int,
              thresholds: Sequence[float], temperatures: Optional[Sequence[float]], want_all: bool):
-        if input_ids is None or pixel_values is None:
-            raise ValueError("the engine runs the multimodal path: input_ids, bbox and pixel_values are required")
+        if pixel_values is None:
+            raise ValueError("pixel_values are required (multimodal and image-only paths)")
+        if input_ids is None:
+            if self.dims.n_text != 0:
+                raise ValueError("this engine was built for the multimodal path: input_ids and bbox are required "
+                                 "(build it with ModelDims(n_text=0) for the image-only path)")
+            input_ids = torch.zeros((pixel_values.shape[0], 0), dtype=torch.int64, device=pixel_values.device)
         B, T = input_ids.shape
         if T != self.dims.n_text:
             raise ValueError(f"expected {self.dims.n_text} text tokens (padding='max_length'), got {T}")

@@ -102,6 +102,12 @@ def make_docs(dims: ModelDims, n: int, seed: int = 1, pad: bool = True) -> Dict[
     """n synthetic documents (SURVEY.md §8(d) recipe).  pad=False -> all n_text tokens real."""
     g = torch.Generator().manual_seed(7919 * (seed + 1))
     T = dims.n_text
+    if T == 0:                                              # image-only documents (BASELINE config 5): patch tokens only
+        pixels = torch.rand((n, dims.channels, dims.image, dims.image), generator=g, dtype=torch.float32) * 2 - 1
+        labels = torch.randint(0, dims.n_labels, (n,), generator=g, dtype=torch.int64)
+        z = torch.zeros((n, 0), dtype=torch.int64)
+        return {"input_ids": z, "attention_mask": z.clone(), "bbox": torch.zeros((n, 0, 4), dtype=torch.int64),
+                "pixel_values": pixels, "labels": labels}
     ids = torch.randint(3, dims.vocab, (n, T), generator=g, dtype=torch.int64)
     if pad:
         lens = torch.randint(min(64, T), T + 1, (n,), generator=g, dtype=torch.int64)

@@ -54,6 +54,8 @@ def relative_position_bucket(rel: torch.Tensor, num_buckets: int, max_distance: 
 def text_embeddings(sd, dims, input_ids, bbox):
     """HF:161-200 with position_ids=None (HF:139-147) and token_type_ids=0; spatial HF:113-137."""
     p = "layoutlmv3.embeddings."
+    if input_ids.shape[1] == 0:                             # image-only path: no text tokens (HF:730-768 with pixel_values only)
+        return torch.zeros((input_ids.shape[0], 0, dims.hidden), dtype=torch.float32)
     mask = input_ids.ne(dims.pad_id).int()
     pos = (torch.cumsum(mask, dim=1).type_as(mask) * mask).long() + dims.pad_id
     e = sd[p + "word_embeddings.weight"][input_ids] + sd[p + "token_type_embeddings.weight"][0]

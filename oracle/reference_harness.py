@@ -122,3 +122,44 @@ def reference_forward(model, docs):
         "criteria": torch.stack(list(out.exit_criteria)).float(),
         "last_hidden": inner.last_hidden_state.float(),
     }
+
+
+def reference_forward_image_only(model, pixel_values):
+    """BASELINE config 5 (image-only, patch tokens only, ramps).  The reference EE model cannot run this through
+    `forward` (UnboundLocalError, EE/models/LayoutLMv3.py:549-565; author's note EE/configs.py:52), so the verified
+    recipe of SURVEY.md Appendix B drives its sub-modules directly with stock-HF image-only semantics (HF:730-768):
+    forward_image -> model LayerNorm -> [concat exit on the mean] -> LayoutLMv3EncoderEE over the 197 visual tokens
+    (visual boxes / positions) -> classifier on the visual CLS token."""
+    import torch
+
+    m = model.layoutlmv3
+    B = pixel_values.shape[0]
+    with torch.no_grad():
+        x = m.dropout(m.LayerNorm(m.forward_image(pixel_values)))
+        n_vis = x.shape[1]
+        heads = []
+        rows = []
+        if hasattr(m, "concat_exit_embeddings"):
+            z = x.mean(1)
+            rows.append(z)
+            heads.append(m.concat_exit_embeddings(z))
+        ext = m.get_extended_attention_mask(torch.ones(B, n_vis), None, x.device, dtype=x.dtype)
+        side = int(pixel_values.shape[2] / m.config.patch_size)
+        enc = m.encoder(x, bbox=m.calculate_visual_bbox(x.device, dtype=torch.long, batch_size=B),
+                        position_ids=torch.arange(n_vis)[None].repeat(B, 1), attention_mask=ext,
+                        head_mask=[None] * m.config.num_hidden_layers, return_dict=True,
+                        patch_height=side, patch_width=side)
+        for st in enc.exit_states:
+            heads.append(st[0] if isinstance(st, tuple) else st)
+        rows += list(enc.gate_inputs) if model.apply_gating else []
+        last = enc[0]
+        final = model.classifier(last[:, 0, :])
+        gate = model.apply_gating
+        per_exit = [model.classifier(z) for z in rows] if gate else heads
+        crit = [model.layoutlmv3.exit_criterion(h) for h in heads] + [model.layoutlmv3.exit_criterion(final)]
+    return {
+        "exit_logits": torch.stack(per_exit + [final]).float(),
+        "head_logits": torch.stack(heads).float(),
+        "criteria": torch.stack(crit).float(),
+        "last_hidden": last.float(),
+    }

@@ -48,6 +48,12 @@ CASES = {
                                             encoder_layer_strategy="ramp", inference_strategy="max_confidence"), 5, 2, 8, True),
     "tiny_modality_gate": ("tiny", {}, dict(exits=["vision_avg", "text_avg", "text_visual_concat", 2],
                                             encoder_layer_strategy="gate", inference_strategy="entropy"), 5, 4, 9, True),
+    # BASELINE.json configs[4]: image-only path (patch tokens only, n_text = 0) with ramps
+    "tiny_image_only": ("tiny", {"n_text": 0}, dict(exits=["text_visual_concat", 1, 2, 3], encoder_layer_strategy="ramp",
+                                                    inference_strategy="max_confidence"), 6, 5, 10, True),
+    "base2_image_only": ("base", {"n_text": 0, "layers": 2}, dict(exits=["text_visual_concat", 1, 2],
+                                                                  encoder_layer_strategy="ramp",
+                                                                  inference_strategy="max_confidence"), 3, 0, 11, True),
     # BASELINE.json configs[3]: LayoutLMv3-large, all 24 layers, ramps every 2 layers
     "large24_ramp2": ("large", {}, dict(exits=["text_visual_concat"] + list(range(2, 25, 2)),
                                         encoder_layer_strategy="ramp", inference_strategy="max_confidence"), 2, 0, 7, True),
@@ -62,7 +68,7 @@ def run_case(name):
     docs = synth.make_docs(dims, n, seed=dseed, pad=pad)
     t0 = time.time()
     model = RH.build_reference_model(dims, ee, sd)
-    ref = RH.reference_forward(model, docs)
+    ref = RH.reference_forward(model, docs) if dims.n_text else RH.reference_forward_image_only(model, docs["pixel_values"])
     dt = time.time() - t0
     # reference Policy on the stored logits (EE/eval.py:91-98 call shape), raw and temperature-scaled
     sys.path.insert(0, os.path.join(RH.REFERENCE_ROOT, "EE"))

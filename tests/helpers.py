@@ -10,7 +10,7 @@ from mmee.config import ExitConfig, ModelDims
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ALL_CASES = ["tiny_ramp_conf", "tiny_gate_ent", "tiny_ramp_1layer_head",
              "base_ramp_conf", "base_gate_ent", "large4_ramp_conf", "large24_ramp2",
-             "tiny_modality_ramp", "tiny_modality_gate"]
+             "tiny_modality_ramp", "tiny_modality_gate", "tiny_image_only", "base2_image_only"]
 
 
 def load_case(name):

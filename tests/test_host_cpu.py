@@ -218,3 +218,16 @@ def test_policy_host_logic_and_loud_failure():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CUDA device|libmmee"):
             Policy(np.zeros((3, 4, 5)), {"exit_threshold": 0.5}).max_confidence_global_thresholding_policy()
+
+
+def test_image_only_documents_and_port():
+    """BASELINE config 5 shape: n_text = 0 -> 197 visual tokens; the oracle port runs it (CPU, tiny dims)."""
+    dims = ModelDims.tiny(n_text=0, layers=1)
+    assert dims.seq == dims.n_vis == 197
+    docs = synth.make_docs(dims, 2, seed=4)
+    assert docs["input_ids"].shape == (2, 0) and docs["bbox"].shape == (2, 0, 4)
+    ee = ExitConfig.from_dict(dict(exits=["text_visual_concat", 1]))
+    sd = synth.make_state_dict(dims, ee, seed=1)
+    out = port.forward(sd, dims, ee, docs)
+    assert out["exit_logits"].shape == (3, 2, dims.n_labels) and out["last_hidden"].shape == (2, 197, dims.hidden)
+    assert torch.isfinite(out["exit_logits"]).all()
