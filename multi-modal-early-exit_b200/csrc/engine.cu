@@ -364,11 +364,12 @@ void finalize(mmee_engine* e) {
     std::vector<float> T1(static_cast<size_t>(d.rel_bins) * h);
     for (int b1 = 0; b1 < d.rel_bins; ++b1)
       for (int hh = 0; hh < h; ++hh) T1[static_cast<size_t>(b1) * h + hh] = t1[static_cast<size_t>(hh) * d.rel_bins + b1] * qscale;
-    std::vector<__half> T2(static_cast<size_t>(d.rel2d_bins) * d.rel2d_bins * h);
+    const int t2p = h + 2;                       // row pitch in halves: (h + 2) / 2 words is odd for h = 12, 16, 2 (bank spread)
+    std::vector<__half> T2(static_cast<size_t>(d.rel2d_bins) * d.rel2d_bins * t2p, __float2half_rn(0.f));
     for (int bx = 0; bx < d.rel2d_bins; ++bx)
       for (int by = 0; by < d.rel2d_bins; ++by)
         for (int hh = 0; hh < h; ++hh)
-          T2[(static_cast<size_t>(bx) * d.rel2d_bins + by) * h + hh] = __float2half_rn(
+          T2[(static_cast<size_t>(bx) * d.rel2d_bins + by) * t2p + hh] = __float2half_rn(
               (tx[static_cast<size_t>(hh) * d.rel2d_bins + bx] + ty[static_cast<size_t>(hh) * d.rel2d_bins + by]) * qscale);
     upload_f32(e->bias_t1, T1);
     e->bias_t2.alloc(T2.size());
@@ -596,7 +597,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     ba.bbox = bbox; ba.vis_bbox = e->vis_bbox.p; ba.t1 = e->bias_t1.p; ba.t2 = e->bias_t2.p;
     ba.lut1 = e->lut1.p; ba.lut2 = e->lut2.p; ba.lut1_n = static_cast<int>(e->lut1.n); ba.lut2_n = static_cast<int>(e->lut2.n);
     ba.maskadd = e->maskadd.p;
-    ba.bins1 = d.rel_bins; ba.bins2 = d.rel2d_bins; ba.heads = heads; ba.n_text = T; ba.seq = S; ba.pitch = e->bias_pitch;
+    ba.bins1 = d.rel_bins; ba.bins2 = d.rel2d_bins; ba.heads = heads; ba.t2_pitch = heads + 2; ba.n_text = T; ba.seq = S; ba.pitch = e->bias_pitch;
     ba.kv_pitch = e->kv_pitch; ba.B = B; ba.out = e->BIAS.p;
     const size_t smem = bias_build_smem(ba);
     static bool configured = false;

@@ -67,13 +67,14 @@ struct BiasArgs {
   const int64_t* bbox;       // [B, n_text, 4]
   const int* vis_bbox;       // [n_vis, 4]
   const float* t1;           // [bins1][heads]            W1d * log2(e)/sqrt(d)
-  const __half* t2;          // [bins2*bins2][heads]      (Wx + Wy) * log2(e)/sqrt(d)
+  const __half* t2;          // [bins2*bins2][t2_pitch]   (Wx + Wy) * log2(e)/sqrt(d); row pitch heads + 2 halves = an odd
+                             //                           number of 32-bit words, so random rows spread over all smem banks
   const uint8_t* lut1;       // |rel| -> bucket offset, 1-D   (size lut1_n)
   const uint8_t* lut2;       // 2-D
   const float* maskadd;      // [B][kv_pitch] 0 / -inf per key (padding, j >= seq)
   int lut1_n, lut2_n;
   int bins1, bins2;          // rel_pos_bins, rel_2d_pos_bins
-  int heads, n_text, seq, pitch, kv_pitch, B;
+  int heads, t2_pitch, n_text, seq, pitch, kv_pitch, B;
   __half* out;               // [B][heads][seq][pitch]
 };
 
@@ -81,14 +82,14 @@ constexpr int BIAS_THREADS = 768;
 constexpr float BIAS_MASKED = -60000.0f;   // finite (0 * x stays 0 in the identity MMA) and exp2() of it is 0
 
 inline size_t bias_build_smem(const BiasArgs& a) {
-  return static_cast<size_t>(a.bins2) * a.bins2 * a.heads * 2 + static_cast<size_t>(a.bins1) * a.heads * 4 + a.lut1_n +
+  return static_cast<size_t>(a.bins2) * a.bins2 * a.t2_pitch * 2 + static_cast<size_t>(a.bins1) * a.heads * 4 + a.lut1_n +
          a.lut2_n + static_cast<size_t>(a.pitch) * 16 + 64;
 }
 
 // thread = 8 consecutive keys j of one query row i; a pass covers blockDim / (pitch/8) rows of one document.
 __global__ void __launch_bounds__(BIAS_THREADS, 1) bias_build_kernel(BiasArgs a) {
   extern __shared__ __align__(16) uint8_t bsm[];
-  const int n_t2 = a.bins2 * a.bins2 * a.heads;
+  const int n_t2 = a.bins2 * a.bins2 * a.t2_pitch;
   __half* s_t2 = reinterpret_cast<__half*>(bsm);
   float* s_t1 = reinterpret_cast<float*>(bsm + static_cast<size_t>(n_t2) * 2);
   int* s_pos = reinterpret_cast<int*>(s_t1 + a.bins1 * a.heads);      // [pitch] each
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(BIAS_THREADS, 1) bias_build_kernel(BiasArgs a)
       const int bx = (rx > 0 ? half2 : 0) + s_l2[min(abs(rx), a.lut2_n - 1)];
       const int by = (ry > 0 ? half2 : 0) + s_l2[min(abs(ry), a.lut2_n - 1)];
       i1[k] = static_cast<uint32_t>(b1 * a.heads);
-      i2[k] = static_cast<uint32_t>((bx * a.bins2 + by) * a.heads);
+      i2[k] = static_cast<uint32_t>((bx * a.bins2 + by) * a.t2_pitch);
       mbits |= static_cast<uint32_t>(s_m[j]) << k;
     }
     __half* out = a.out + ((static_cast<size_t>(doc) * a.heads) * a.seq + i) * a.pitch + j0;
@@ -159,9 +160,13 @@ __global__ void __launch_bounds__(BIAS_THREADS, 1) bias_build_kernel(BiasArgs a)
       for (int k = 0; k < 8; ++k) {
         const float2 t1 = *reinterpret_cast<const float2*>(s_t1 + i1[k] + h);
         const float2 t2 = __half22float2(*reinterpret_cast<const __half2*>(s_t2 + i2[k] + h));
-        const bool m = (mbits >> k) & 1u;
-        v0[k] = m ? BIAS_MASKED : t1.x + t2.x;
-        v1[k] = m ? BIAS_MASKED : t1.y + t2.y;
+        v0[k] = t1.x + t2.x;
+        v1[k] = t1.y + t2.y;
+      }
+      if (mbits) {                                     // padded keys (rare): the mask rides in the bias
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if ((mbits >> k) & 1u) { v0[k] = BIAS_MASKED; v1[k] = BIAS_MASKED; }
       }
       auto pack = [](float lo, float hi) {
         __half2 t = __floats2half2_rn(lo, hi);

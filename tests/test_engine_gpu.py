@@ -263,3 +263,27 @@ def policy_port_criterion(logits):
     from oracle import policy_port
 
     return policy_port.criterion(logits, "max_confidence")
+
+
+def test_larger_batch_parity_vs_port():
+    """Error tail at a larger batch than the goldens hold: 24 base documents (padded and unpadded), all 14 exits, engine
+    vs the oracle port run on the box's host cores (the port itself is pinned to the reference goldens, max|d| = 0)."""
+    from mmee.model import B200EEForSequenceClassification
+    from oracle import port
+
+    dims = ModelDims.base()
+    ee = ExitConfig.from_dict(dict(exits=["text_visual_concat"] + list(range(1, 13)), encoder_layer_strategy="gate",
+                                   inference_strategy="entropy"))
+    sd = synth.make_state_dict(dims, ee, seed=3)
+    docs = synth.make_docs(dims, 24, seed=31, pad=True)
+    model = B200EEForSequenceClassification(dims, ee, sd, device=0, max_batch=24)
+    got = model.forward(**_cuda(docs)).exit_logits.cpu().numpy()
+    torch.set_num_threads(max(1, (torch.get_num_threads())))
+    want = port.forward(sd, dims, ee, docs)["exit_logits"].numpy()
+    err = np.abs(got - want)
+    print(f"24 base docs x 14 exits: max|logits - port| = {err.max():.3e}, mean = {err.mean():.3e}")
+    assert err.max() <= LOGIT_TOL
+    srt = np.sort(want, axis=-1)
+    decisive = (srt[..., -1] - srt[..., -2]) > 2 * LOGIT_TOL
+    assert (got.argmax(-1) == want.argmax(-1))[decisive].all()
+    model.close()
