@@ -281,12 +281,13 @@ void launch_gemm_t(mmee_engine* e, const CUtensorMap& ta, const CUtensorMap& tb,
 template <int EPI>
 void launch_gemm_pair(mmee_engine* e, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t st) {
   auto kern = gemm_tc_pair_kernel<EPI>;
+  using PS = GemmPairSmemT<gemm_pair_epi_warps<EPI>()>;
   static bool configured = false;
   if (!configured) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmPairSmem::DYN_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PS::DYN_BYTES));
     configured = true;
   }
-  kern<<<e->sms & ~1, GEMM_THREADS, GemmPairSmem::DYN_BYTES, st>>>(ta, tb, a);
+  kern<<<e->sms & ~1, PS::THREADS, PS::DYN_BYTES, st>>>(ta, tb, a);
   CUDA_OK(cudaGetLastError());
   e->launches++;
 }

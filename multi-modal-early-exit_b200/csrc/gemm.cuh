@@ -85,8 +85,8 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 }
 
 // Epilogue of one 128-row x BLOCK_N accumulator for one epilogue warp (TMEM lane quarter `quarter`, column half
-// `half`): TMEM -> registers -> (+bias, activation) -> per-warp swizzled smem transpose -> coalesced global stores.
-template <int BLOCK_N, int EPI>
+// `half` of PARTS column parts): TMEM -> registers -> (+bias, activation) -> per-warp swizzled smem transpose -> coalesced global stores.
+template <int BLOCK_N, int EPI, int PARTS = 2>
 __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, int m0, int n0, uint32_t tmem_acc,
                                                    uint8_t* stg, int quarter, int half, int lane) {
       const int row_base = m0 + quarter * 32;     // first row of this warp's 32-row slab
@@ -95,7 +95,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
       const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
 
 #pragma unroll 1
-      for (int c = half * (BLOCK_N / 2); c < (half + 1) * (BLOCK_N / 2); c += 32) {
+      for (int c = half * (BLOCK_N / PARTS); c < (half + 1) * (BLOCK_N / PARTS); c += 32) {
         const int n = n0 + c;
         uint2 rs[8], rl[8];
         if constexpr (EPI == EPI_RESID_F32) {       // residual loads first: independent of the accumulator
@@ -335,22 +335,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // L2 -> SM operand traffic at these shapes, see profiles/).  The leader (cluster rank 0) issues every MMA; its
 // tcgen05.commit is multicast to the stage / accumulator barriers of both CTAs; both CTAs' epilogue warps release
 // the accumulator on the leader's barrier.  Epilogue as above, each CTA for its own 128 rows.
-struct GemmPairSmem {
+// EPI_WARPS: 8 (two column halves per TMEM lane quarter) or 16 (four column quarters: twice the epilogue issue
+// bandwidth for the math-heavy GELU / QKV epilogues; the residual epilogue needs too many registers for 576 threads).
+template <int EPI_WARPS>
+struct GemmPairSmemT {
   static constexpr int STAGES = 5;
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;       // 16 KB
   static constexpr int B_BYTES = 128 * GEMM_BLOCK_K * 2;                // 16 KB: this CTA's half of the 256 columns
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = STG_OFF + GEMM_EPI_WARPS * 4096;
+  static constexpr int BAR_OFF = STG_OFF + EPI_WARPS * 4096;
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL;                               // dynamic smem base is 1024 B aligned
+  static constexpr int THREADS = 64 + EPI_WARPS * 32;
 };
+using GemmPairSmem = GemmPairSmemT<8>;
+template <int EPI>
+__host__ __device__ constexpr int gemm_pair_epi_warps() { return EPI == EPI_RESID_F32 ? 8 : 16; }
 
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + gemm_pair_epi_warps<EPI>() * 32, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmArgs args) {
-  using SM = GemmPairSmem;
+  constexpr int EPI_WARPS = gemm_pair_epi_warps<EPI>();
+  constexpr int PARTS = EPI_WARPS / 4;
+  using SM = GemmPairSmemT<EPI_WARPS>;
   constexpr int STAGES = SM::STAGES;
   constexpr int BLOCK_N = 256;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -384,7 +393,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bars + 2 * STAGES + i, 1);                          // tmem_full: multicast commit
-      mbar_init(bars + 2 * STAGES + 2 + i, 2 * GEMM_EPI_WARPS);     // tmem_empty: epilogue warps of both CTAs
+      mbar_init(bars + 2 * STAGES + 2 + i, 2 * EPI_WARPS);          // tmem_empty: epilogue warps of both CTAs
     }
     fence_mbar_init();
   }
@@ -441,7 +450,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps (2..9), both CTAs
+    // ------------------------------------------------------------ epilogue warps (2..), both CTAs
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     uint8_t* stg = smem + SM::STG_OFF + (warp - 2) * 4096;
@@ -457,9 +466,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (nt < total_tiles) {
           const int pr = (nt / n_blocks) * 2 * GEMM_BLOCK_M + static_cast<int>(rank) * GEMM_BLOCK_M + quarter * 32 + lane;
           if (pr < M) {
-            const size_t off = static_cast<size_t>(pr) * args.N + (nt % n_blocks) * BLOCK_N + half * (BLOCK_N / 2);
+            const size_t off = static_cast<size_t>(pr) * args.N + (nt % n_blocks) * BLOCK_N + half * (BLOCK_N / PARTS);
 #pragma unroll
-            for (int b = 0; b < BLOCK_N; b += 128) {     // BLOCK_N/2 bf16 = BLOCK_N bytes per row
+            for (int b = 0; b < 2 * BLOCK_N / PARTS; b += 128) {     // BLOCK_N/PARTS bf16 per row
               asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(args.resid + off) + b));
               if (args.resid_lo)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(args.resid_lo + off) + b));
@@ -469,7 +478,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       mbar_wait(tmem_full + acc * 8, acc_phase);
       tc_fence_after();
-      gemm_epilogue_warp<BLOCK_N, EPI>(args, M, m0, n0, tmem_base + acc * BLOCK_N, stg, quarter, half, lane);
+      gemm_epilogue_warp<BLOCK_N, EPI, PARTS>(args, M, m0, n0, tmem_base + acc * BLOCK_N, stg, quarter, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tmem_empty + acc * 8, 0);

@@ -48,8 +48,9 @@ template <int BN, int EPI>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int sms, cudaStream_t st = 0) {
   if (g_pair && BN == 256) {
     auto kp = gemm_tc_pair_kernel<EPI>;
-    CK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmPairSmem::DYN_BYTES));
-    kp<<<sms & ~1, GEMM_THREADS, GemmPairSmem::DYN_BYTES, st>>>(ta, tb, a);
+    using PS = GemmPairSmemT<gemm_pair_epi_warps<EPI>()>;
+    CK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, PS::DYN_BYTES));
+    kp<<<sms & ~1, PS::THREADS, PS::DYN_BYTES, st>>>(ta, tb, a);
     return;
   }
   auto kern = gemm_tc_kernel<BN, EPI>;
