@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -310,6 +311,30 @@ void launch_nv(int H, F&& f) {   // dispatch on values-per-lane for the warp-per
   else if (H <= 768) f(std::integral_constant<int, 24>{});
   else if (H <= 1024) f(std::integral_constant<int, 32>{});
   else throw std::runtime_error("hidden size > 1024 not supported");
+}
+
+// LayerNorm of the active rows (fp32 Y -> bf16 X [+ low part]); vectorised when H is a multiple of 128
+void launch_ln(mmee_engine* e, const float* Y, __nv_bfloat16* X, __nv_bfloat16* Xlo, const float* w, const float* b,
+               int B, const int* m_dev, const int* slot_src, cudaStream_t st) {
+  const int H = e->H, S = e->S;
+  const float eps = e->d.ln_eps;
+  const int rows = B * S;
+  auto vec = [&](auto nv4) {
+    const int blocks = std::min((rows + 7) / 8, e->sms * 16);      // grid-stride over rows, 8 warps per block
+    ln_rows_vec_kernel<decltype(nv4)::value><<<blocks, 256, 0, st>>>(Y, X, Xlo, w, b, eps, H, S, m_dev, slot_src);
+  };
+  switch (H % 128 == 0 ? H / 128 : 0) {
+    case 1: vec(std::integral_constant<int, 1>{}); break;
+    case 2: vec(std::integral_constant<int, 2>{}); break;
+    case 4: vec(std::integral_constant<int, 4>{}); break;
+    case 6: vec(std::integral_constant<int, 6>{}); break;
+    case 8: vec(std::integral_constant<int, 8>{}); break;
+    default:
+      launch_nv(H, [&](auto nv) {
+        ln_rows_kernel<decltype(nv)::value><<<(rows + 7) / 8, 256, 0, st>>>(Y, X, Xlo, w, b, eps, H, S, m_dev, slot_src);
+      });
+  }
+  CUDA_OK(cudaGetLastError());
 }
 
 void mark(mmee_engine* e, const char* name, cudaStream_t st) {
@@ -767,10 +792,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     ga.resid_lo = x_lo_valid ? e->Xlo[cur].p : nullptr;
     launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_ctx, w.t_wo, ga, st);
     mark(e, "gemm", st);
-    launch_nv(H, [&](auto nv) {
-      ln_rows_kernel<decltype(nv)::value><<<(B * S + 7) / 8, 256, 0, st>>>(e->Y.p, e->A1.p, e->A1lo.p, w.ln1_w.p, w.ln1_b.p,
-                                                                          d.ln_eps, H, S, mdev, nullptr);
-    });
+    launch_ln(e, e->Y.p, e->A1.p, e->A1lo.p, w.ln1_w.p, w.ln1_b.p, B, mdev, nullptr, st);
     e->launches++;
     mark(e, "norm", st);
 
@@ -792,10 +814,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
       mark(e, "exit", st);
     }
     if (!last) {
-      launch_nv(H, [&](auto nv) {
-        ln_rows_kernel<decltype(nv)::value><<<(B * S + 7) / 8, 256, 0, st>>>(
-            e->Y.p, e->X[cur ^ 1].p, e->Xlo[cur ^ 1].p, w.ln2_w.p, w.ln2_b.p, d.ln_eps, H, S, e->m_dev.p + stage, ln_src);
-      });
+      launch_ln(e, e->Y.p, e->X[cur ^ 1].p, e->Xlo[cur ^ 1].p, w.ln2_w.p, w.ln2_b.p, B, e->m_dev.p + stage, ln_src, st);
       e->launches++;
       cur ^= 1;
       x_lo_valid = e->precise_residual;

@@ -52,6 +52,62 @@ __global__ void ln_rows_kernel(const float* __restrict__ Y, __nv_bfloat16* __res
   }
 }
 
+// Vectorised variant for H = 128 * NV4: every lane owns whole float4s (columns 4*(lane + 32*i) .. +3), 16 B loads and
+// 8 B stores; two rows per warp iteration keep more loads in flight (the kernel is a pure HBM stream:
+// 4 B read + 2 (+2) B written per element).
+template <int NV4>
+__global__ void __launch_bounds__(256) ln_rows_vec_kernel(const float* __restrict__ Y, __nv_bfloat16* __restrict__ X,
+                                                          __nv_bfloat16* __restrict__ Xlo, const float* __restrict__ w,
+                                                          const float* __restrict__ b, float eps, int H, int seq,
+                                                          const int* __restrict__ m_dst_dev,
+                                                          const int* __restrict__ slot_src) {
+  const int lane = threadIdx.x & 31;
+  const int M = *m_dst_dev;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  float4 w4[NV4], b4[NV4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    w4[i] = __ldg(reinterpret_cast<const float4*>(w + 4 * (lane + 32 * i)));
+    b4[i] = __ldg(reinterpret_cast<const float4*>(b + 4 * (lane + 32 * i)));
+  }
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps_total) {
+    size_t src_row = row;
+    if (slot_src) {
+      const int s = row / seq;
+      src_row = static_cast<size_t>(slot_src[s]) * seq + (row - s * seq);
+    }
+    const float* y = Y + src_row * H;
+    float4 v[NV4];
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) v[i] = __ldcs(reinterpret_cast<const float4*>(y + 4 * (lane + 32 * i)));   // streamed once
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) / H;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / H + eps);
+    __nv_bfloat16* out = X + static_cast<size_t>(row) * H;
+    __nv_bfloat16* out_lo = Xlo ? Xlo + static_cast<size_t>(row) * H : nullptr;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const float o0 = (v[i].x - mean) * rstd * w4[i].x + b4[i].x, o1 = (v[i].y - mean) * rstd * w4[i].y + b4[i].y;
+      const float o2 = (v[i].z - mean) * rstd * w4[i].z + b4[i].z, o3 = (v[i].w - mean) * rstd * w4[i].w + b4[i].w;
+      const uint32_t h01 = pack_bf16x2(o0, o1), h23 = pack_bf16x2(o2, o3);
+      *reinterpret_cast<uint2*>(out + 4 * (lane + 32 * i)) = make_uint2(h01, h23);
+      if (out_lo) {
+        const float2 f01 = unpack_bf16x2(h01), f23 = unpack_bf16x2(h23);
+        *reinterpret_cast<uint2*>(out_lo + 4 * (lane + 32 * i)) =
+            make_uint2(pack_bf16x2(o0 - f01.x, o1 - f01.y), pack_bf16x2(o2 - f23.x, o3 - f23.y));
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ attention bias
 // The additive attention bias (rel_pos + rel_2d_pos)/sqrt(d) is layer-invariant (the reference builds it once per
 // forward, EE/models/LayoutLMv3.py:170-179; HF:393-458).  It is materialised once per forward as fp16 in the log2
