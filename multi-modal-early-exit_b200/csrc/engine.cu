@@ -267,7 +267,8 @@ void load_head(mmee_engine* e, HeadW& h, const std::string& prefix, int n_out) {
 template <int BN, int EPI>
 void launch_gemm_t(mmee_engine* e, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t st) {
   auto kern = gemm_tc_kernel<BN, EPI>;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[e->device & 63];   // the attribute is per device
   if (!configured) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::DYN_BYTES));
     configured = true;
@@ -283,7 +284,8 @@ template <int EPI>
 void launch_gemm_pair(mmee_engine* e, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t st) {
   auto kern = gemm_tc_pair_kernel<EPI>;
   using PS = GemmPairSmemT<gemm_pair_epi_warps<EPI>()>;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool& configured = configured_dev[e->device & 63];   // the attribute is per device
   if (!configured) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PS::DYN_BYTES));
     configured = true;
@@ -626,7 +628,8 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     ba.bins1 = d.rel_bins; ba.bins2 = d.rel2d_bins; ba.heads = heads; ba.t2_pitch = heads + 2; ba.n_text = T; ba.seq = S; ba.pitch = e->bias_pitch;
     ba.kv_pitch = e->kv_pitch; ba.B = B; ba.out = e->BIAS.p;
     const size_t smem = bias_build_smem(ba);
-    static bool configured = false;
+    static bool configured_dev[64] = {};
+    bool& configured = configured_dev[e->device & 63];   // the attribute is per device
     if (!configured) {
       CUDA_OK(cudaFuncSetAttribute(bias_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = true;
@@ -706,7 +709,8 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     ca.all_logits = want_all ? e->all_logits.p : nullptr; ca.all_head = want_all ? e->all_head.p : nullptr;
     ca.all_crit = want_all ? e->all_crit.p : nullptr; ca.B = B; ca.n_head_max = K; ca.hist = e->hist.p;
     const size_t smem = exit_fused_smem(H);
-    static bool configured = false;
+    static bool configured_dev[64] = {};
+    bool& configured = configured_dev[e->device & 63];   // the attribute is per device
     if (!configured) {
       CUDA_OK(cudaFuncSetAttribute(exit_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       configured = true;
@@ -770,7 +774,8 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     aa.n_active_dev = e->n_dev.p + stage; aa.slot_meta = e->slot_meta.p; aa.ctx = e->CTX.p; aa.H = H;
     aa.heads = heads; aa.seq = S; aa.err_flag = e->att_err.p; aa.trace = e->att_trace.p;
     {
-      static bool configured = false;
+      static bool configured_dev[64] = {};
+      bool& configured = configured_dev[e->device & 63];   // the attribute is per device
       if (!configured) {
         CUDA_OK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
         CUDA_OK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
