@@ -59,17 +59,50 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clock + throttle reasons for one GPU while the timed region runs."""
+    """Samples the SM clock + throttle reasons of one GPU while the timed region runs: in-process NVML (cheap enough
+    for a 20 ms period, no driver-lock storms when 8 ranks share a box), `nvidia-smi` as the fallback."""
 
-    def __init__(self, index: int):
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
+
+    def __init__(self, index: int, enabled: bool = True):
         self.index = index
+        self.enabled = enabled
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
+        self.source = None
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
 
+    def _nvml_handle(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
     def _run(self):
+        try:
+            nv, h = self._nvml_handle()
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.source = "nvml"
+            while not self._stop.is_set():
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+                self._stop.wait(0.02)
+            return
+        except Exception:
+            pass
+        self.source = "nvidia-smi"
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -87,16 +120,18 @@ class ClockSampler:
             self._stop.wait(0.2)
 
     def __enter__(self):
-        self._t.start()
+        if self.enabled:
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self.enabled:
+            self._t.join(timeout=6)
 
     def summary(self):
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
 
 
 def layer_flops(dims: ModelDims):
@@ -201,14 +236,19 @@ def main():
     packed_all = torch.empty((world * B, K + 2), dtype=torch.float32, device=dev)
 
     def step_device():
-        r = model.infer(**dev_docs, exit_threshold=thr, temperatures=temps)
-        if world > 1:
-            from mmee.dist import gather_results_fixed
+        if world == 1:
+            return model.infer(**dev_docs, exit_threshold=thr, temperatures=temps)
+        # data parallel: results stay on the device, one all_gather + one all_reduce, then ONE read-back of the
+        # whole job's results (what a caller of the sharded job consumes)
+        from mmee.dist import gather_results_fixed
 
-            packed = torch.cat([r.logits, torch.from_numpy(r.exits_store).to(dev, torch.float32)[:, None],
-                                torch.from_numpy(r.criteria).to(dev)[:, None]], dim=1)
-            hist = torch.from_numpy(r.exit_hist).to(dev)
-            gather_results_fixed(packed, hist, packed_all)
+        r = model.infer_device(**dev_docs, exit_threshold=thr, temperatures=temps)
+        packed = torch.cat([r["logits"], r["exit_index"].to(torch.float32)[:, None], r["criterion"][:, None]], dim=1)
+        job_hist = r["hist"].clone()
+        gather_results_fixed(packed, job_hist, packed_all)
+        host = packed_all.cpu()                      # synchronises: the step ends when the job's results are on the host
+        r["exit_hist"] = r["hist"].cpu().numpy()
+        r["job_results"] = host
         return r
 
     def step_host():
@@ -237,7 +277,7 @@ def main():
         return float(t.item()) / steps, last
 
     model.set_profiling(True)
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, enabled=(rank == 0)) as clk:      # rank 0 reports the clocks of its own GPU
         ms_step, res = timed(step_device, args.steps, args.warmup)
     stage = model.last_stage_ms()          # per-stage CUDA-event times of the last timed step
     launches = model.last_launch_count()
@@ -253,7 +293,7 @@ def main():
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e}
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM): algorithmic FLOPs of the docs that reached each layer
-    hist = res.exit_hist.astype(np.int64)
+    hist = (res["exit_hist"] if isinstance(res, dict) else res.exit_hist).astype(np.int64)
     fl = layer_flops(dims)
     reached = []          # documents entering encoder layer l (1-based)
     active = B

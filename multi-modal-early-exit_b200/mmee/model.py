@@ -277,6 +277,19 @@ class B200EEForSequenceClassification:
             res.all_criteria = r["all_crit"]
         return res
 
+    def infer_device(self, input_ids=None, attention_mask=None, bbox=None, pixel_values=None, labels=None,
+                     exit_threshold: Union[float, Sequence[float], None] = None,
+                     temperatures: Optional[Sequence[float]] = None, criterion: Optional[str] = None,
+                     early_exit: bool = True, **unused) -> Dict[str, torch.Tensor]:
+        """`infer` without the device->host read-back: results stay on the GPU (logits f32 [B,K], exit_index i32 [B],
+        criterion f32 [B], hist i64 [E+1]) and the call is asynchronous on the current stream — what the
+        data-parallel gather (`mmee.dist`) and pipelined callers want.  Inputs must be CUDA tensors."""
+        thr = self.ee.global_threshold if exit_threshold is None else exit_threshold
+        crit_name = criterion or self.ee.inference_strategy
+        r = self._run(input_ids, attention_mask, bbox, pixel_values, crit_name, 1 if early_exit else 0,
+                      np.atleast_1d(np.asarray(thr, dtype=np.float32)), temperatures, False)
+        return {"logits": r["logits"], "exit_index": r["exit_index"], "criterion": r["criterion"], "hist": r["hist"]}
+
     # ------------------------------------------------------------------ introspection
     def last_launch_count(self) -> int:
         return int(self._lib.mmee_last_launch_count(self._h))
