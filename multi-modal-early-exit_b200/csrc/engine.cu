@@ -60,10 +60,6 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i < n) dst[i] = __float2bfloat16_rn(src[i] * scale);
 }
-__global__ void scale_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, float scale) {
-  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (i < n) dst[i] = src[i] * scale;
-}
 __global__ void init_forward_kernel(int* slot_doc, int* out_exit, int* n_dev, int* m_dev, unsigned long long* hist,
                                     int B, int seq, int n_hist) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -848,6 +844,17 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   mark(e, "end", st);
 }
 
+// The attention kernel raises a flag when a score jumped more than 2^100 above everything before it in its row
+// (lazy-rescaling range exceeded): results would be inf/NaN, so synchronous calls turn it into an error.
+void check_attention_flag(mmee_engine* e) {
+  int flag = 0;
+  CUDA_OK(cudaMemcpy(&flag, e->att_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) {
+    CUDA_OK(cudaMemset(e->att_err.p, 0, sizeof(int)));
+    throw std::runtime_error("attention scores exceeded the online-softmax range (a score > 2^100 above its row reference)");
+  }
+}
+
 void collect_profile(mmee_engine* e) {
   e->stage_ms.clear();
   if (!e->profiling || e->ev.size() < 2) return;
@@ -993,6 +1000,7 @@ int mmee_forward_device(mmee_engine* e, int B, const int64_t* input_ids, const i
   if (!cuda_stream) {
     CUDA_OK(cudaStreamSynchronize(st));
     collect_profile(e);
+    check_attention_flag(e);
   }
   return 0;
   MMEE_CATCH
@@ -1045,6 +1053,7 @@ int mmee_forward(mmee_engine* e, int B, const int64_t* input_ids, const int64_t*
   if (out->all_criteria) CUDA_OK(cudaMemcpyAsync(out->all_criteria, dv.all_criteria, static_cast<size_t>(E1) * B * 4, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   collect_profile(e);
+  check_attention_flag(e);
   return 0;
   MMEE_CATCH
 }

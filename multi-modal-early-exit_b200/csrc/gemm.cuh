@@ -459,23 +459,6 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int tile = pair; tile < total_tiles; tile += n_pairs) {
       const int m0 = (tile / n_blocks) * 2 * GEMM_BLOCK_M + static_cast<int>(rank) * GEMM_BLOCK_M;
       const int n0 = (tile % n_blocks) * BLOCK_N;
-      if constexpr (EPI == EPI_RESID_F32) {
-        // pull the NEXT tile's residual slab (32 rows x 128 columns of this warp, hi and lo parts) into L2 while this
-        // tile's MMAs are still running: the residual was written a layer ago and has long left the cache
-        const int nt = tile + n_pairs;
-        if (nt < total_tiles) {
-          const int pr = (nt / n_blocks) * 2 * GEMM_BLOCK_M + static_cast<int>(rank) * GEMM_BLOCK_M + quarter * 32 + lane;
-          if (pr < M) {
-            const size_t off = static_cast<size_t>(pr) * args.N + (nt % n_blocks) * BLOCK_N + half * (BLOCK_N / PARTS);
-#pragma unroll
-            for (int b = 0; b < 2 * BLOCK_N / PARTS; b += 128) {     // BLOCK_N/PARTS bf16 per row
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(args.resid + off) + b));
-              if (args.resid_lo)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(args.resid_lo + off) + b));
-            }
-          }
-        }
-      }
       mbar_wait(tmem_full + acc * 8, acc_phase);
       tc_fence_after();
       gemm_epilogue_warp<BLOCK_N, EPI, PARTS>(args, M, m0, n0, tmem_base + acc * BLOCK_N, stg, quarter, half, lane);
