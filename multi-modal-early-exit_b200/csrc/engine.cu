@@ -385,10 +385,10 @@ void finalize(mmee_engine* e) {
     const auto& tx = need(e, p + "encoder.rel_pos_x_bias.weight", {h, d.rel2d_bins});
     const auto& ty = need(e, p + "encoder.rel_pos_y_bias.weight", {h, d.rel2d_bins});
     if (h % 2) throw std::runtime_error("attention heads must be even");
-    std::vector<float> T1(static_cast<size_t>(d.rel_bins) * h);
+    const int t2p = h + 2;                       // table row pitch (elements): spreads random rows over the smem banks
+    std::vector<float> T1(static_cast<size_t>(d.rel_bins) * t2p, 0.f);
     for (int b1 = 0; b1 < d.rel_bins; ++b1)
-      for (int hh = 0; hh < h; ++hh) T1[static_cast<size_t>(b1) * h + hh] = t1[static_cast<size_t>(hh) * d.rel_bins + b1] * qscale;
-    const int t2p = h + 2;                       // row pitch in halves: (h + 2) / 2 words is odd for h = 12, 16, 2 (bank spread)
+      for (int hh = 0; hh < h; ++hh) T1[static_cast<size_t>(b1) * t2p + hh] = t1[static_cast<size_t>(hh) * d.rel_bins + b1] * qscale;
     std::vector<__half> T2(static_cast<size_t>(d.rel2d_bins) * d.rel2d_bins * t2p, __float2half_rn(0.f));
     for (int bx = 0; bx < d.rel2d_bins; ++bx)
       for (int by = 0; by < d.rel2d_bins; ++by)

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) ln_rows_vec_kernel(const float* __restric
 struct BiasArgs {
   const int64_t* bbox;       // [B, n_text, 4]
   const int* vis_bbox;       // [n_vis, 4]
-  const float* t1;           // [bins1][heads]            W1d * log2(e)/sqrt(d)
+  const float* t1;           // [bins1][t2_pitch]         W1d * log2(e)/sqrt(d)   (same padded row pitch as t2)
   const __half* t2;          // [bins2*bins2][t2_pitch]   (Wx + Wy) * log2(e)/sqrt(d); row pitch heads + 2 halves = an odd
                              //                           number of 32-bit words, so random rows spread over all smem banks
   const uint8_t* lut1;       // |rel| -> bucket offset, 1-D   (size lut1_n)
@@ -138,8 +138,8 @@ constexpr int BIAS_THREADS = 768;
 constexpr float BIAS_MASKED = -60000.0f;   // finite (0 * x stays 0 in the identity MMA) and exp2() of it is 0
 
 inline size_t bias_build_smem(const BiasArgs& a) {
-  return static_cast<size_t>(a.bins2) * a.bins2 * a.t2_pitch * 2 + static_cast<size_t>(a.bins1) * a.heads * 4 + a.lut1_n +
-         a.lut2_n + static_cast<size_t>(a.pitch) * 16 + 64;
+  return static_cast<size_t>(a.bins2) * a.bins2 * a.t2_pitch * 2 + static_cast<size_t>(a.bins1) * a.t2_pitch * 4 + a.lut1_n +
+         a.lut2_n + static_cast<size_t>(a.pitch + (a.pitch >> 3) + 8) * 16 + 64;
 }
 
 // thread = 8 consecutive keys j of one query row i; a pass covers blockDim / (pitch/8) rows of one document.
@@ -148,15 +148,18 @@ __global__ void __launch_bounds__(BIAS_THREADS, 1) bias_build_kernel(BiasArgs a)
   const int n_t2 = a.bins2 * a.bins2 * a.t2_pitch;
   __half* s_t2 = reinterpret_cast<__half*>(bsm);
   float* s_t1 = reinterpret_cast<float*>(bsm + static_cast<size_t>(n_t2) * 2);
-  int* s_pos = reinterpret_cast<int*>(s_t1 + a.bins1 * a.heads);      // [pitch] each
-  int* s_x = s_pos + a.pitch;
-  int* s_y = s_x + a.pitch;
-  int* s_m = s_y + a.pitch;                                           // 1 = masked key
-  uint8_t* s_l1 = reinterpret_cast<uint8_t*>(s_m + a.pitch);
+  // key coordinates, stored at index j + (j >> 3): lane l reads keys 8l .. 8l+7, and the odd stride 9 spreads the
+  // warp's 32 reads of "key k of my chunk" over all banks (plain [pitch] arrays gave 8-way conflicts, ncu)
+  const int cpitch = a.pitch + (a.pitch >> 3) + 8;
+  int* s_pos = reinterpret_cast<int*>(s_t1 + a.bins1 * a.t2_pitch);   // [cpitch] each
+  int* s_x = s_pos + cpitch;
+  int* s_y = s_x + cpitch;
+  int* s_m = s_y + cpitch;                                            // 1 = masked key
+  uint8_t* s_l1 = reinterpret_cast<uint8_t*>(s_m + cpitch);
   uint8_t* s_l2 = s_l1 + a.lut1_n;
   for (int i = threadIdx.x; i < n_t2 / 8; i += blockDim.x)
     reinterpret_cast<uint4*>(s_t2)[i] = __ldg(reinterpret_cast<const uint4*>(a.t2) + i);
-  for (int i = threadIdx.x; i < a.bins1 * a.heads; i += blockDim.x) s_t1[i] = a.t1[i];
+  for (int i = threadIdx.x; i < a.bins1 * a.t2_pitch; i += blockDim.x) s_t1[i] = a.t1[i];
   for (int i = threadIdx.x; i < a.lut1_n; i += blockDim.x) s_l1[i] = a.lut1[i];
   for (int i = threadIdx.x; i < a.lut2_n; i += blockDim.x) s_l2[i] = a.lut2[i];
 
@@ -188,23 +191,26 @@ __global__ void __launch_bounds__(BIAS_THREADS, 1) bias_build_kernel(BiasArgs a)
           }
           m = a.maskadd[static_cast<size_t>(doc) * a.kv_pitch + t] < 0.f ? 1 : 0;
         }
-        s_pos[t] = pos; s_x[t] = x0; s_y[t] = y1; s_m[t] = m;
+        const int tp = t + (t >> 3);
+        s_pos[tp] = pos; s_x[tp] = x0; s_y[tp] = y1; s_m[tp] = m;
       }
       cur_doc = doc;
       __syncthreads();
     }
     if (!active || i >= a.seq) continue;
-    const int pi = s_pos[i], xi = s_x[i], yi = s_y[i];
+    const int ip = i + (i >> 3);
+    const int pi = s_pos[ip], xi = s_x[ip], yi = s_y[ip];
+    const int jp0 = j0 + (j0 >> 3);                    // j0 is a multiple of 8: keys j0 .. j0+7 are contiguous from here
     uint32_t i1[8], i2[8];
     uint32_t mbits = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int j = j0 + k;
+      const int j = jp0 + k;
       const int r1 = s_pos[j] - pi, rx = s_x[j] - xi, ry = s_y[j] - yi;
       const int b1 = (r1 > 0 ? half1 : 0) + s_l1[min(abs(r1), a.lut1_n - 1)];
       const int bx = (rx > 0 ? half2 : 0) + s_l2[min(abs(rx), a.lut2_n - 1)];
       const int by = (ry > 0 ? half2 : 0) + s_l2[min(abs(ry), a.lut2_n - 1)];
-      i1[k] = static_cast<uint32_t>(b1 * a.heads);
+      i1[k] = static_cast<uint32_t>(b1 * a.t2_pitch);
       i2[k] = static_cast<uint32_t>((bx * a.bins2 + by) * a.t2_pitch);
       mbits |= static_cast<uint32_t>(s_m[j]) << k;
     }
