@@ -287,3 +287,25 @@ def test_larger_batch_parity_vs_port():
     decisive = (srt[..., -1] - srt[..., -2]) > 2 * LOGIT_TOL
     assert (got.argmax(-1) == want.argmax(-1))[decisive].all()
     model.close()
+
+
+@pytest.mark.parametrize("n_text,layers", [(77, 2), (200, 1), (448, 1)])
+def test_odd_sequence_lengths_vs_port(n_text, layers):
+    """Sequence lengths that are not 709: partial key / query tiles, other pitches.  Engine vs the oracle port."""
+    from mmee.model import B200EEForSequenceClassification
+    from oracle import port
+
+    dims = ModelDims.tiny(n_text=n_text, layers=layers)
+    ee = ExitConfig.from_dict(dict(exits=["text_visual_concat"] + list(range(1, layers + 1)), encoder_layer_strategy="ramp",
+                                   inference_strategy="max_confidence"))
+    sd = synth.make_state_dict(dims, ee, seed=5)
+    docs = synth.make_docs(dims, 5, seed=41, pad=True)
+    model = B200EEForSequenceClassification(dims, ee, sd, device=0, max_batch=8)
+    got = model.forward(**_cuda(docs)).exit_logits.cpu().numpy()
+    want = port.forward(sd, dims, ee, docs)["exit_logits"].numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() <= LOGIT_TOL
+    dense = model.infer(**_cuda(docs), exit_threshold=0.2, early_exit=False)
+    early = model.infer(**_cuda(docs), exit_threshold=0.2)
+    assert np.array_equal(dense.exits_store, early.exits_store) and torch.equal(dense.logits, early.logits)
+    model.close()
