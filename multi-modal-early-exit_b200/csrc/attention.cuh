@@ -2,7 +2,8 @@
 //     ctx = softmax( (Q/8) K^T + (rel_pos + rel_2d_pos)/8 + key_mask ) V
 // Persistent kernel, TWO co-resident CTAs per SM (grid = 2 x #SMs), work item = (document slot, head,
 // 128-query tile), 64-key tiles.  Everything between Q/K/V and ctx stays on the SM:
-//   S_t  = Q K_t^T + B_t I    tcgen05.mma 128x64x64 twice into the same fp32 TMEM accumulator: bf16 Q.K^T, then the
+//   S_t  = Q K_t^T + B_t I    tcgen05.mma 128x64x64 twice into the same fp32 TMEM accumulator: bf16 Q.K^T (Q resident in
+//                             TMEM for the whole item, copied there once by the softmax warps), then the
 //                             fp16 bias tile B_t (relative-position bias in the log2 domain with -60000 on padded
 //                             keys, built once per forward by bias_build_kernel, streamed by TMA) times a 64x64
 //                             identity -- the bias add and the key mask cost no thread instruction
@@ -56,8 +57,8 @@ struct AttSmem {
   static constexpr int V_OFF = KB_OFF + ATT_KB_STAGES * KB_STAGE;
   static constexpr int I_OFF = V_OFF + ATT_V_STAGES * V_BYTES;
   static constexpr int BAR_OFF = I_OFF + I_BYTES;
-  // q_full[2] q_empty[2] kb_full[KB] kb_empty[KB] v_full[V] v_empty[V] s_full[2] p_full[2] o_full[1]
-  static constexpr int N_BARS = 2 + 2 + 2 * ATT_KB_STAGES + 2 * ATT_V_STAGES + 2 + 2 + 1;
+  // q_full[2] q_empty[2] kb_full[KB] kb_empty[KB] v_full[V] v_empty[V] s_full[2] p_full[2] o_full[1] qt_full[1]
+  static constexpr int N_BARS = 2 + 2 + 2 * ATT_KB_STAGES + 2 * ATT_V_STAGES + 2 + 2 + 1 + 1;
   static constexpr int TOTAL = BAR_OFF + N_BARS * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL;                      // the dynamic smem base itself is 1024 B aligned
 };
@@ -165,6 +166,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t s_full = v_empty + ATT_V_STAGES * 8;            // [2]
   const uint32_t p_full = s_full + 2 * 8;                        // [2]
   const uint32_t o_full = p_full + 2 * 8;                        // [1]  every P V commit
+  const uint32_t qt_full = o_full + 8;                           // [1]  once per item: Q has been copied into TMEM
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttSmem::BAR_OFF);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + AttSmem::N_BARS);
 
@@ -183,12 +185,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     tma_prefetch_desc(&tmap_bias);
     uint64_t* b = bars;
     for (int i = 0; i < 2; ++i) mbar_init(b++, 1);                  // q_full
-    for (int i = 0; i < 2; ++i) mbar_init(b++, 1);                  // q_empty
+    for (int i = 0; i < 2; ++i) mbar_init(b++, ATT_SM_WARPS);       // q_empty: the softmax warps copied Q to TMEM
     for (int i = 0; i < 2 * ATT_KB_STAGES; ++i) mbar_init(b++, 1);  // kb_full, kb_empty (S commit)
     for (int i = 0; i < 2 * ATT_V_STAGES; ++i) mbar_init(b++, 1);   // v_full, v_empty (P V commit)
     for (int i = 0; i < 2; ++i) mbar_init(b++, 1);                  // s_full
     for (int i = 0; i < 2; ++i) mbar_init(b++, ATT_SM_WARPS);       // p_full
     mbar_init(b++, 1);                                              // o_full
+    mbar_init(b++, ATT_SM_WARPS);                                   // qt_full
     fence_mbar_init();
   }
   // constant rows 64..79 of every V^T tile: row 64 = 1.0 (PV then also yields the row sum of P), rest 0
@@ -213,6 +216,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;            // 2 x 64 columns; P_t (bf16 pairs) overwrites columns [0,32) of S_t
   const uint32_t tmem_O = tmem_base + 128;      // 80 columns: 64 dims + row sum + padding
+  const uint32_t tmem_Q = tmem_base + 208;      // 32 columns: the item's Q tile (64 bf16 per row) as the TMEM A operand
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -299,25 +303,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       uint32_t ts = 0;
       auto issue_s = [&]() {
         const int st = ts % ATT_KB_STAGES;
-        const int qb = cs.ii & 1;
         ATT_TRACE(1, ts, 0)
-        if (cs.j == cs.first_j) mbar_wait(q_full + qb * 8, (cs.ii >> 1) & 1);
+        if (cs.j == cs.first_j) mbar_wait(qt_full, cs.ii & 1);      // the item's Q is in TMEM (softmax warps, below)
         mbar_wait(kb_full + st * 8, (ts / ATT_KB_STAGES) & 1);
         ATT_TRACE(1, ts, 1)
         tc_fence_after();
         const uint32_t stage = sb + AttSmem::KB_OFF + st * AttSmem::KB_STAGE;
-        const uint64_t dq = umma_desc_sw128_kmajor(sb + AttSmem::Q_OFF + qb * AttSmem::Q_BYTES);
         const uint64_t dk = umma_desc_sw128_kmajor(stage);
         const uint64_t db = umma_desc_sw128_kmajor(stage + AttSmem::K_BYTES);
         const uint32_t d_s = tmem_S + (ts & 1) * ATT_BKV;
         // S buffer ts&1 last held P_{ts-2}; its P V was issued before this point and tcgen05.mma executes in order
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(d_s, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+        for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ts(d_s, tmem_Q + k * 8, dk + 2 * k, idesc_s, k ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < ATT_BKV / 16; ++k) umma_bf16_ss(d_s, db + 2 * k, di + 2 * k, idesc_b, 1u);   // += bias16 x I
         umma_commit(s_full + (ts & 1) * 8);
         umma_commit(kb_empty + st * 8);
-        if (cs.j == cs.last_j) umma_commit(q_empty + qb * 8);   // last use of this item's Q
         ++ts;
         cs = att_next(cs, total_items, n_qt, stride, args);
       };
@@ -382,6 +383,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
     };
 
+    // Q of item `ii` : smem (TMA, SW128) -> this thread's row -> TMEM A operand.  Read once per item instead of by
+    // every Q.K^T MMA (16 KB of shared-memory reads per key tile less).  Called when no S MMA of the previous item is
+    // pending any more (its last s_full has been waited on).
+    auto q_to_tmem = [&](int ii) {
+      const int qb = ii & 1;
+      mbar_wait(q_full + qb * 8, (ii >> 1) & 1);
+      const uint32_t qrow = sb + AttSmem::Q_OFF + qb * AttSmem::Q_BYTES + r * 128;
+      uint32_t q[32];
+#pragma unroll
+      for (int cch = 0; cch < 8; ++cch) {
+        const uint4 x = lds128(qrow + ((cch ^ (r & 7)) << 4));
+        q[4 * cch] = x.x; q[4 * cch + 1] = x.y; q[4 * cch + 2] = x.z; q[4 * cch + 3] = x.w;
+      }
+      tmem_st32(tmem_Q + lane_addr, q);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(qt_full); mbar_arrive(q_empty + qb * 8); }
+    };
+    if (c.valid) q_to_tmem(0);
+
     while (c.valid) {
       const int b = t & 1;
       const bool first = (c.j == c.first_j);                 // first processed tile of a new item
@@ -396,6 +418,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_wait(s_full + b * 8, (t >> 1) & 1);      // S_t = Q K^T + bias (+ key mask) is complete
       tc_fence_after();
       if (tr) { ATT_TRACE(0, t, 1) }
+      // last tile of this item: every S MMA that reads the item's Q has completed -> stage the next item's Q
+      if (c.j == c.last_j && c.item + stride < total_items) q_to_tmem(c.ii + 1);
 
       uint32_t v0[32], v1[32], pk[32];
       tmem_ld32(tS, v0);
