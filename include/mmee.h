@@ -93,6 +93,16 @@ int  mmee_forward_device(mmee_engine* e, int B, const int64_t* input_ids, const 
                          const int64_t* attention_mask, const float* pixel_values, const mmee_policy* policy,
                          const mmee_outputs* out, void* cuda_stream);
 
+/* Pipelined form of mmee_forward for throughput callers (a dataset loop such as EE/utils.py:169-193): up to TWO
+ * forwards in flight, so the upload of batch n+1 (160 MB of pixels at 256 documents) overlaps the computation of
+ * batch n.  submit enqueues the host->device copies, the forward and the result staging and returns a ticket (0 or 1)
+ * without waiting; the host input buffers must stay valid (and should be pinned) until the ticket is collected.
+ * collect blocks until that forward has finished and copies logits / exit_index / criterion / exit_hist to the host
+ * buffers of `out` (the all_* outputs are not available on this path). */
+int  mmee_forward_submit(mmee_engine* e, int B, const int64_t* input_ids, const int64_t* bbox,
+                         const int64_t* attention_mask, const float* pixel_values, const mmee_policy* policy);
+int  mmee_forward_collect(mmee_engine* e, int ticket, const mmee_outputs* out);
+
 /* Number of kernels launched by the engine in the last forward (for the bench's gpu_launches). */
 int64_t mmee_last_launch_count(mmee_engine* e);
 /* Device time of the named stage of the last forward in ms ("total", "embed", "gemm", "attention", "norm", "exit");

@@ -175,14 +175,25 @@ struct mmee_engine {
   // staged inputs (host path)
   DevBuf<int64_t> in_ids, in_bbox, in_mask;
   DevBuf<float> in_px;
-  void* pin_in = nullptr;
-  size_t pin_in_bytes = 0;
-  void* pin_out = nullptr;
-  size_t pin_out_bytes = 0;
+  // pipelined host path (mmee_forward_submit / mmee_forward_collect): two forwards in flight
+  struct Slot {
+    DevBuf<int64_t> ids, bbox, mask;
+    DevBuf<float> px, logits, crit;
+    DevBuf<int32_t> exit_index;
+    DevBuf<int64_t> hist;
+    cudaEvent_t small_ready = nullptr, px_ready = nullptr, done = nullptr;
+    int B = 0;
+    bool busy = false;
+  } slots[2];
+  int next_slot = 0;
+  cudaEvent_t px_wait = nullptr;            // event forward_device waits on before touching pixels (px_async)
 
   ~mmee_engine() {
-    if (pin_in) cudaFreeHost(pin_in);
-    if (pin_out) cudaFreeHost(pin_out);
+    for (auto& sl : slots) {
+      if (sl.small_ready) cudaEventDestroy(sl.small_ready);
+      if (sl.px_ready) cudaEventDestroy(sl.px_ready);
+      if (sl.done) cudaEventDestroy(sl.done);
+    }
     for (auto& e : ev) cudaEventDestroy(e.second);
     if (stream) cudaStreamDestroy(stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -637,7 +648,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   }
   {
     const size_t total = static_cast<size_t>(B) * e->n_patch * e->kdim_patch / 4;
-    if (e->px_async) CUDA_OK(cudaStreamWaitEvent(st, e->px_ready, 0));
+    if (e->px_async) CUDA_OK(cudaStreamWaitEvent(st, e->px_wait ? e->px_wait : e->px_ready, 0));
     im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(px, e->PATCH.p, B, d.image, d.patch,
                                                                               d.channels);
     e->launches++;
@@ -1053,6 +1064,78 @@ int mmee_forward(mmee_engine* e, int B, const int64_t* input_ids, const int64_t*
   if (out->all_criteria) CUDA_OK(cudaMemcpyAsync(out->all_criteria, dv.all_criteria, static_cast<size_t>(E1) * B * 4, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   collect_profile(e);
+  check_attention_flag(e);
+  return 0;
+  MMEE_CATCH
+}
+
+int mmee_forward_submit(mmee_engine* e, int B, const int64_t* input_ids, const int64_t* bbox,
+                        const int64_t* attention_mask, const float* pixel_values, const mmee_policy* policy) {
+  MMEE_TRY
+  if (!e) throw std::runtime_error("null engine");
+  if (B < 1 || B > e->max_batch) throw std::runtime_error("batch out of range");
+  CUDA_OK(cudaSetDevice(e->device));
+  const int ticket = e->next_slot;
+  mmee_engine::Slot& sl = e->slots[ticket];
+  if (sl.busy) throw std::runtime_error("both pipeline slots are in flight: collect a ticket first");
+  const int T = e->T, K = e->K, E1 = e->d.n_exits + 1;
+  const size_t n_ids = static_cast<size_t>(B) * T, n_px = static_cast<size_t>(B) * e->d.channels * e->d.image * e->d.image;
+  if (!sl.done) {
+    const size_t mb = e->max_batch;
+    sl.ids.alloc(mb * T); sl.bbox.alloc(mb * T * 4); sl.mask.alloc(mb * T);
+    sl.px.alloc(mb * e->d.channels * e->d.image * e->d.image);
+    sl.logits.alloc(mb * K); sl.crit.alloc(mb); sl.exit_index.alloc(mb); sl.hist.alloc(E1);
+    CUDA_OK(cudaEventCreateWithFlags(&sl.small_ready, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&sl.px_ready, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  }
+  // all uploads on the copy stream: they overlap the forward that is still running on the compute stream
+  cudaStream_t cs = e->copy_stream, st = e->stream;
+  CUDA_OK(cudaMemcpyAsync(sl.ids.p, input_ids, n_ids * 8, cudaMemcpyHostToDevice, cs));
+  CUDA_OK(cudaMemcpyAsync(sl.bbox.p, bbox, n_ids * 32, cudaMemcpyHostToDevice, cs));
+  CUDA_OK(cudaMemcpyAsync(sl.mask.p, attention_mask, n_ids * 8, cudaMemcpyHostToDevice, cs));
+  CUDA_OK(cudaEventRecord(sl.small_ready, cs));
+  CUDA_OK(cudaMemcpyAsync(sl.px.p, pixel_values, n_px * 4, cudaMemcpyHostToDevice, cs));
+  CUDA_OK(cudaEventRecord(sl.px_ready, cs));
+  CUDA_OK(cudaStreamWaitEvent(st, sl.small_ready, 0));
+  mmee_outputs dv{};
+  dv.logits = e->out_logits.p; dv.exit_index = e->out_exit.p; dv.criterion = e->out_crit.p;
+  dv.exit_hist = reinterpret_cast<int64_t*>(e->hist64.p);
+  e->px_async = true;
+  e->px_wait = sl.px_ready;
+  try {
+    forward_device(e, B, sl.ids.p, sl.bbox.p, sl.mask.p, sl.px.p, policy, &dv, st);
+  } catch (...) {
+    e->px_async = false; e->px_wait = nullptr;
+    throw;
+  }
+  e->px_async = false; e->px_wait = nullptr;
+  // stage the results: the next forward overwrites the engine's own output buffers
+  CUDA_OK(cudaMemcpyAsync(sl.logits.p, e->out_logits.p, static_cast<size_t>(B) * K * 4, cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(sl.exit_index.p, e->out_exit.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(sl.crit.p, e->out_crit.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(sl.hist.p, e->hist64.p, static_cast<size_t>(E1) * 8, cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaEventRecord(sl.done, st));
+  sl.B = B;
+  sl.busy = true;
+  e->next_slot ^= 1;
+  return ticket;
+  MMEE_CATCH
+}
+
+int mmee_forward_collect(mmee_engine* e, int ticket, const mmee_outputs* out) {
+  MMEE_TRY
+  if (!e || !out || !out->logits || !out->exit_index) throw std::runtime_error("null argument");
+  if (ticket < 0 || ticket > 1 || !e->slots[ticket].busy) throw std::runtime_error("no forward in flight for this ticket");
+  CUDA_OK(cudaSetDevice(e->device));
+  mmee_engine::Slot& sl = e->slots[ticket];
+  const int B = sl.B, K = e->K, E1 = e->d.n_exits + 1;
+  CUDA_OK(cudaEventSynchronize(sl.done));
+  sl.busy = false;
+  CUDA_OK(cudaMemcpy(out->logits, sl.logits.p, static_cast<size_t>(B) * K * 4, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(out->exit_index, sl.exit_index.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost));
+  if (out->criterion) CUDA_OK(cudaMemcpy(out->criterion, sl.crit.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost));
+  if (out->exit_hist) CUDA_OK(cudaMemcpy(out->exit_hist, sl.hist.p, static_cast<size_t>(E1) * 8, cudaMemcpyDeviceToHost));
   check_attention_flag(e);
   return 0;
   MMEE_CATCH

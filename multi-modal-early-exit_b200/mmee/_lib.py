@@ -16,7 +16,7 @@ EXPORTED_SYMBOLS = [
     "mmee_create", "mmee_destroy", "mmee_set_weight", "mmee_set_bucket_lut", "mmee_get_bucket_lut",
     "mmee_finalize_weights", "mmee_forward", "mmee_forward_device", "mmee_last_launch_count",
     "mmee_set_profiling", "mmee_collect_profile", "mmee_last_stage_ms", "mmee_debug_read", "mmee_last_error",
-    "mmee_version", "mmee_policy_scan",
+    "mmee_version", "mmee_policy_scan", "mmee_forward_submit", "mmee_forward_collect",
 ]
 
 
@@ -78,6 +78,10 @@ def load() -> C.CDLL:
     lib.mmee_forward.restype = C.c_int
     lib.mmee_forward_device.argtypes = fwd_args + [C.c_void_p]
     lib.mmee_forward_device.restype = C.c_int
+    lib.mmee_forward_submit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Policy)]
+    lib.mmee_forward_submit.restype = C.c_int
+    lib.mmee_forward_collect.argtypes = [C.c_void_p, C.c_int, C.POINTER(Outputs)]
+    lib.mmee_forward_collect.restype = C.c_int
     lib.mmee_last_launch_count.argtypes = [C.c_void_p]
     lib.mmee_last_launch_count.restype = C.c_int64
     lib.mmee_set_profiling.argtypes = [C.c_void_p, C.c_int]

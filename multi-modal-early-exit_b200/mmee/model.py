@@ -290,6 +290,65 @@ class B200EEForSequenceClassification:
                       np.atleast_1d(np.asarray(thr, dtype=np.float32)), temperatures, False)
         return {"logits": r["logits"], "exit_index": r["exit_index"], "criterion": r["criterion"], "hist": r["hist"]}
 
+    # ------------------------------------------------------------------ pipelined host path
+    def infer_submit(self, input_ids=None, attention_mask=None, bbox=None, pixel_values=None, labels=None,
+                     exit_threshold: Union[float, Sequence[float], None] = None,
+                     temperatures: Optional[Sequence[float]] = None, criterion: Optional[str] = None,
+                     early_exit: bool = True, **unused):
+        """Enqueue one early-exit forward over HOST tensors (pinned memory recommended) and return a ticket without
+        waiting; at most two tickets may be outstanding.  The upload of this batch overlaps the forward of the
+        previous one (`mmee_forward_submit`).  Pass the ticket to `infer_collect`."""
+        if pixel_values is None or pixel_values.is_cuda:
+            raise ValueError("infer_submit takes host tensors (use infer / infer_device for CUDA tensors)")
+        if input_ids is None:
+            input_ids = torch.zeros((pixel_values.shape[0], 0), dtype=torch.int64)
+        B, T = input_ids.shape
+        if T != self.dims.n_text:
+            raise ValueError(f"expected {self.dims.n_text} text tokens (padding='max_length'), got {T}")
+        if attention_mask is None:
+            attention_mask = torch.ones_like(input_ids)
+        if bbox is None:
+            bbox = torch.zeros((B, T, 4), dtype=torch.long)
+        ids = input_ids.to(torch.int64).contiguous()
+        msk = attention_mask.to(torch.int64).contiguous()
+        bb = bbox.to(torch.int64).contiguous()
+        px = pixel_values.to(torch.float32).contiguous()
+        thr = self.ee.global_threshold if exit_threshold is None else exit_threshold
+        thr = np.broadcast_to(np.asarray(thr, dtype=np.float32), (max(self.n_exits, 1),)).copy()
+        pol = _lib.Policy()
+        pol.criterion = 0 if (criterion or self.ee.inference_strategy) == "max_confidence" else 1
+        pol.mode = 1 if early_exit else 0
+        pol.thresholds = thr.ctypes.data_as(C.POINTER(C.c_float))
+        tmp = None
+        if temperatures is not None:
+            tmp = np.asarray(temperatures, dtype=np.float32).reshape(-1).copy()
+            if tmp.shape[0] != self.n_exits + 1:
+                raise ValueError(f"temperatures must have {self.n_exits + 1} entries (one per exit + final)")
+            pol.temperatures = tmp.ctypes.data_as(C.POINTER(C.c_float))
+        t = self._lib.mmee_forward_submit(self._h, B, C.c_void_p(ids.data_ptr()), C.c_void_p(bb.data_ptr()),
+                                          C.c_void_p(msk.data_ptr()), C.c_void_p(px.data_ptr()), C.byref(pol))
+        if t < 0:
+            _lib.check(t)
+        return {"ticket": t, "B": B, "_keep": (ids, msk, bb, px, thr, tmp)}
+
+    def infer_collect(self, ticket) -> EarlyExitResult:
+        """Wait for a submitted forward and read its results back (same result object as `infer`)."""
+        B, K, E1 = ticket["B"], self.dims.n_labels, self.n_exits + 1
+        logits = torch.empty((B, K), dtype=torch.float32)
+        exit_index = torch.empty((B,), dtype=torch.int32)
+        crit = torch.empty((B,), dtype=torch.float32)
+        hist = torch.zeros((E1,), dtype=torch.int64)
+        out = _lib.Outputs()
+        out.logits, out.exit_index, out.criterion = logits.data_ptr(), exit_index.data_ptr(), crit.data_ptr()
+        out.exit_hist = hist.data_ptr()
+        _lib.check(self._lib.mmee_forward_collect(self._h, ticket["ticket"], C.byref(out)))
+        ticket["_keep"] = None
+        ex = exit_index.numpy().astype(np.int32)
+        h = hist.numpy()
+        dist = {e: float(h[e]) / B for e in range(E1)}
+        return EarlyExitResult(exits_store=ex, predictions=logits.to(torch.float64), exit_distribution=dist,
+                               criteria=crit.numpy(), exit_hist=h, logits=logits)
+
     # ------------------------------------------------------------------ introspection
     def last_launch_count(self) -> int:
         return int(self._lib.mmee_last_launch_count(self._h))

@@ -309,3 +309,28 @@ def test_odd_sequence_lengths_vs_port(n_text, layers):
     early = model.infer(**_cuda(docs), exit_threshold=0.2)
     assert np.array_equal(dense.exits_store, early.exits_store) and torch.equal(dense.logits, early.logits)
     model.close()
+
+
+def test_pipelined_submit_collect_equals_blocking():
+    """mmee_forward_submit / mmee_forward_collect (two forwards in flight) return what the blocking call returns."""
+    model, g, dims, ee, sd, docs = _engine("tiny_ramp_conf")
+    temps = g["temps"]
+    a = {k: v.clone().pin_memory() for k, v in docs.items()}
+    b = {k: v.flip(0).clone().pin_memory() for k, v in docs.items()}
+    ra = model.infer(**a, exit_threshold=0.5, temperatures=temps)
+    rb = model.infer(**b, exit_threshold=0.5, temperatures=temps)
+    t1 = model.infer_submit(**a, exit_threshold=0.5, temperatures=temps)
+    t2 = model.infer_submit(**b, exit_threshold=0.5, temperatures=temps)
+    with pytest.raises(RuntimeError, match="in flight"):
+        model.infer_submit(**a, exit_threshold=0.5, temperatures=temps)
+    pa = model.infer_collect(t1)
+    t3 = model.infer_submit(**a, exit_threshold=0.9, temperatures=temps)
+    pb = model.infer_collect(t2)
+    pc = model.infer_collect(t3)
+    for p, r in ((pa, ra), (pb, rb)):
+        assert np.array_equal(p.exits_store, r.exits_store) and torch.equal(p.logits, r.logits.cpu())
+        assert np.array_equal(p.exit_hist, r.exit_hist) and np.array_equal(p.criteria, r.criteria)
+    rc = model.infer(**a, exit_threshold=0.9, temperatures=temps)
+    assert np.array_equal(pc.exits_store, rc.exits_store) and torch.equal(pc.logits, rc.logits.cpu())
+    with pytest.raises(RuntimeError, match="ticket"):
+        model.infer_collect(t1)
