@@ -334,3 +334,33 @@ def test_pipelined_submit_collect_equals_blocking():
     assert np.array_equal(pc.exits_store, rc.exits_store) and torch.equal(pc.logits, rc.logits.cpu())
     with pytest.raises(RuntimeError, match="ticket"):
         model.infer_collect(t1)
+
+
+@pytest.mark.parametrize("gain", [8.0, 25.0])
+def test_large_scores_exercise_lazy_rescale(gain):
+    """Trained-model-like score ranges: scale W_q / W_k and the relative-position tables so that attention scores
+    span tens of log2 units within a row and the row maximum moves from key tile to key tile.  This drives the lazy
+    O-rescale path of the attention kernel (reference raised by more than 2^8 after the first tile), which the
+    random-init fixtures never reach.  Engine vs the fp32 oracle port; probabilities are peaky here, so the bar is the
+    bf16 one on the logits plus finiteness."""
+    from mmee.model import B200EEForSequenceClassification
+    from oracle import port
+
+    dims = ModelDims.tiny(layers=2)
+    ee = ExitConfig.from_dict(dict(exits=["text_visual_concat", 1, 2], encoder_layer_strategy="ramp",
+                                   inference_strategy="max_confidence"))
+    sd = synth.make_state_dict(dims, ee, seed=9)
+    for k in list(sd):
+        if k.endswith("attention.self.query.weight") or k.endswith("attention.self.key.weight"):
+            sd[k] = sd[k] * gain
+        if "rel_pos" in k:
+            sd[k] = sd[k] * (gain * 10.0)
+    docs = synth.make_docs(dims, 4, seed=51, pad=True)
+    model = B200EEForSequenceClassification(dims, ee, sd, device=0, max_batch=4)
+    got = model.forward(**_cuda(docs)).exit_logits.cpu().numpy()
+    want = port.forward(sd, dims, ee, docs)["exit_logits"].numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - want).max()
+    print(f"gain {gain}: max|logits - port| = {err:.3e}")
+    assert err <= LOGIT_TOL
+    model.close()
