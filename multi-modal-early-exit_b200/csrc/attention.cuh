@@ -22,8 +22,8 @@
 // Everything runs in the log2 domain (log2(e)/sqrt(d) is folded into W_q and into the bias).  The first tile of an
 // item takes its exact row maximum as reference.  Later tiles keep it unless a score exceeds it by more than 2^8
 // (lazy rescaling: P <= 256 is harmless in bf16/fp32); then the reference is raised for the following tiles and O
-// is rescaled in place in TMEM by exp2(old - new) before the next P V.  A score that jumps 2^100 above everything
-// before it raises err_flag.
+// is rescaled in place in TMEM by exp2(old - new) before the next P V.  A score more than 2^40 above the reference
+// takes an exact path: the reference is raised at once, the row's P is recomputed and O rescaled before this P V.
 #pragma once
 #include <cuda.h>
 
@@ -44,6 +44,7 @@ constexpr int ATT_KB_STAGES = 2;  // K + bias ring: a stage is released as soon 
 constexpr int ATT_V_STAGES = 2;   // V^T ring: released when P V_t has completed
 constexpr int ATT_MAX_KV_TILES = 16;
 constexpr float ATT_LAZY = 8.0f;   // raise the row reference only when a score exceeds it by more than 2^8
+constexpr float ATT_JUMP = 40.0f;  // ... and immediately (P recomputed) when it exceeds it by more than 2^40
 
 struct AttSmem {
   static constexpr int Q_BYTES = ATT_BQ * ATT_D * 2;           // 16 KB
@@ -70,7 +71,7 @@ static_assert(AttSmem::KB_STAGE % 1024 == 0 && AttSmem::K_BYTES % 1024 == 0 && A
 struct AttArgs {
   const int* n_active_dev;
   const uint2* slot_meta;      // slot -> {live_tiles, doc}   (see slot_meta_kernel)
-  int* err_flag;               // set to 1 if a score ran > 2^100 above its row reference (never in practice)
+  int* err_flag;               // guard: set to 1 if a deferred rescale factor underflowed (unreachable, see ATT_JUMP)
   long long* trace;            // developer trace (kTrace instantiation only): clock64 stamps of CTA 0
   __nv_bfloat16* ctx;          // [M, H]
   int H, heads, seq;
@@ -453,6 +454,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         pmax = fmaxf(m0, m1);
       }
+      if (pmax > ATT_JUMP) {
+        // a score of this tile is more than 2^40 above the row reference (never at init, possible with sharp trained
+        // heads): raise the reference NOW, recompute this row's P against it and fold the factor into the rescale of
+        // O below, so no probability ever leaves the fp32 / bf16 range
+        const float dq = ceilf(pmax);
+        ref += dq;
+        alpha_pend *= fast_exp2(-dq);
+        pmax -= dq;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          pk[i] = pack_bf16x2(fast_exp2(__uint_as_float(v0[2 * i]) - ref), fast_exp2(__uint_as_float(v0[2 * i + 1]) - ref));
+          pk[16 + i] = pack_bf16x2(fast_exp2(__uint_as_float(v1[2 * i]) - ref), fast_exp2(__uint_as_float(v1[2 * i + 1]) - ref));
+        }
+      }
+      __syncwarp();
       tmem_st32(tS, pk);
       if (tr) { ATT_TRACE(0, t, 3) }
 
@@ -491,7 +507,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const float dq = ceilf(pmax);
         ref += dq;
         alpha_pend = fast_exp2(-dq);
-        if (pmax > 100.f) *args.err_flag = 1;
+        if (!(alpha_pend > 0.f)) *args.err_flag = 1;       // unreachable with the jump handling above; kept as a guard
       }
       ++t;
       c = att_next(c, total_items, n_qt, stride, args);

@@ -855,14 +855,14 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   mark(e, "end", st);
 }
 
-// The attention kernel raises a flag when a score jumped more than 2^100 above everything before it in its row
-// (lazy-rescaling range exceeded): results would be inf/NaN, so synchronous calls turn it into an error.
+// Guard flag of the attention kernel's online softmax (a deferred rescale factor underflowed; unreachable by
+// construction, see ATT_JUMP in attention.cuh): synchronous calls turn it into an error instead of returning NaNs.
 void check_attention_flag(mmee_engine* e) {
   int flag = 0;
   CUDA_OK(cudaMemcpy(&flag, e->att_err.p, sizeof(int), cudaMemcpyDeviceToHost));
   if (flag) {
     CUDA_OK(cudaMemset(e->att_err.p, 0, sizeof(int)));
-    throw std::runtime_error("attention scores exceeded the online-softmax range (a score > 2^100 above its row reference)");
+    throw std::runtime_error("attention online-softmax guard tripped (rescale factor underflow)");
   }
 }
 

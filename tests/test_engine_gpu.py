@@ -336,7 +336,7 @@ def test_pipelined_submit_collect_equals_blocking():
         model.infer_collect(t1)
 
 
-@pytest.mark.parametrize("gain", [8.0, 25.0])
+@pytest.mark.parametrize("gain", [8.0, 25.0, 60.0])
 def test_large_scores_exercise_lazy_rescale(gain):
     """Trained-model-like score ranges: scale W_q / W_k and the relative-position tables so that attention scores
     span tens of log2 units within a row and the row maximum moves from key tile to key tile.  This drives the lazy
