@@ -75,6 +75,7 @@ struct AttArgs {
   long long* trace;            // developer trace (kTrace instantiation only): clock64 stamps of CTA 0
   __nv_bfloat16* ctx;          // [M, H]
   int H, heads, seq;
+  int tail_j;                  // key tile that holds only <= 16 real keys and is run as a 16-key tile (-1: none)
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -298,6 +299,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, ATT_BKV);
       constexpr uint32_t idesc_b = umma_idesc_f16(ATT_BQ, ATT_BKV);
       constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, ATT_DV);
+      constexpr uint32_t idesc_s16 = umma_idesc_bf16(ATT_BQ, 16);   // the 16-key tail tile (args.tail_j)
+      constexpr uint32_t idesc_b16 = umma_idesc_f16(ATT_BQ, 16);
       const uint64_t di = umma_desc_sw128_kmajor(sb + AttSmem::I_OFF);
       AttCursor cs = att_first(total_items, n_qt, stride, args);   // next S = Q K^T + B I to issue (one tile ahead)
       AttCursor cp = cs;                                              // next P V to issue
@@ -314,10 +317,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const uint64_t db = umma_desc_sw128_kmajor(stage + AttSmem::K_BYTES);
         const uint32_t d_s = tmem_S + (ts & 1) * ATT_BKV;
         // S buffer ts&1 last held P_{ts-2}; its P V was issued before this point and tcgen05.mma executes in order
+        if (cs.j != args.tail_j) {
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ts(d_s, tmem_Q + k * 8, dk + 2 * k, idesc_s, k ? 1u : 0u);
+          for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ts(d_s, tmem_Q + k * 8, dk + 2 * k, idesc_s, k ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < ATT_BKV / 16; ++k) umma_bf16_ss(d_s, db + 2 * k, di + 2 * k, idesc_b, 1u);   // += bias16 x I
+          for (int k = 0; k < ATT_BKV / 16; ++k) umma_bf16_ss(d_s, db + 2 * k, di + 2 * k, idesc_b, 1u);   // += bias16 x I
+        } else {
+          // only keys 0..15 of the tile exist: N = 16 (K rows 0..15, bias columns 0..15, one identity block)
+#pragma unroll
+          for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ts(d_s, tmem_Q + k * 8, dk + 2 * k, idesc_s16, k ? 1u : 0u);
+          umma_bf16_ss(d_s, db, di, idesc_b16, 1u);
+        }
         umma_commit(s_full + (ts & 1) * 8);
         umma_commit(kb_empty + st * 8);
         ++ts;
@@ -336,9 +346,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         mbar_wait(v_full + sv * 8, (t / ATT_V_STAGES) & 1);
         tc_fence_after();
         const uint64_t dv = umma_desc_sw128_kmajor(sb + AttSmem::V_OFF + sv * AttSmem::V_BYTES);
+        const int pv_steps = (cp.j != args.tail_j) ? ATT_BKV / 16 : 1;      // tail tile: P is [128 x 16]
 #pragma unroll
         for (int k = 0; k < ATT_BKV / 16; ++k)
-          umma_bf16_ts(tmem_O, tmem_S + b * ATT_BKV + k * 8, dv + 2 * k, idesc_o, (k || !first) ? 1u : 0u);
+          if (k < pv_steps)
+            umma_bf16_ts(tmem_O, tmem_S + b * ATT_BKV + k * 8, dv + 2 * k, idesc_o, (k || !first) ? 1u : 0u);
         umma_commit(o_full);
         umma_commit(v_empty + sv * 8);
         cp = att_next(cp, total_items, n_qt, stride, args);
@@ -422,54 +434,87 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       // last tile of this item: every S MMA that reads the item's Q has completed -> stage the next item's Q
       if (c.j == c.last_j && c.item + stride < total_items) q_to_tmem(c.ii + 1);
 
-      uint32_t v0[32], v1[32], pk[32];
-      tmem_ld32(tS, v0);
-      tmem_ld32(tS + 32, v1);
-      tmem_ld_wait();
-      if (tr) { ATT_TRACE(0, t, 2) }
       float pmax;
-      if (first) {
-        // exact row maximum of the first tile as the reference, then p = exp2(s - ref)
-        float m0 = fmaxf(__uint_as_float(v0[0]), __uint_as_float(v0[1]));
-        float m1 = fmaxf(__uint_as_float(v1[0]), __uint_as_float(v1[1]));
+      if (c.j == args.tail_j) {
+        // 16-key tail tile: a quarter of the loads, exponentials and stores
+        uint32_t v[16], pq[8];
+        tmem_ld16(tS, v);
+        tmem_ld_wait();
+        if (tr) { ATT_TRACE(0, t, 2) }
+        if (first) {
+          float m = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
 #pragma unroll
-        for (int i = 2; i < 32; i += 2) {
-          m0 = fmaxf(m0, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v0[i + 1])));
-          m1 = fmaxf(m1, fmaxf(__uint_as_float(v1[i]), __uint_as_float(v1[i + 1])));
+          for (int i = 2; i < 16; i += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          ref = m;
         }
-        ref = fmaxf(m0, m1);
-        pmax = 0.f;
-      }
-      {
-        // p = exp2(s - ref); the running max rides along (FMNMX on the ALU pipe, MUFU on the XU pipe)
-        float m0 = -INFINITY, m1 = -INFINITY;
+        float m = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float a0 = __uint_as_float(v0[2 * i]) - ref, a1 = __uint_as_float(v0[2 * i + 1]) - ref;
-          const float c0 = __uint_as_float(v1[2 * i]) - ref, c1 = __uint_as_float(v1[2 * i + 1]) - ref;
-          m0 = fmaxf(m0, fmaxf(a0, a1));
-          m1 = fmaxf(m1, fmaxf(c0, c1));
-          pk[i] = pack_bf16x2(fast_exp2(a0), fast_exp2(a1));
-          pk[16 + i] = pack_bf16x2(fast_exp2(c0), fast_exp2(c1));
+        for (int i = 0; i < 8; ++i) {
+          const float a0 = __uint_as_float(v[2 * i]) - ref, a1 = __uint_as_float(v[2 * i + 1]) - ref;
+          m = fmaxf(m, fmaxf(a0, a1));
+          pq[i] = pack_bf16x2(fast_exp2(a0), fast_exp2(a1));
         }
-        pmax = fmaxf(m0, m1);
-      }
-      if (pmax > ATT_JUMP) {
-        // a score of this tile is more than 2^40 above the row reference (never at init, possible with sharp trained
-        // heads): raise the reference NOW, recompute this row's P against it and fold the factor into the rescale of
-        // O below, so no probability ever leaves the fp32 / bf16 range
-        const float dq = ceilf(pmax);
-        ref += dq;
-        alpha_pend *= fast_exp2(-dq);
-        pmax -= dq;
+        pmax = m;
+        if (pmax > ATT_JUMP) {                       // see the full-tile path below
+          const float dq = ceilf(pmax);
+          ref += dq;
+          alpha_pend *= fast_exp2(-dq);
+          pmax -= dq;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          pk[i] = pack_bf16x2(fast_exp2(__uint_as_float(v0[2 * i]) - ref), fast_exp2(__uint_as_float(v0[2 * i + 1]) - ref));
-          pk[16 + i] = pack_bf16x2(fast_exp2(__uint_as_float(v1[2 * i]) - ref), fast_exp2(__uint_as_float(v1[2 * i + 1]) - ref));
+          for (int i = 0; i < 8; ++i)
+            pq[i] = pack_bf16x2(fast_exp2(__uint_as_float(v[2 * i]) - ref), fast_exp2(__uint_as_float(v[2 * i + 1]) - ref));
         }
+        __syncwarp();
+        tmem_st8(tS, pq);
+      } else {
+        uint32_t v0[32], v1[32], pk[32];
+        tmem_ld32(tS, v0);
+        tmem_ld32(tS + 32, v1);
+        tmem_ld_wait();
+        if (tr) { ATT_TRACE(0, t, 2) }
+        if (first) {
+          // exact row maximum of the first tile as the reference, then p = exp2(s - ref)
+          float m0 = fmaxf(__uint_as_float(v0[0]), __uint_as_float(v0[1]));
+          float m1 = fmaxf(__uint_as_float(v1[0]), __uint_as_float(v1[1]));
+#pragma unroll
+          for (int i = 2; i < 32; i += 2) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v0[i + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(v1[i]), __uint_as_float(v1[i + 1])));
+          }
+          ref = fmaxf(m0, m1);
+          pmax = 0.f;
+        }
+        {
+          // p = exp2(s - ref); the running max rides along (FMNMX on the ALU pipe, MUFU on the XU pipe)
+          float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a0 = __uint_as_float(v0[2 * i]) - ref, a1 = __uint_as_float(v0[2 * i + 1]) - ref;
+            const float c0 = __uint_as_float(v1[2 * i]) - ref, c1 = __uint_as_float(v1[2 * i + 1]) - ref;
+            m0 = fmaxf(m0, fmaxf(a0, a1));
+            m1 = fmaxf(m1, fmaxf(c0, c1));
+            pk[i] = pack_bf16x2(fast_exp2(a0), fast_exp2(a1));
+            pk[16 + i] = pack_bf16x2(fast_exp2(c0), fast_exp2(c1));
+          }
+          pmax = fmaxf(m0, m1);
+        }
+        if (pmax > ATT_JUMP) {
+          // a score of this tile is more than 2^40 above the row reference (never at init, possible with sharp trained
+          // heads): raise the reference NOW, recompute this row's P against it and fold the factor into the rescale of
+          // O below, so no probability ever leaves the fp32 / bf16 range
+          const float dq = ceilf(pmax);
+          ref += dq;
+          alpha_pend *= fast_exp2(-dq);
+          pmax -= dq;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            pk[i] = pack_bf16x2(fast_exp2(__uint_as_float(v0[2 * i]) - ref), fast_exp2(__uint_as_float(v0[2 * i + 1]) - ref));
+            pk[16 + i] = pack_bf16x2(fast_exp2(__uint_as_float(v1[2 * i]) - ref), fast_exp2(__uint_as_float(v1[2 * i + 1]) - ref));
+          }
+        }
+        __syncwarp();
+        tmem_st32(tS, pk);
       }
-      __syncwarp();
-      tmem_st32(tS, pk);
       if (tr) { ATT_TRACE(0, t, 3) }
 
       // ---- P V_{t-1} must be complete before O is read (new item) or rescaled, and before P V_t may be issued

@@ -117,6 +117,7 @@ struct mmee_engine {
   int max_batch = 0;
   int H, L, heads, I, T, P, S, K, n_vis, n_patch, kdim_patch;
   int kv_pitch = 768, bias_pitch = 768;
+  int att_tail_j = -1, bias_width = 768;
   int m_max = 0;            // padded row capacity of activation buffers
   int sms = 148;
   int bn_h, bn_qkv, bn_i;   // BLOCK_N per GEMM family
@@ -525,7 +526,7 @@ void allocate(mmee_engine* e) {
   e->t_qk = make_tmap_2d_sw128(e->QK.p, M, 2 * H, 2 * H, 128);
   e->t_vt = make_tmap_2d_sw128(e->VT.p, static_cast<uint64_t>(B) * heads * 64, e->kv_pitch, e->kv_pitch, 64);
   e->t_k64 = make_tmap_2d_sw128(e->QK.p, M, 2 * H, 2 * H, ATT_BKV);
-  e->t_bias = make_tmap_2d_sw128(e->BIAS.p, static_cast<uint64_t>(B) * heads * S, e->bias_pitch, e->bias_pitch, ATT_BQ,
+  e->t_bias = make_tmap_2d_sw128(e->BIAS.p, static_cast<uint64_t>(B) * heads * S, e->bias_width, e->bias_pitch, ATT_BQ,
                                  CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
   if (e->n_kv_tiles > ATT_MAX_KV_TILES) throw std::runtime_error("too many key tiles");
   e->n_kv_tiles = (S + ATT_BKV - 1) / ATT_BKV;
@@ -779,7 +780,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     }
     AttArgs aa;
     aa.n_active_dev = e->n_dev.p + stage; aa.slot_meta = e->slot_meta.p; aa.ctx = e->CTX.p; aa.H = H;
-    aa.heads = heads; aa.seq = S; aa.err_flag = e->att_err.p; aa.trace = e->att_trace.p;
+    aa.heads = heads; aa.seq = S; aa.tail_j = e->att_tail_j; aa.err_flag = e->att_err.p; aa.trace = e->att_trace.p;
     {
       static bool configured_dev[64] = {};
       bool& configured = configured_dev[e->device & 63];   // the attribute is per device
@@ -932,6 +933,14 @@ int mmee_create(const mmee_model_desc* desc, int device, int max_batch, mmee_eng
   e->kdim_patch = d.channels * d.patch * d.patch;
   e->kv_pitch = ((e->S + 127) / 128) * 128;
   e->bias_pitch = ((e->S + ATT_BKV - 1) / ATT_BKV) * ATT_BKV;   // whole key tiles: the pitch padding carries the -60000 mask
+  // a last key tile with <= 16 real keys (S = 709: 5) runs as a 16-key tile: the bias rows end after those 16 columns
+  // (the tensor map is that narrow: TMA zero-fills the rest of the box without reading HBM) and S / softmax / P V touch a quarter of the tile
+  e->att_tail_j = -1;
+  e->bias_width = e->bias_pitch;
+  if (e->S > ATT_BKV && e->S % ATT_BKV != 0 && e->S % ATT_BKV <= 16 && !getenv("MMEE_NO_TAIL16")) {
+    e->att_tail_j = e->S / ATT_BKV;
+    e->bias_width = e->att_tail_j * ATT_BKV + 16;   // the row pitch stays a multiple of 128 B (a 1440 B pitch cost 5 %)
+  }
   if (e->kv_pitch > 1024) throw std::runtime_error("sequence too long for keymask_kernel");
   e->sms = prop.multiProcessorCount;
   if (const char* pr = getenv("MMEE_PRECISE_RESIDUAL")) e->precise_residual = pr[0] != '0';   // developer A/B switch
