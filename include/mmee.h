@@ -133,6 +133,25 @@ int  mmee_policy_scan(int device, int n_exits_plus1, int64_t n_samples, int n_la
                       const int64_t* labels, int32_t* exits_out, double* crit_out, int64_t* hist_out,
                       int64_t* correct_out);
 
+/* Temperature calibration of the per-exit logits: the device replacement of TemperatureScaler.set_temperature
+ * (EE/generic_scaling.py:64-111, scipy L-BFGS-B on log_loss(labels, softmax(logits / T))) as EE/eval.py:311-335 runs
+ * it once per exit.  Minimises nll(T_e) = mean_i -log softmax(logits[e][i] / T_e)[labels[i]] for every exit at once
+ * (safeguarded Newton on 1 / T, fp64; the problem is convex in 1 / T).  All buffers in HOST memory.
+ *   logits   f64 [E1, N, K] ; labels i64 [N] in [0, K) ; t_init f64 [E1] or NULL (= 1.0, the reference's start)
+ *   max_iter <= 0 : 40
+ * Outputs ([E1] each, all but t_out nullable): t_out fitted temperatures, nll_before (at t_init), nll_after,
+ * mean_conf_out = mean max softmax(logits / T) and accuracy_out = mean(argmax == label) at the fitted T.
+ * An exit whose data are separable has no finite minimiser (nll -> 0 as T -> 0); the iteration then stops where the
+ * fp64 gradient vanishes, as the reference's does. */
+int  mmee_temperature_fit(int device, int n_exits_plus1, int64_t n_samples, int n_labels, const double* logits,
+                          const int64_t* labels, const double* t_init, int max_iter, double* t_out, double* nll_before,
+                          double* nll_after, double* mean_conf_out, double* accuracy_out);
+/* The same statistics for given temperatures (NULL = 1.0): what EE/eval.py:325-335 collects from the calibrated
+ * test logits.  Outputs f64 [E1], each nullable. */
+int  mmee_calibration_stats(int device, int n_exits_plus1, int64_t n_samples, int n_labels, const double* logits,
+                            const int64_t* labels, const double* temperatures, double* nll_out, double* mean_conf_out,
+                            double* accuracy_out);
+
 const char* mmee_last_error(void);
 const char* mmee_version(void);
 

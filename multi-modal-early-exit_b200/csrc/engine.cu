@@ -21,6 +21,7 @@
 #include "gemm.cuh"
 #include "norm_exit.cuh"
 #include "policy.cuh"
+#include "calibrate.cuh"
 #include "tmap.h"
 
 using namespace mmee;
@@ -1235,6 +1236,88 @@ int mmee_policy_scan(int device, int n_exits_plus1, int64_t n_samples, int n_lab
   if (crit_out) CUDA_OK(cudaMemcpy(crit_out, d_crit.p, n_en * 8, cudaMemcpyDeviceToHost));
   if (hist_out) CUDA_OK(cudaMemcpy(hist_out, d_hist.p, static_cast<size_t>(n_thr) * E1 * 8, cudaMemcpyDeviceToHost));
   if (correct_out) CUDA_OK(cudaMemcpy(correct_out, d_correct.p, static_cast<size_t>(n_thr) * 8, cudaMemcpyDeviceToHost));
+  return 0;
+  MMEE_CATCH
+}
+
+namespace {
+// shared body of mmee_temperature_fit / mmee_calibration_stats: logits + labels to the device, `iters` Newton
+// iterations from t_init (0: none), then one statistics pass at the final temperatures
+void calibration_run(int device, int E1, int64_t N, int K, const double* logits, const int64_t* labels,
+                     const double* t_init, int iters, double* t_out, double* nll_before, double* nll_out,
+                     double* conf_out, double* acc_out) {
+  if (!logits || !labels) throw std::runtime_error("null argument");
+  if (E1 < 1 || N < 1 || K < 1) throw std::runtime_error("bad shape");
+  for (int64_t i = 0; i < N; ++i)
+    if (labels[i] < 0 || labels[i] >= K) throw std::runtime_error("label out of range");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw std::runtime_error("no CUDA device: libmmee has no CPU fallback");
+  CUDA_OK(cudaSetDevice(device));
+  const size_t n_log = static_cast<size_t>(E1) * N * K;
+  const int blocks = static_cast<int>(std::min<int64_t>((N + CALIB_THREADS - 1) / CALIB_THREADS, 64));
+  DevBuf<double> d_logits, d_beta, d_partial, d_stats;
+  DevBuf<int64_t> d_labels;
+  DevBuf<CalibState> d_state;
+  d_logits.alloc(n_log); d_labels.alloc(N); d_beta.alloc(E1);
+  d_partial.alloc(static_cast<size_t>(E1) * blocks * CALIB_NSTAT); d_stats.alloc(static_cast<size_t>(E1) * CALIB_NSTAT);
+  d_state.alloc(E1);
+  std::vector<double> beta(E1);
+  std::vector<CalibState> st(E1);
+  for (int e = 0; e < E1; ++e) {
+    const double t = t_init ? t_init[e] : 1.0;
+    if (!(t > 0.0)) throw std::runtime_error("temperatures must be positive");
+    beta[e] = 1.0 / t;
+    st[e] = CalibState{beta[e], beta[e], 0.0, 0.0, 0.0, 0};
+  }
+  CUDA_OK(cudaMemcpy(d_logits.p, logits, n_log * 8, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d_labels.p, labels, static_cast<size_t>(N) * 8, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d_beta.p, beta.data(), static_cast<size_t>(E1) * 8, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d_state.p, st.data(), static_cast<size_t>(E1) * sizeof(CalibState), cudaMemcpyHostToDevice));
+  const unsigned ub = (E1 + 31) / 32;
+  for (int it = 0; it < iters; ++it) {
+    calib_stats_kernel<<<dim3(blocks, E1), CALIB_THREADS>>>(d_logits.p, d_labels.p, d_beta.p, N, K, d_partial.p);
+    calib_update_kernel<<<ub, 32>>>(d_partial.p, blocks, N, E1, d_state.p, d_beta.p, d_stats.p, 1);
+  }
+  CUDA_OK(cudaGetLastError());
+  if (iters > 0) {
+    // the last ACCEPTED point is the answer (the pending trial step is dropped)
+    CUDA_OK(cudaMemcpy(st.data(), d_state.p, static_cast<size_t>(E1) * sizeof(CalibState), cudaMemcpyDeviceToHost));
+    for (int e = 0; e < E1; ++e) beta[e] = st[e].beta_ok;
+    CUDA_OK(cudaMemcpy(d_beta.p, beta.data(), static_cast<size_t>(E1) * 8, cudaMemcpyHostToDevice));
+  }
+  calib_stats_kernel<<<dim3(blocks, E1), CALIB_THREADS>>>(d_logits.p, d_labels.p, d_beta.p, N, K, d_partial.p);
+  calib_update_kernel<<<ub, 32>>>(d_partial.p, blocks, N, E1, d_state.p, d_beta.p, d_stats.p, 0);
+  CUDA_OK(cudaGetLastError());
+  std::vector<double> stats(static_cast<size_t>(E1) * CALIB_NSTAT);
+  CUDA_OK(cudaMemcpy(stats.data(), d_stats.p, stats.size() * 8, cudaMemcpyDeviceToHost));
+  for (int e = 0; e < E1; ++e) {
+    if (t_out) t_out[e] = 1.0 / beta[e];
+    if (nll_before) nll_before[e] = iters > 0 ? st[e].nll_first : stats[e * CALIB_NSTAT + 0];
+    if (nll_out) nll_out[e] = stats[e * CALIB_NSTAT + 0];
+    if (conf_out) conf_out[e] = stats[e * CALIB_NSTAT + 3];
+    if (acc_out) acc_out[e] = stats[e * CALIB_NSTAT + 4];
+  }
+}
+}  // namespace
+
+int mmee_temperature_fit(int device, int n_exits_plus1, int64_t n_samples, int n_labels, const double* logits,
+                         const int64_t* labels, const double* t_init, int max_iter, double* t_out, double* nll_before,
+                         double* nll_after, double* mean_conf_out, double* accuracy_out) {
+  MMEE_TRY
+  if (!t_out) throw std::runtime_error("null argument");
+  calibration_run(device, n_exits_plus1, n_samples, n_labels, logits, labels, t_init, max_iter > 0 ? max_iter : 40,
+                  t_out, nll_before, nll_after, mean_conf_out, accuracy_out);
+  return 0;
+  MMEE_CATCH
+}
+
+int mmee_calibration_stats(int device, int n_exits_plus1, int64_t n_samples, int n_labels, const double* logits,
+                           const int64_t* labels, const double* temperatures, double* nll_out, double* mean_conf_out,
+                           double* accuracy_out) {
+  MMEE_TRY
+  calibration_run(device, n_exits_plus1, n_samples, n_labels, logits, labels, temperatures, 0, nullptr, nullptr,
+                  nll_out, mean_conf_out, accuracy_out);
   return 0;
   MMEE_CATCH
 }

@@ -1,6 +1,8 @@
 """CPU tests: the oracle port and policy port against the golden vectors (outputs of the
 unmodified reference, tests/golden/make_golden.py) and, when /root/reference is present,
 against the reference's own classes live."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -82,3 +84,20 @@ def test_port_matches_live_reference_tiny():
     assert torch.allclose(out["exit_logits"], ref["exit_logits"], atol=2e-6)
     assert torch.allclose(out["head_logits"], ref["head_logits"], atol=2e-6)
     assert torch.allclose(out["last_hidden"], ref["last_hidden"], atol=2e-5)
+
+
+@pytest.mark.parametrize("name", ["cal_a", "cal_b", "cal_c"])
+def test_calibration_port_matches_reference_temperatures(name):
+    """oracle/calibration_port.py against the temperatures the reference's own TemperatureScaler produced
+    (tests/golden/make_calibration_golden.py; one scaler reused across exits as EE/eval.py:298-313 does)."""
+    from oracle import calibration_port
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "calibration.npz"))
+    seed, E1, N, K = (int(v) for v in g[f"{name}_shape"])
+    logits, labels = calibration_port.synthetic_exit_logits(seed, E1, N, K)
+    scaler = calibration_port.TemperatureScalerPort()
+    for e in range(E1):
+        t = float(scaler.fit(labels, logits[e])[0])
+        assert abs(t - g[f"{name}_t_ref"][e]) <= 1e-3 * g[f"{name}_t_ref"][e]
+        assert abs(calibration_port.nll(labels, logits[e], t) - g[f"{name}_nll_ref"][e]) < 1e-8
+        # both sit at the minimiser up to L-BFGS-B's tolerance
+        assert abs(t - g[f"{name}_t_opt"][e]) <= 1e-3 * g[f"{name}_t_opt"][e]

@@ -90,3 +90,90 @@ def test_accuracy_calibration_heuristic_matches_loop():
     assert np.array_equal(ex, want) and np.array_equal(pred.numpy(), wpred)
     with pytest.raises(Exception, match="calibration_metrics"):
         Policy(lg, {"epsilon": 0.1}).accuracy_calibration_heuristic()
+
+
+# ------------------------------------------------------------------ temperature calibration (mmee_temperature_fit)
+def _cal_case(name):
+    import os
+    from oracle import calibration_port
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "calibration.npz"))
+    seed, E1, N, K = (int(v) for v in g[f"{name}_shape"])
+    logits, labels = calibration_port.synthetic_exit_logits(seed, E1, N, K)
+    return g, logits, labels
+
+
+@pytest.mark.parametrize("name", ["cal_a", "cal_b", "cal_c"])
+def test_temperature_fit_matches_reference_golden(name):
+    """Device fit vs the temperatures of the reference's own TemperatureScaler (golden) and the exact minimiser.
+    The reference stops within 4e-4 (relative) of the minimiser (L-BFGS-B defaults, finite-difference gradient,
+    tests/golden/make_calibration_golden.py), hence 1e-3 against it and 1e-7 against the minimiser; the device NLL
+    is never above the reference's."""
+    from mmee.calibration import temperature_fit
+    from oracle import calibration_port
+    g, logits, labels = _cal_case(name)
+    res = temperature_fit(logits, labels)
+    t = res["temperature"]
+    assert np.all(np.abs(t - g[f"{name}_t_ref"]) <= 1e-3 * g[f"{name}_t_ref"])
+    assert np.all(np.abs(t - g[f"{name}_t_opt"]) <= 1e-7 * g[f"{name}_t_opt"])
+    for e in range(logits.shape[0]):
+        assert abs(res["nll_after"][e] - calibration_port.nll(labels, logits[e], t[e])) < 1e-12
+        assert res["nll_after"][e] <= g[f"{name}_nll_ref"][e] + 1e-13
+        assert abs(res["nll_before"][e] - calibration_port.nll(labels, logits[e], 1.0)) < 1e-11
+        assert res["accuracy"][e] == pytest.approx(np.mean(logits[e].argmax(-1) == labels), abs=1e-15)
+        sm = policy_port.softmax64(logits[e] / t[e])
+        assert res["average_confidence"][e] == pytest.approx(sm.max(-1).mean(), abs=1e-12)
+
+
+def test_temperature_scaler_drop_in_and_calibrate_loop():
+    """Same object protocol as EE/generic_scaling.py:37-61 (fit -> temperature [1], temperature_scale, transform),
+    warm start from the previous exit as EE/eval.py:298-313; `calibrate` equals the oracle's restatement of
+    EE/eval.py:293-335 (temperatures to L-BFGS-B's tolerance, accuracy exactly)."""
+    from mmee.calibration import TemperatureScaler, calibrate, calibration_stats
+    from oracle import calibration_port
+    g, logits, labels = _cal_case("cal_a")
+    T = TemperatureScaler()
+    for e in range(logits.shape[0]):
+        t = T.fit(labels, logits[e])
+        assert t.shape == (1,) and abs(t[0] - g["cal_a_t_opt"][e]) <= 1e-7 * g["cal_a_t_opt"][e]
+        assert np.allclose(T.temperature_scale(logits[e]), logits[e] / t[0], rtol=0, atol=0)
+        assert np.allclose(T.transform(logits[e]).sum(-1), 1.0)
+    test_logits, _ = calibration_port.synthetic_exit_logits(99, logits.shape[0], logits.shape[1], logits.shape[2])
+    cal, met = calibrate(logits, labels, test_logits)
+    cal_o, met_o = calibration_port.calibrate(logits, labels, test_logits)
+    assert set(met) == {"ece", "accuracy", "temperature", "average_confidence"}
+    assert np.allclose(met["temperature"], met_o["temperature"], rtol=1e-3)
+    assert np.allclose(cal, cal_o, rtol=1e-3)
+    assert met["accuracy"] == pytest.approx(met_o["accuracy"], abs=1e-15)
+    assert np.allclose(met["average_confidence"], met_o["average_confidence"], atol=1e-3)
+    assert np.allclose(met["ece"], met_o["ece"], atol=5e-3)
+    # the metrics feed the heuristic policy unchanged (EE/policy.py:68-79)
+    thr = heuristic_thresholds(met, 0.05, logits.shape[0])
+    assert thr.shape == (logits.shape[0],) and np.all((thr > 0) & (thr < 1))
+    st = calibration_stats(test_logits, labels, met["temperature"])
+    assert np.allclose(st["average_confidence"], met["average_confidence"])
+
+
+def test_temperature_fit_full_size_stationary_and_edge_cases():
+    """RVL-CDIP-validation-sized store (40k samples, 14 exits): at the returned T the NLL derivative vanishes and
+    neighbouring temperatures are worse (size-independent optimality check); separable exits and bad labels."""
+    from mmee.calibration import temperature_fit
+    from oracle import calibration_port
+    logits, labels = calibration_port.synthetic_exit_logits(5, 14, 40000, 16)
+    res = temperature_fit(logits, labels)
+    for e in (0, 6, 13):
+        t = res["temperature"][e]
+        n0, n1, n2 = (calibration_port.nll(labels, logits[e], t * f) for f in (1.0, 1.001, 0.999))
+        assert n0 <= n1 and n0 <= n2
+        assert abs((n1 - n2) / (0.002 * t)) < 1e-6                      # central difference of d nll / dT
+        assert abs(res["nll_after"][e] - n0) < 1e-12
+    # warm start far away converges to the same minimiser
+    far = temperature_fit(logits, labels, t_init=np.full(14, 50.0))
+    assert np.allclose(far["temperature"], res["temperature"], rtol=1e-7)
+    # a separable exit has no finite minimiser: the call returns a small positive T with nll ~ 0, no NaN
+    sep = np.zeros((1, 64, 4)); lab = np.arange(64) % 4; sep[0, np.arange(64), lab] = 5.0
+    r = temperature_fit(sep, lab)
+    assert np.isfinite(r["temperature"][0]) and 0 < r["temperature"][0] < 1 and r["nll_after"][0] < 1e-6
+    with pytest.raises(RuntimeError, match="label out of range"):
+        temperature_fit(sep, lab + 1)
+    with pytest.raises(ValueError):
+        temperature_fit(sep, lab[:-1])
