@@ -48,8 +48,17 @@ typedef struct {
 
 /* Exit policy: EarlyExitInference criterion + sign (EE/models/EE_modules.py:116-146), per-exit thresholds
  * (EE/policy.py:17, :71-79) and per-exit temperatures (EE/generic_scaling.py:54-61, EE/eval.py:312-327). */
+#define MMEE_CRIT_MAX_CONFIDENCE 0
+#define MMEE_CRIT_ENTROPY        1
+#define MMEE_CRIT_LTE            2
+
 typedef struct {
-  int criterion;              /* 0 max_confidence: exit iff crit > thr ; 1 entropy: exit iff crit < thr */
+  int criterion;              /* 0 max_confidence: exit iff crit > thr ; 1 entropy: exit iff crit < thr ;
+                                 2 LTE (EE_config["use_lte"], EE/models/LayoutLMv3.py:142-149, 231-268): crit =
+                                 sigmoid(lte_classifier(exit input row)), exit iff crit < thr, taken only at encoder
+                                 exits after layer l < number of encoder exits (the reference's `i + 1 <
+                                 self.num_layers`); embedding-level exits are scored but never taken.  Temperatures
+                                 do not enter the LTE score.  Needs layoutlmv3.encoder.lte_classifier.{weight,bias}. */
   int mode;                   /* 0 dense: every exit head for every document (what the reference computes);
                                  1 early-exit: exiting documents leave, deeper layers run on survivors only */
   const float* thresholds;    /* [n_exits]   (host) */

@@ -119,6 +119,8 @@ struct mmee_engine {
   int H, L, heads, I, T, P, S, K, n_vis, n_patch, kdim_patch;
   int kv_pitch = 768, bias_pitch = 768;
   int att_tail_j = -1, bias_width = 768;
+  DevBuf<float> lte_w, slot_lte;   // learned-to-exit scorer [H] (optional) and its per-slot scores
+  float lte_b = 0.f;
   int m_max = 0;            // padded row capacity of activation buffers
   int sms = 148;
   int bn_h, bn_qkv, bn_i;   // BLOCK_N per GEMM family
@@ -464,6 +466,12 @@ void finalize(mmee_engine* e) {
     upload_f32(e->classifier.dense_b, need(e, "classifier.dense.bias", {H}));
   }
 
+  // optional learned-to-exit scorer (EE/models/LayoutLMv3.py:142-149): Linear(H, 1); needed for criterion 2 only
+  if (e->raw.count(p + "encoder.lte_classifier.weight")) {
+    upload_f32(e->lte_w, need(e, p + "encoder.lte_classifier.weight", {1, H}));
+    e->lte_b = need(e, p + "encoder.lte_classifier.bias", {1})[0];
+  }
+
   if (e->h_lut1.empty()) e->h_lut1 = default_lut(d.rel_bins, d.max_rel, 1024);
   if (e->h_lut2.empty()) e->h_lut2 = default_lut(d.rel2d_bins, d.max_rel2d, 1024);
   e->lut1.alloc(e->h_lut1.size());
@@ -560,6 +568,7 @@ void allocate(mmee_engine* e) {
   e->all_head.alloc(static_cast<size_t>(E1) * B * K);
   e->all_crit.alloc(static_cast<size_t>(E1) * B);
   e->hist.alloc(E1, true);
+  e->slot_lte.alloc(B, true);
   e->hist64.alloc(E1, true);
 }
 
@@ -570,6 +579,9 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   if (B < 1 || B > e->max_batch) throw std::runtime_error("batch out of range");
   if (!pol || (e->d.n_exits > 0 && !pol->thresholds)) throw std::runtime_error("policy/thresholds missing");
   if (!out || !out->logits || !out->exit_index) throw std::runtime_error("outputs missing");
+  if (pol->criterion < 0 || pol->criterion > 2) throw std::runtime_error("criterion must be 0, 1 or 2");
+  if (pol->criterion == MMEE_CRIT_LTE && !e->lte_w.p)
+    throw std::runtime_error("criterion LTE needs the weights layoutlmv3.encoder.lte_classifier.{weight,bias}");
   const mmee_model_desc& d = e->d;
   const int H = e->H, S = e->S, T = e->T, K = e->K, heads = e->heads, I = e->I;
   const int E = d.n_exits, E1 = E + 1;
@@ -704,6 +716,15 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     xa.inv_temp = 1.0f / Te;
     xa.threshold = is_final ? 0.f : pol->thresholds[exit_no];
     xa.force = is_final ? 1 : 0;
+    if (pol->criterion == MMEE_CRIT_LTE) {
+      // the reference raises EarlyExitException only inside the encoder, at layer i + 1 < num_layers where
+      // num_layers = len(exit_encoder_layers) (EE/models/LayoutLMv3.py:139, 250-268); other exits are scored, never taken
+      int n_enc = 0;
+      for (int x = 0; x < E; ++x) n_enc += d.exit_after_layer[x] > 0 ? 1 : 0;
+      const int code = is_final ? 0 : d.exit_after_layer[exit_no];
+      if (!is_final && !(code > 0 && code < n_enc)) xa.threshold = -INFINITY;
+      xa.lte_w = e->lte_w.p; xa.lte_b = e->lte_b; xa.slot_lte = e->slot_lte.p;
+    }
     xa.slot_logits = e->slot_logits.p; xa.slot_head = e->slot_head.p; xa.slot_crit = e->slot_crit.p;
     xa.slot_fire = e->slot_fire.p;
     xa.group_ticket = e->exit_tickets.p; xa.groups_done = e->exit_tickets.p + (e->max_batch + EXF_DOCS - 1) / EXF_DOCS;

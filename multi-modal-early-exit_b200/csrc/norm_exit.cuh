@@ -343,7 +343,10 @@ struct ExitFusedArgs {
   // (3) heads: input of each out_proj: 0 / 1 = T[0] / T[1], 2 = the normalised rows themselves, -1 = head unused
   int head_src, cls_src;
   HeadWeights head, cls;
-  int gate_mode, n_labels, criterion;
+  int gate_mode, n_labels, criterion;   // criterion: 0 max softmax (>), 1 entropy (<), 2 LTE (<)
+  const float* lte_w;       // criterion 2: the learned-to-exit scorer sigmoid(lte_w . row + lte_b) on the exit head's
+  float lte_b;              // own input row (EE/models/LayoutLMv3.py:142-149, 231-237); the class logits are unchanged
+  float* slot_lte;          // [maxB] scratch
   float inv_temp, threshold;
   int force;
   float* slot_logits; float* slot_head; float* slot_crit; int* slot_fire;
@@ -486,6 +489,20 @@ __global__ void __launch_bounds__(EXF_THREADS) exit_fused_kernel(ExitFusedArgs a
       const int c = (lane + 32 * i) * 4;
       if (c < H) *reinterpret_cast<float4*>(z + c) = v[i];
     }
+    if (a.lte_w && blockIdx.x == 0 && blockIdx.z == 0) {       // one CTA of the group scores the rows
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (c < H) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.lte_w + c));
+          acc = fmaf(w4.x, v[i].x, acc); acc = fmaf(w4.y, v[i].y, acc);
+          acc = fmaf(w4.z, v[i].z, acc); acc = fmaf(w4.w, v[i].w, acc);
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) a.slot_lte[slot] = acc + a.lte_b;
+    }
   }
   __syncthreads();
 
@@ -589,6 +606,8 @@ __global__ void __launch_bounds__(EXF_THREADS) exit_fused_kernel(ExitFusedArgs a
     float crit;
     if (a.criterion == 0) {
       crit = 1.0f / A;
+    } else if (a.criterion == 2) {
+      crit = 1.0f / (1.0f + expf(-__ldcg(a.slot_lte + slot)));     // nn.Sigmoid of the LTE score (written by another SM)
     } else {
       const float Bz = warp_sum((lane < K) ? (z - zmax) * ex : 0.f);
       crit = logf(A) - Bz / A;

@@ -27,12 +27,14 @@ class ExitConfig:
     encoder_layer_strategy: str = "ramp"            # "ramp" | "gate"
     exit_head_num_layers: int = 2
     model_weights: str = ""                         # accepted and ignored (reference: processor name)
+    use_lte: bool = False                           # EE_config["use_lte"] (EE/models/LayoutLMv3.py:140): learned-to-exit
 
     @classmethod
     def from_dict(cls, d: dict) -> "ExitConfig":
         known = {k: v for k, v in d.items() if k in cls.__dataclass_fields__}
         cfg = cls(**known)
         cfg.inference_strategy = str(cfg.inference_strategy)
+        cfg.use_lte = bool(cfg.use_lte) and str(cfg.use_lte) != "False"
         cfg.encoder_layer_strategy = str(cfg.encoder_layer_strategy)
         if isinstance(cfg.exits, str):  # reference accepts "a,b,1,2" (EE/models/LayoutLMv3.py:100-108)
             parsed: List[Union[str, int]] = []

@@ -77,6 +77,7 @@ def bucket_lut(num_buckets: int, max_distance: int, n: int = 1024) -> np.ndarray
 
 
 EMBEDDING_EXIT_CODES = {"vision_avg": -2, "text_avg": -1, "text_visual_concat": 0}   # include/mmee.h MMEE_EXIT_*
+CRITERION_CODES = {"max_confidence": 0, "entropy": 1, "lte": 2}                        # include/mmee.h MMEE_CRIT_*
 
 
 class B200EEForSequenceClassification:
@@ -165,6 +166,12 @@ class B200EEForSequenceClassification:
     def eval(self):
         return self
 
+    def _default_criterion(self) -> str:
+        """Early-exit decision rule of `infer*`: the learned-to-exit scorer when EE_config["use_lte"] is set
+        (EE/models/LayoutLMv3.py:140, 231-268: sigmoid(lte_classifier(CLS)) < global_threshold, encoder exits
+        after layer l < number of encoder exits only), else the configured confidence criterion."""
+        return "lte" if self.ee.use_lte else self.ee.inference_strategy
+
     def __call__(self, *a, **k):
         return self.forward(*a, **k)
 
@@ -208,7 +215,7 @@ class B200EEForSequenceClassification:
             out.all_exit_logits, out.all_head_logits, out.all_criteria = all_l.data_ptr(), all_h.data_ptr(), all_c.data_ptr()
         thr = np.broadcast_to(np.asarray(thresholds, dtype=np.float32), (max(self.n_exits, 1),)).copy()
         pol = _lib.Policy()
-        pol.criterion = 0 if criterion == "max_confidence" else 1
+        pol.criterion = CRITERION_CODES[criterion]
         pol.mode = mode
         pol.thresholds = thr.ctypes.data_as(C.POINTER(C.c_float))
         tmp = None
@@ -262,7 +269,7 @@ class B200EEForSequenceClassification:
               temperatures: Optional[Sequence[float]] = None, criterion: Optional[str] = None,
               early_exit: bool = True, return_all: bool = False, **unused) -> EarlyExitResult:
         thr = self.ee.global_threshold if exit_threshold is None else exit_threshold
-        crit_name = criterion or self.ee.inference_strategy
+        crit_name = criterion or self._default_criterion()
         r = self._run(input_ids, attention_mask, bbox, pixel_values, crit_name, 1 if early_exit else 0,
                       np.atleast_1d(np.asarray(thr, dtype=np.float32)), temperatures, return_all)
         ex = r["exit_index"].cpu().numpy().astype(np.int32)
@@ -285,7 +292,7 @@ class B200EEForSequenceClassification:
         criterion f32 [B], hist i64 [E+1]) and the call is asynchronous on the current stream — what the
         data-parallel gather (`mmee.dist`) and pipelined callers want.  Inputs must be CUDA tensors."""
         thr = self.ee.global_threshold if exit_threshold is None else exit_threshold
-        crit_name = criterion or self.ee.inference_strategy
+        crit_name = criterion or self._default_criterion()
         r = self._run(input_ids, attention_mask, bbox, pixel_values, crit_name, 1 if early_exit else 0,
                       np.atleast_1d(np.asarray(thr, dtype=np.float32)), temperatures, False)
         return {"logits": r["logits"], "exit_index": r["exit_index"], "criterion": r["criterion"], "hist": r["hist"]}
@@ -316,7 +323,7 @@ class B200EEForSequenceClassification:
         thr = self.ee.global_threshold if exit_threshold is None else exit_threshold
         thr = np.broadcast_to(np.asarray(thr, dtype=np.float32), (max(self.n_exits, 1),)).copy()
         pol = _lib.Policy()
-        pol.criterion = 0 if (criterion or self.ee.inference_strategy) == "max_confidence" else 1
+        pol.criterion = CRITERION_CODES[criterion or self._default_criterion()]
         pol.mode = 1 if early_exit else 0
         pol.thresholds = thr.ctypes.data_as(C.POINTER(C.c_float))
         tmp = None

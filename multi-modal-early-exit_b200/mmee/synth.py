@@ -79,7 +79,9 @@ def state_dict_spec(dims: ModelDims, ee: ExitConfig) -> "OrderedDict[str, Tuple[
         head(p + "concat_exit_embeddings", out_f)
     lin("classifier.dense", H, H)
     lin("classifier.out_proj", dims.n_labels, H)
-    return spec
+    if getattr(ee, "use_lte", False):
+        lin(p + "encoder.lte_classifier", 1, H)             # EE/models/LayoutLMv3.py:144 (appended last: earlier
+    return spec                                             # tensors keep their seeded values)
 
 
 def make_state_dict(dims: ModelDims, ee: ExitConfig, seed: int = 0, std: float = 0.02,

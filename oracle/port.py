@@ -215,3 +215,34 @@ def forward(sd, dims, ee, docs, keep_hidden: bool = False) -> Dict[str, torch.Te
     if keep_hidden:
         out["hidden"] = torch.stack(hidden)
     return out
+
+
+def lte_scores(sd, out) -> torch.Tensor:
+    """sigmoid(lte_classifier(exit input row)) for every exit row [E+1, B]
+    (EE/models/LayoutLMv3.py:142-149, 231-237; model level :597-602)."""
+    w = sd["layoutlmv3.encoder.lte_classifier.weight"].float()
+    b = sd["layoutlmv3.encoder.lte_classifier.bias"].float()
+    return torch.sigmoid(out["cls_rows"] @ w.t() + b).squeeze(-1)
+
+
+def lte_exit(sd, ee, out, threshold: float) -> Dict[str, torch.Tensor]:
+    """Learned-to-exit decision per document (the reference evaluates it for one document at a time,
+    EE/models/LayoutLMv3.py:250-268): the first ENCODER exit after layer l with l < len(exit_encoder_layers)
+    (`i + 1 < self.num_layers`, :139, :252) whose score is < threshold (`lte_th = [exit_threshold] * num_layers`,
+    :147-149) is taken and its class logits returned (:739-748); embedding-level exits are scored only.
+    `out` is the dict of `forward`.  Returns exit_index [B] (index into the E+1 exits), logits [B,K], scores."""
+    scores = lte_scores(sd, out)
+    names = [x for x in ("vision_avg", "text_avg", "text_visual_concat") if x in ee.exits]
+    enc = sorted(ee.encoder_exit_layers)
+    layer_of = [0] * len(names) + enc                       # 0 = embedding level
+    E = len(layer_of)
+    B = scores.shape[1]
+    exit_index = torch.full((B,), E, dtype=torch.int64)
+    for d in range(B):
+        for e in range(E):
+            if 0 < layer_of[e] < len(enc) and scores[e, d] < threshold:
+                exit_index[d] = e
+                break
+    logits = out["exit_logits"][exit_index, torch.arange(B)]
+    return {"exit_index": exit_index, "logits": logits, "scores": scores,
+            "exit_layer": torch.tensor([layer_of[e] if e < E else 0 for e in exit_index.tolist()])}

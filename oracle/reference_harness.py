@@ -91,6 +91,8 @@ def build_reference_model(dims, ee, state_dict=None):
         "global_threshold": ee.global_threshold,
         "model_weights": "microsoft/layoutlmv3-base",
     }
+    if getattr(ee, "use_lte", False):
+        cfg.EE_config["use_lte"] = True
     torch.manual_seed(0)
     model = L.LayoutLMv3EEForSequenceClassification(cfg).eval()
     if state_dict is not None:
@@ -163,3 +165,30 @@ def reference_forward_image_only(model, pixel_values):
         "criteria": torch.stack(crit).float(),
         "last_hidden": last.float(),
     }
+
+
+def reference_forward_lte(model, docs):
+    """The reference's learned-to-exit inference (EE_config["use_lte"], EE/models/LayoutLMv3.py:231-268, 728-748).
+    Its exit test compares a squeezed tensor with a float, which is only defined for ONE document, so the model is
+    run document by document; no labels are passed (they would only add losses).  Returns logits [B,K] (the
+    `outputs.logits` of each call: the exit ramp's logits / classifier(CLS_j) in gate mode when the encoder raised
+    EarlyExitException, else the final classifier) and exit_layer [B] (encoder layer of the exit taken, 0 = ran to
+    the end), read from the exception the inner model raises."""
+    import torch
+
+    L = load()
+    B = docs["pixel_values"].shape[0]
+    logits, layers = [], []
+    with torch.no_grad():
+        for i in range(B):
+            d1 = {k: v[i:i + 1] for k, v in docs.items() if k != "labels"}
+            out = model(**d1)
+            logits.append(out.logits.reshape(-1).float())
+            try:
+                model.layoutlmv3(d1["input_ids"], attention_mask=d1["attention_mask"], bbox=d1["bbox"],
+                                 pixel_values=d1["pixel_values"], return_dict=True)
+                layers.append(0)
+            except L.EarlyExitException as ex:
+                # identifier = "encoder_exit_<layer>_<head type>" (EE/models/LayoutLMv3.py:82, 115-118)
+                layers.append(int(str(ex.exit_layer).split("_")[2]))
+    return {"logits": torch.stack(logits), "exit_layer": torch.tensor(layers, dtype=torch.int64)}

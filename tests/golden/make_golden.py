@@ -60,6 +60,64 @@ CASES = {
 }
 
 
+# learned-to-exit inference (EE_config["use_lte"]); the reference runs it one document at a time.  The tiny cases
+# use weight std 0.08 (at 0.02 their CLS rows are nearly identical across documents and every document takes the
+# same exit); the base case keeps the usual 0.02, for which the 1e-2 logit tolerance is stated.  The global threshold is picked (with the oracle port's scores) as the candidate that yields the most distinct exit
+# layers with the widest margin between any visited score and the threshold, then the REFERENCE is run with it.
+LTE_CASES = {
+    # name: (dims ctor, dims kwargs, ee dict, n_docs, weight seed, doc seed, weight std)
+    "tiny_lte_ramp": ("tiny", {}, dict(exits=["text_visual_concat", 1, 2, 3], encoder_layer_strategy="ramp",
+                                       inference_strategy="max_confidence", use_lte=True), 10, 6, 12, 0.08),
+    "tiny_lte_gate": ("tiny", {}, dict(exits=["vision_avg", "text_visual_concat", 1, 2, 3], encoder_layer_strategy="gate",
+                                       inference_strategy="entropy", use_lte=True), 8, 7, 13, 0.08),
+    "base4_lte_ramp": ("base", {"layers": 4}, dict(exits=["text_visual_concat", 1, 2, 3, 4], encoder_layer_strategy="ramp",
+                                                   inference_strategy="max_confidence", use_lte=True), 8, 1, 14, 0.02),
+}
+
+
+def pick_lte_threshold(sd, ee, out):
+    from oracle import port
+    sc = port.lte_scores(sd, out).double()
+    vals = torch.unique(sc.flatten())
+    best = None
+    for thr in ((vals[:-1] + vals[1:]) / 2).tolist():
+        r = port.lte_exit(sd, ee, out, thr)
+        margin = 1.0
+        for d, e in enumerate(r["exit_index"].tolist()):            # every score the decision path of document d visits
+            for x in range(min(e, sc.shape[0] - 2) + 1):
+                margin = min(margin, abs(float(sc[x, d]) - thr))
+        key = (len(set(r["exit_layer"].tolist())), margin)
+        if best is None or key > best[0]:
+            best = (key, thr)
+    return round(best[1], 6), best[0]
+
+
+def run_lte_case(name):
+    from oracle import port
+    ctor, kw, eed, n, wseed, dseed, std = LTE_CASES[name]
+    dims = getattr(ModelDims, ctor)(**kw)
+    ee = ExitConfig.from_dict(eed)
+    sd = synth.make_state_dict(dims, ee, seed=wseed, std=std)
+    docs = synth.make_docs(dims, n, seed=dseed, pad=True)
+    thr, key = pick_lte_threshold(sd, ee, port.forward(sd, dims, ee, docs))
+    eed = dict(eed, global_threshold=thr)
+    ee = ExitConfig.from_dict(eed)
+    t0 = time.time()
+    model = RH.build_reference_model(dims, ee, sd)
+    ref = RH.reference_forward_lte(model, docs)
+    dt = time.time() - t0
+    np.savez_compressed(
+        os.path.join(OUT, f"{name}.npz"),
+        meta=json.dumps(dict(ctor=ctor, dims_kw=kw, ee=eed, n=n, wseed=wseed, dseed=dseed, pad=True, std=std,
+                             torch=torch.__version__, ref_seconds=round(dt, 2))),
+        logits=ref["logits"].numpy(), exit_layer=ref["exit_layer"].numpy(),
+        input_ids_sum=docs["input_ids"].sum(1).numpy(),
+        bbox_sum=docs["bbox"].sum((1, 2)).numpy(),
+        pixel_sum=docs["pixel_values"].double().sum((1, 2, 3)).numpy())
+    print(f"{name}: thr {thr} (distinct layers, margin) {key}  reference LTE forwards {dt:.1f}s  "
+          f"exit layers {ref['exit_layer'].tolist()}")
+
+
 def run_case(name):
     ctor, kw, eed, n, wseed, dseed, pad = CASES[name]
     dims = getattr(ModelDims, ctor)(**kw)
@@ -110,6 +168,6 @@ def run_case(name):
 if __name__ == "__main__":
     assert RH.available(), "reference not present"
     torch.set_num_threads(os.cpu_count())
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or list(CASES) + list(LTE_CASES)
     for nm in names:
-        run_case(nm)
+        run_lte_case(nm) if nm in LTE_CASES else run_case(nm)

@@ -364,3 +364,54 @@ def test_large_scores_exercise_lazy_rescale(gain):
     print(f"gain {gain}: max|logits - port| = {err:.3e}")
     assert err <= LOGIT_TOL
     model.close()
+
+
+DELTA_LTE = 2.5e-3        # decisive margin on the learned-to-exit score sigmoid(w . CLS + b); measured engine-vs-port
+                          # score error: 5e-4 (base, std 0.02 weights), 1.8e-3 (tiny cases, std 0.08 weights)
+
+
+@pytest.mark.parametrize("name", ["tiny_lte_ramp", "tiny_lte_gate", "base4_lte_ramp"])
+def test_lte_early_exit_matches_reference_golden(name):
+    """EE_config["use_lte"] (EE/models/LayoutLMv3.py:142-149, 231-268): documents leave at the first eligible
+    encoder exit whose learned score is below the global threshold.  Exit layers equal the reference's (run one
+    document at a time, golden) for every document whose visited scores keep DELTA_LTE from the threshold;
+    returned logits within 1e-2; early-exit mode == dense mode bit for bit."""
+    from helpers import LTE_CASES  # noqa: F401
+    from oracle import port
+    model, g, dims, ee, sd, docs = _engine(name, max_batch=16)
+    thr = float(ee.global_threshold)
+    res = model.infer(**_cuda(docs), return_all=True)               # criterion defaults to "lte"
+    layer_of = [max(l, 0) for l in model.exit_layers] + [0]          # exit index -> encoder layer (0 = none / final)
+    got_layer = np.array([layer_of[e] for e in res.exits_store])
+    ref_layer = g["exit_layer"]
+    scores = port.lte_scores(sd, port.forward(sd, dims, ee, docs)).numpy()
+    E = model.n_exits
+    decisive = np.ones(len(ref_layer), bool)
+    for d_i, l in enumerate(ref_layer):
+        stop = model.exit_layers.index(int(l)) if l > 0 else E - 1
+        decisive[d_i] = np.abs(scores[:stop + 1, d_i] - thr).min() > DELTA_LTE
+    agree = (got_layer == ref_layer)
+    print(f"{name}: exit layers {got_layer.tolist()} reference {ref_layer.tolist()} decisive {int(decisive.sum())}/{len(decisive)}")
+    assert decisive.sum() >= 3
+    assert agree[decisive].all()
+    err = np.abs(res.logits.cpu().numpy() - g["logits"])[agree].max()
+    print(f"{name}: max|logits - reference| = {err:.3e}")
+    assert err <= LOGIT_TOL
+    # the engine's scores at the exits each document reached equal the port's
+    got_scores = res.all_criteria.cpu().numpy()
+    reached = ~np.isnan(got_scores)
+    print(f"{name}: max|score - port| = {np.abs(got_scores - scores)[reached].max():.3e}")
+    assert np.abs(got_scores - scores)[reached].max() < DELTA_LTE
+    # dense mode takes the same decisions and returns the same bits
+    dense = model.infer(**_cuda(docs), early_exit=False)
+    assert np.array_equal(dense.exits_store, res.exits_store)
+    assert torch.equal(dense.logits, res.logits)
+    # max-confidence policy on the same engine still works (the scorer is only read by criterion "lte")
+    conf = model.infer(**_cuda(docs), criterion="max_confidence", exit_threshold=0.5)
+    assert conf.exits_store.shape == res.exits_store.shape
+
+
+def test_lte_needs_its_weights():
+    model, g, dims, ee, sd, docs = _engine("tiny_ramp_conf")
+    with pytest.raises(RuntimeError, match="lte_classifier"):
+        model.infer(**_cuda(docs), criterion="lte")

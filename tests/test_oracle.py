@@ -101,3 +101,16 @@ def test_calibration_port_matches_reference_temperatures(name):
         assert abs(calibration_port.nll(labels, logits[e], t) - g[f"{name}_nll_ref"][e]) < 1e-8
         # both sit at the minimiser up to L-BFGS-B's tolerance
         assert abs(t - g[f"{name}_t_opt"][e]) <= 1e-3 * g[f"{name}_t_opt"][e]
+
+
+@pytest.mark.parametrize("name", ["tiny_lte_ramp", "tiny_lte_gate", "base4_lte_ramp"])
+def test_lte_port_matches_reference_golden(name):
+    """Learned-to-exit inference (EE_config["use_lte"]): the port's per-document decision and returned logits
+    against what the unmodified reference produced document by document (tests/golden/make_golden.py)."""
+    g, dims, ee, sd, docs = load_case(name)
+    assert ee.use_lte and "layoutlmv3.encoder.lte_classifier.weight" in sd
+    out = port.forward(sd, dims, ee, docs)
+    r = port.lte_exit(sd, ee, out, float(ee.global_threshold))
+    assert r["exit_layer"].tolist() == g["exit_layer"].tolist()
+    assert len(set(g["exit_layer"].tolist())) >= 2                   # the case exercises several exits
+    assert np.abs(r["logits"].numpy() - g["logits"]).max() < 1e-4
