@@ -415,3 +415,35 @@ def test_lte_needs_its_weights():
     model, g, dims, ee, sd, docs = _engine("tiny_ramp_conf")
     with pytest.raises(RuntimeError, match="lte_classifier"):
         model.infer(**_cuda(docs), criterion="lte")
+
+
+def test_ragged_attention_masks_vs_port():
+    """Masks the tokenizer never emits but the interface allows: holes in the middle, a document with every text token
+    masked (all eight text key tiles are skipped), a single live token, an all-ones mask.  Engine vs the oracle port."""
+    from mmee.model import B200EEForSequenceClassification
+    from oracle import port
+
+    dims = ModelDims.tiny(layers=2)
+    ee = ExitConfig.from_dict(dict(exits=["text_visual_concat", 1, 2], encoder_layer_strategy="ramp",
+                                   inference_strategy="max_confidence"))
+    sd = synth.make_state_dict(dims, ee, seed=9)
+    docs = synth.make_docs(dims, 6, seed=51, pad=False)
+    g = torch.Generator().manual_seed(7)
+    m = docs["attention_mask"].clone()
+    m[0] = (torch.rand(dims.n_text, generator=g) < 0.5).long()       # random holes
+    m[1] = 0                                                          # no text token visible
+    m[2] = 0; m[2, 0] = 1                                             # only <s>
+    m[3, 64:192] = 0                                                  # two whole key tiles masked in the middle
+    m[4, :448] = 0                                                    # only the last text tile is live
+    docs["attention_mask"] = m
+    model = B200EEForSequenceClassification(dims, ee, sd, device=0, max_batch=8)
+    got = model.forward(**_cuda(docs)).exit_logits.cpu().numpy()
+    want = port.forward(sd, dims, ee, docs)["exit_logits"].numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - want).max()
+    print(f"ragged masks: max|logits - port| = {err:.3e}")
+    assert err <= LOGIT_TOL
+    early = model.infer(**_cuda(docs), exit_threshold=0.0701)
+    dense = model.infer(**_cuda(docs), exit_threshold=0.0701, early_exit=False)
+    assert np.array_equal(dense.exits_store, early.exits_store) and torch.equal(dense.logits, early.logits)
+    model.close()
