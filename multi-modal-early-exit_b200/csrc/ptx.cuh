@@ -248,12 +248,16 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // shared-window address of the SAME offset in the pair's CTA 0 (bit 24 of a shared::cluster address = CTA rank in the pair)
 __device__ __forceinline__ uint32_t pair_leader_addr(uint32_t local_addr) { return local_addr & 0xFEFFFFFFu; }
-// arrive on the barrier at this offset in cluster CTA `rank`
+// arrive on the barrier at this offset in cluster CTA `rank`.  Default semantics (.release.cta), as CUTLASS's
+// ClusterBarrier::arrive(cta_id) does: the hand-off it guards is TMEM, ordered by the tcgen05 fences around it.  A
+// .release.cluster arrive compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive, i.e. every epilogue warp would wait
+// for its own global stores to drain before the MMA issuer may reuse the accumulator (ncu: membar was the second
+// largest stall of the QKV GEMM).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_addr, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(local_addr), "r"(rank)
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(local_addr), "r"(rank)
       : "memory");
 }
 // TMA load issued by either CTA of a pair into ITS OWN smem; the transaction bytes are credited to CTA 0's barrier
