@@ -84,6 +84,14 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// (a, b) + (c, c) as one packed-fp32 add (FADD2 on sm_100): half the issue slots of two FADDs
+__device__ __forceinline__ void sub_ref_x2(uint32_t a, uint32_t b, uint64_t nref2, float& ya, float& yb) {
+  uint64_t x, y;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(a), "r"(b));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(y) : "l"(x), "l"(nref2));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(ya), "=f"(yb) : "l"(y));
+}
+
 // Position in this CTA's (item, key tile) sequence; fully masked tiles are skipped.  Every role walks the same
 // sequence so the pipeline counters stay in lock-step.  Passed by value so it lives in registers.
 struct AttCursor {
@@ -487,10 +495,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         {
           // p = exp2(s - ref); the running max rides along (FMNMX on the ALU pipe, MUFU on the XU pipe)
           float m0 = -INFINITY, m1 = -INFINITY;
+          uint64_t nref2;
+          asm("mov.b64 %0, {%1, %1};" : "=l"(nref2) : "f"(-ref));
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float a0 = __uint_as_float(v0[2 * i]) - ref, a1 = __uint_as_float(v0[2 * i + 1]) - ref;
-            const float c0 = __uint_as_float(v1[2 * i]) - ref, c1 = __uint_as_float(v1[2 * i + 1]) - ref;
+            float a0, a1, c0, c1;                       // s - ref, two per packed-fp32 instruction (FADD2)
+            sub_ref_x2(v0[2 * i], v0[2 * i + 1], nref2, a0, a1);
+            sub_ref_x2(v1[2 * i], v1[2 * i + 1], nref2, c0, c1);
             m0 = fmaxf(m0, fmaxf(a0, a1));
             m1 = fmaxf(m1, fmaxf(c0, c1));
             pk[i] = pack_bf16x2(fast_exp2(a0), fast_exp2(a1));

@@ -84,6 +84,38 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return x * phi;
 }
 
+// Two elements at a time: the polynomial runs on the packed-fp32 pipe (FFMA2 on sm_100: one issue slot per pair), so the
+// GELU epilogue of the MLP-up GEMM spends 6 + 2 x 5 instead of 2 x 11 FMA/ALU-pipe slots per pair.  Same arithmetic
+// (round-to-nearest FMAs in the same order) as gelu_erf_fast: bit-identical results.
+__device__ __forceinline__ uint64_t f32x2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ void gelu_erf_fast2(float x0, float x1, float& y0, float& y1) {
+  const float z0 = fminf(fabsf(x0) * 0.70710678118654752f, 4.3f);
+  const float z1 = fminf(fabsf(x1) * 0.70710678118654752f, 4.3f);
+  const uint64_t z = f32x2_pack(z0, z1);
+  uint64_t q = f32x2_pack(2.699725252e-04f, 2.699725252e-04f);
+  q = f32x2_fma(q, z, f32x2_pack(-4.347565948e-03f, -4.347565948e-03f));
+  q = f32x2_fma(q, z, f32x2_pack(3.221176717e-02f, 3.221176717e-02f));
+  q = f32x2_fma(q, z, f32x2_pack(-1.508187237e-01f, -1.508187237e-01f));
+  q = f32x2_fma(q, z, f32x2_pack(-9.177533792e-01f, -9.177533792e-01f));
+  q = f32x2_fma(q, z, f32x2_pack(-1.627978526e+00f, -1.627978526e+00f));
+  q = f32x2_fma(q, z, f32x2_pack(-9.999988147e-01f, -9.999988147e-01f));
+  float q0, q1, h0, h1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(q0), "=f"(q1) : "l"(q));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(q1));
+  y0 = x0 * ((x0 >= 0.f) ? (1.0f - h0) : h0);
+  y1 = x1 * ((x1 >= 0.f) ? (1.0f - h1) : h1);
+}
+
 // Epilogue of one 128-row x BLOCK_N accumulator for one epilogue warp (TMEM lane quarter `quarter`, column half
 // `half` of PARTS column parts): TMEM -> registers -> (+bias, activation) -> per-warp swizzled smem transpose -> coalesced global stores.
 template <int BLOCK_N, int EPI, int PARTS = 2>
@@ -129,8 +161,13 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float g[8];
+              if constexpr (EPI == EPI_GELU_BF16) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) g[j] = (EPI == EPI_GELU_BF16) ? gelu_erf_fast(f[q * 8 + j]) : f[q * 8 + j];
+                for (int j = 0; j < 8; j += 2) gelu_erf_fast2(f[q * 8 + j], f[q * 8 + j + 1], g[j], g[j + 1]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g[j] = f[q * 8 + j];
+              }
               *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
                   make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
                              pack_bf16x2(g[6], g[7]));
