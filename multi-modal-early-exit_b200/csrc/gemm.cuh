@@ -141,16 +141,21 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
         }
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
-        float bv[32];
+        uint64_t bv[16];                            // bias pairs for the packed-fp32 add (FADD2)
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + n) + q);
-          bv[q * 4 + 0] = b4.x; bv[q * 4 + 1] = b4.y; bv[q * 4 + 2] = b4.z; bv[q * 4 + 3] = b4.w;
+          bv[q * 2 + 0] = f32x2_pack(b4.x, b4.y); bv[q * 2 + 1] = f32x2_pack(b4.z, b4.w);
         }
         tmem_ld_wait();
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bv[j];
+        for (int j = 0; j < 16; ++j) {
+          uint64_t x, y;
+          asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(v[2 * j]), "r"(v[2 * j + 1]));
+          asm("add.rn.f32x2 %0, %1, %2;" : "=l"(y) : "l"(x), "l"(bv[j]));
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(f[2 * j]), "=f"(f[2 * j + 1]) : "l"(y));
+        }
 
         if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_QKV) {
           bool transposed_v = false;
