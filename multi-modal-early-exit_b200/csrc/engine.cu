@@ -400,7 +400,7 @@ void finalize(mmee_engine* e) {
     const auto& tx = need(e, p + "encoder.rel_pos_x_bias.weight", {h, d.rel2d_bins});
     const auto& ty = need(e, p + "encoder.rel_pos_y_bias.weight", {h, d.rel2d_bins});
     if (h % 2) throw std::runtime_error("attention heads must be even");
-    const int t2p = h + 2;                       // table row pitch (elements): spreads random rows over the smem banks
+    const int t2p = bias_table_pitch(h);         // table row pitch (elements)
     std::vector<float> T1(static_cast<size_t>(d.rel_bins) * t2p, 0.f);
     for (int b1 = 0; b1 < d.rel_bins; ++b1)
       for (int hh = 0; hh < h; ++hh) T1[static_cast<size_t>(b1) * t2p + hh] = t1[static_cast<size_t>(hh) * d.rel_bins + b1] * qscale;
@@ -644,9 +644,12 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     keymask_kernel<<<B, e->kv_pitch, 0, st>>>(mask, e->maskadd.p, e->tileflag.p, T, S, e->kv_pitch, e->n_kv_tiles, ATT_BKV);
     BiasArgs ba;
     ba.bbox = bbox; ba.vis_bbox = e->vis_bbox.p; ba.t1 = e->bias_t1.p; ba.t2 = e->bias_t2.p;
-    ba.lut1 = e->lut1.p; ba.lut2 = e->lut2.p; ba.lut1_n = static_cast<int>(e->lut1.n); ba.lut2_n = static_cast<int>(e->lut2.n);
+    ba.lut1 = e->lut1.p; ba.lut2 = e->lut2.p; // every |rel| >= max_distance lands in the last bucket (HF:393-414), so the lookup index is clamped there: far keys
+    // (most of them) then read the same table word, which the shared-memory crossbar broadcasts without a conflict
+    ba.lut1_n = std::min(static_cast<int>(e->lut1.n), d.max_rel + 1);
+    ba.lut2_n = std::min(static_cast<int>(e->lut2.n), d.max_rel2d + 1);
     ba.maskadd = e->maskadd.p;
-    ba.bins1 = d.rel_bins; ba.bins2 = d.rel2d_bins; ba.heads = heads; ba.t2_pitch = heads + 2; ba.n_text = T; ba.seq = S; ba.pitch = e->bias_pitch;
+    ba.bins1 = d.rel_bins; ba.bins2 = d.rel2d_bins; ba.heads = heads; ba.t2_pitch = bias_table_pitch(heads); ba.n_text = T; ba.seq = S; ba.pitch = e->bias_pitch;
     ba.kv_pitch = e->kv_pitch; ba.B = B; ba.out = e->BIAS.p;
     const size_t smem = bias_build_smem(ba);
     static bool configured_dev[64] = {};

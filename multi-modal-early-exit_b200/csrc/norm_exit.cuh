@@ -119,6 +119,11 @@ __global__ void __launch_bounds__(256) ln_rows_vec_kernel(const float* __restric
 // Persistent kernel, one CTA per SM: the 2-D table T2[bx][by][head] = fp16((Wx + Wy) * c) (98 KB for base, built at
 // weight load) and T1[b1][head] = W1d * c (fp32) live in shared memory for the whole launch, so each (i, j) pair
 // costs one bucket computation for all heads and one T1 + one T2 lookup per head PAIR.
+// Row pitch (elements) of the two bias tables in shared memory.  heads % 4 == 0: rows are packed (8 B / 16 B aligned)
+// so the kernel reads four heads per LDS.64 / LDS.128; otherwise heads + 2 (an odd number of 32-bit words per fp16 row:
+// random rows spread over all banks for the two-head reads).
+inline int bias_table_pitch(int heads) { return (heads % 4 == 0) ? heads : heads + 2; }
+
 struct BiasArgs {
   const int64_t* bbox;       // [B, n_text, 4]
   const int* vis_bbox;       // [n_vis, 4]
@@ -216,11 +221,48 @@ __global__ void __launch_bounds__(BIAS_THREADS, 1) bias_build_kernel(BiasArgs a)
     }
     __half* out = a.out + ((static_cast<size_t>(doc) * a.heads) * a.seq + i) * a.pitch + j0;
     const size_t head_stride = static_cast<size_t>(a.seq) * a.pitch;
+    // the 1-D buckets are log-spaced: away from the diagonal all 8 keys of a chunk share one, and that table row is
+    // read once per head pair instead of once per key
+    bool same1 = true;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) same1 = same1 && (i1[k] == i1[0]);
+    auto pack = [](float lo, float hi) {
+      __half2 t = __floats2half2_rn(lo, hi);
+      return *reinterpret_cast<uint32_t*>(&t);
+    };
+    if ((a.heads & 3) == 0) {
+      // table rows are 8 B (fp16) / 16 B (fp32) aligned: four heads per shared-memory read
+      for (int h = 0; h < a.heads; h += 4) {
+        float v[4][8];
+        const float4 t1c = *reinterpret_cast<const float4*>(s_t1 + i1[0] + h);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float4 t1 = t1c;
+          if (!same1) t1 = *reinterpret_cast<const float4*>(s_t1 + i1[k] + h);
+          const uint2 raw = *reinterpret_cast<const uint2*>(s_t2 + i2[k] + h);
+          const float2 ta = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+          const float2 tb = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+          v[0][k] = t1.x + ta.x; v[1][k] = t1.y + ta.y; v[2][k] = t1.z + tb.x; v[3][k] = t1.w + tb.y;
+        }
+        if (mbits) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if ((mbits >> k) & 1u) { v[0][k] = BIAS_MASKED; v[1][k] = BIAS_MASKED; v[2][k] = BIAS_MASKED; v[3][k] = BIAS_MASKED; }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(out + (h + q) * head_stride) =
+              make_uint4(pack(v[q][0], v[q][1]), pack(v[q][2], v[q][3]), pack(v[q][4], v[q][5]), pack(v[q][6], v[q][7]));
+      }
+      continue;
+    }
     for (int h = 0; h < a.heads; h += 2) {
       float v0[8], v1[8];
+      float2 t1c = *reinterpret_cast<const float2*>(s_t1 + i1[0] + h);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float2 t1 = *reinterpret_cast<const float2*>(s_t1 + i1[k] + h);
+        float2 t1 = t1c;
+        if (!same1) t1 = *reinterpret_cast<const float2*>(s_t1 + i1[k] + h);
         const float2 t2 = __half22float2(*reinterpret_cast<const __half2*>(s_t2 + i2[k] + h));
         v0[k] = t1.x + t2.x;
         v1[k] = t1.y + t2.y;
@@ -230,10 +272,6 @@ __global__ void __launch_bounds__(BIAS_THREADS, 1) bias_build_kernel(BiasArgs a)
         for (int k = 0; k < 8; ++k)
           if ((mbits >> k) & 1u) { v0[k] = BIAS_MASKED; v1[k] = BIAS_MASKED; }
       }
-      auto pack = [](float lo, float hi) {
-        __half2 t = __floats2half2_rn(lo, hi);
-        return *reinterpret_cast<uint32_t*>(&t);
-      };
       *reinterpret_cast<uint4*>(out + h * head_stride) =
           make_uint4(pack(v0[0], v0[1]), pack(v0[2], v0[3]), pack(v0[4], v0[5]), pack(v0[6], v0[7]));
       *reinterpret_cast<uint4*>(out + (h + 1) * head_stride) =
