@@ -312,17 +312,38 @@ struct HeadWeights {
   int n_out;
 };
 
-__device__ __forceinline__ float warp_dot(const float* __restrict__ w, const float* __restrict__ x, int H, int lane) {
-  float acc = 0.f;
-  for (int k = lane * 4; k < H; k += 128) {
-    const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + k));
-    const float4 x4 = *reinterpret_cast<const float4*>(x + k);
-    acc = fmaf(w4.x, x4.x, acc);
-    acc = fmaf(w4.y, x4.y, acc);
-    acc = fmaf(w4.z, x4.z, acc);
-    acc = fmaf(w4.w, x4.w, acc);
+// out_proj of one row: y[j] = w[j] . x + b[j] for j < n_out (<= 32); lane j returns y[j].  Eight outputs at a time so
+// that eight independent weight loads are in flight per step (one dot after the other left a single L2 round trip
+// outstanding per step, and the 18 dots of a gate-mode exit took most of the kernel's 50 us).
+__device__ __forceinline__ float warp_dots_to_lanes(const float* __restrict__ w, const float* __restrict__ b,
+                                                    const float* __restrict__ x, int H, int n_out, int lane) {
+  float mine = 0.f;
+  for (int j0 = 0; j0 < n_out; j0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int k = lane * 4; k < H; k += 128) {
+      const float4 x4 = *reinterpret_cast<const float4*>(x + k);
+      float4 w4[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        w4[j] = (j0 + j < n_out) ? __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(j0 + j) * H + k))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] = fmaf(w4[j].x, x4.x, acc[j]);
+        acc[j] = fmaf(w4[j].y, x4.y, acc[j]);
+        acc[j] = fmaf(w4[j].z, x4.z, acc[j]);
+        acc[j] = fmaf(w4[j].w, x4.w, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = warp_sum(acc[j]);
+      if (lane == j0 + j) mine = v + __ldg(b + j0 + j);
+    }
   }
-  return warp_sum(acc);
+  return mine;
 }
 
 // ------------------------------------------------------------------ compaction
@@ -620,22 +641,11 @@ __global__ void __launch_bounds__(EXF_THREADS) exit_fused_kernel(ExitFusedArgs a
     if (slot >= n) continue;
     float head_val = 0.f;                 // lane j holds head logit j
     if (a.head_src >= 0 && a.head.out_w) {
-      const float* x = sZ + dd * H;
-      for (int j = 0; j < a.head.n_out; ++j) {
-        const float v = warp_dot(a.head.out_w + static_cast<size_t>(j) * H, x, H, lane) + __ldg(a.head.out_b + j);
-        if (lane == j) head_val = v;
-      }
+      head_val = warp_dots_to_lanes(a.head.out_w, a.head.out_b, sZ + dd * H, H, a.head.n_out, lane);
       if (lane < a.head.n_out) a.slot_head[static_cast<size_t>(slot) * a.head.n_out + lane] = head_val;
     }
     float raw = head_val;                 // class logit of lane k
-    if (a.gate_mode) {
-      raw = 0.f;
-      const float* x = sX + dd * H;
-      for (int j = 0; j < K; ++j) {
-        const float v = warp_dot(a.cls.out_w + static_cast<size_t>(j) * H, x, H, lane) + __ldg(a.cls.out_b + j);
-        if (lane == j) raw = v;
-      }
-    }
+    if (a.gate_mode) raw = warp_dots_to_lanes(a.cls.out_w, a.cls.out_b, sX + dd * H, H, K, lane);
     if (lane < K) a.slot_logits[static_cast<size_t>(slot) * K + lane] = raw;
     const float z = raw * a.inv_temp;
     const float zmax = warp_max(lane < K ? z : -INFINITY);
