@@ -573,10 +573,17 @@ __global__ void __launch_bounds__(EXF_THREADS) exit_fused_kernel(ExitFusedArgs a
     float acc[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    float4 wn[4];                                 // weights of the NEXT k step: its L2 round trip overlaps this step's FMAs
+#pragma unroll
+    for (int f = 0; f < 4; ++f) wn[f] = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(f) * H + lane * 4));
     for (int k = lane * 4; k < H; k += 128) {
       float4 w4[4];
 #pragma unroll
-      for (int f = 0; f < 4; ++f) w4[f] = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(f) * H + k));
+      for (int f = 0; f < 4; ++f) w4[f] = wn[f];
+      if (k + 128 < H) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) wn[f] = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(f) * H + k + 128));
+      }
 #pragma unroll
       for (int d = 0; d < EXF_DOCS; ++d) {
         const float4 z4 = *reinterpret_cast<const float4*>(sZ + d * H + k);
