@@ -209,14 +209,15 @@ __global__ void im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __res
                               int patch, int chans) {
   const int np = img / patch;
   const int kdim = chans * patch * patch;
-  const size_t total = static_cast<size_t>(n_docs) * np * np * kdim / 4;     // 4 pixels (one float4) per thread
-  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (i >= total) return;
-  const size_t e = i * 4;
-  const int k = static_cast<int>(e % kdim);
-  const size_t rowi = e / kdim;
-  const int p = static_cast<int>(rowi % (np * np));
-  const int doc = static_cast<int>(rowi / (np * np));
+  // grid.y = document: all index arithmetic stays 32-bit (the 64-bit divisions of a flat index cost more than the copy)
+  const int doc = blockIdx.y;
+  const int per_doc = np * np * kdim / 4;                                    // float4 groups per document
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per_doc || doc >= n_docs) return;
+  const int el = i * 4;
+  const int k = el % kdim;
+  const int p = el / kdim;
+  const size_t e = static_cast<size_t>(doc) * np * np * kdim + el;
   const int c = k / (patch * patch), kh = (k / patch) % patch, kw = k % patch;
   const int pr = p / np, pc = p % np;
   const float4 v = *reinterpret_cast<const float4*>(

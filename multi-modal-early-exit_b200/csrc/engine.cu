@@ -664,10 +664,9 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     e->launches += 2;
   }
   {
-    const size_t total = static_cast<size_t>(B) * e->n_patch * e->kdim_patch / 4;
+    const int per_doc = e->n_patch * e->kdim_patch / 4;
     if (e->px_async) CUDA_OK(cudaStreamWaitEvent(st, e->px_wait ? e->px_wait : e->px_ready, 0));
-    im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(px, e->PATCH.p, B, d.image, d.patch,
-                                                                              d.channels);
+    im2col_kernel<<<dim3((per_doc + 255) / 256, B), 256, 0, st>>>(px, e->PATCH.p, B, d.image, d.patch, d.channels);
     e->launches++;
     GemmArgs ga{};
     ga.m_dev = nullptr; ga.m_static = B * e->n_patch; ga.N = H; ga.K = e->kdim_patch; ga.bias = e->patch_b.p;
