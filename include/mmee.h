@@ -117,6 +117,10 @@ int64_t mmee_last_launch_count(mmee_engine* e);
 /* Device time of the named stage of the last forward in ms ("total", "embed", "gemm", "attention", "norm", "exit");
  * only recorded when mmee_set_profiling(e, 1) is on (adds event records between stages). */
 int  mmee_set_profiling(mmee_engine* e, int on);
+/* Wait for the forwards enqueued on `cuda_stream` (NULL: the engine's own stream), fold the stage events and turn a
+ * tripped attention guard into an error: what the synchronous entry points do before they return, for callers of the
+ * asynchronous mmee_forward_device. */
+int  mmee_sync(mmee_engine* e, void* cuda_stream);
 /* Synchronise the device and fold the recorded stage events of the last forward into per-stage times. */
 int  mmee_collect_profile(mmee_engine* e);
 double mmee_last_stage_ms(mmee_engine* e, const char* stage);

@@ -1176,6 +1176,17 @@ int mmee_forward_collect(mmee_engine* e, int ticket, const mmee_outputs* out) {
 
 int64_t mmee_last_launch_count(mmee_engine* e) { return e ? e->launches : -1; }
 
+int mmee_sync(mmee_engine* e, void* cuda_stream) {
+  MMEE_TRY
+  if (!e) throw std::runtime_error("null engine");
+  CUDA_OK(cudaSetDevice(e->device));
+  CUDA_OK(cudaStreamSynchronize(cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->stream));
+  collect_profile(e);
+  check_attention_flag(e);
+  return 0;
+  MMEE_CATCH
+}
+
 int mmee_collect_profile(mmee_engine* e) {
   MMEE_TRY
   if (!e) throw std::runtime_error("null engine");

@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = [
     "mmee_finalize_weights", "mmee_forward", "mmee_forward_device", "mmee_last_launch_count",
     "mmee_set_profiling", "mmee_collect_profile", "mmee_last_stage_ms", "mmee_debug_read", "mmee_last_error",
     "mmee_version", "mmee_policy_scan", "mmee_forward_submit", "mmee_forward_collect",
-    "mmee_temperature_fit", "mmee_calibration_stats",
+    "mmee_temperature_fit", "mmee_calibration_stats", "mmee_sync",
 ]
 
 
@@ -102,6 +102,8 @@ def load() -> C.CDLL:
     lib.mmee_calibration_stats.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mmee_calibration_stats.restype = C.c_int
+    lib.mmee_sync.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mmee_sync.restype = C.c_int
     lib.mmee_last_error.argtypes = []
     lib.mmee_last_error.restype = C.c_char_p
     lib.mmee_version.argtypes = []

@@ -177,7 +177,8 @@ class B200EEForSequenceClassification:
 
     # ------------------------------------------------------------------ engine call
     def _run(self, input_ids, attention_mask, bbox, pixel_values, criterion: str, mode: int,
-             thresholds: Sequence[float], temperatures: Optional[Sequence[float]], want_all: bool):
+             thresholds: Sequence[float], temperatures: Optional[Sequence[float]], want_all: bool,
+             blocking: bool = True):
         if pixel_values is None:
             raise ValueError("pixel_values are required (multimodal and image-only paths)")
         if input_ids is None:
@@ -229,8 +230,13 @@ class B200EEForSequenceClassification:
         if on_dev:
             if dev.index is not None and dev.index != self.device_index:
                 raise ValueError("inputs live on a different GPU than the engine")
-            stream = torch.cuda.current_stream(dev).cuda_stream
+            # torch's legacy default stream has handle 0, which the C ABI reads as "the engine's own stream,
+            # synchronous": pass cudaStreamLegacy (1) instead, so the forward is ordered after the torch work that
+            # produced the inputs and stays asynchronous; blocking callers wait explicitly below
+            stream = torch.cuda.current_stream(dev).cuda_stream or 1
             _lib.check(self._lib.mmee_forward_device(*args, C.c_void_p(stream)))
+            if blocking:
+                _lib.check(self._lib.mmee_sync(self._h, C.c_void_p(stream)))
         else:
             _lib.check(self._lib.mmee_forward(*args))
         return dict(logits=logits, exit_index=exit_index, criterion=crit, hist=hist, all_logits=all_l,
@@ -294,7 +300,7 @@ class B200EEForSequenceClassification:
         thr = self.ee.global_threshold if exit_threshold is None else exit_threshold
         crit_name = criterion or self._default_criterion()
         r = self._run(input_ids, attention_mask, bbox, pixel_values, crit_name, 1 if early_exit else 0,
-                      np.atleast_1d(np.asarray(thr, dtype=np.float32)), temperatures, False)
+                      np.atleast_1d(np.asarray(thr, dtype=np.float32)), temperatures, False, blocking=False)
         return {"logits": r["logits"], "exit_index": r["exit_index"], "criterion": r["criterion"], "hist": r["hist"]}
 
     # ------------------------------------------------------------------ pipelined host path

@@ -447,3 +447,25 @@ def test_ragged_attention_masks_vs_port():
     dense = model.infer(**_cuda(docs), exit_threshold=0.0701, early_exit=False)
     assert np.array_equal(dense.exits_store, early.exits_store) and torch.equal(dense.logits, early.logits)
     model.close()
+
+
+def test_infer_device_is_stream_ordered_and_async():
+    """infer_device enqueues on torch's current stream (the legacy default stream included) without waiting: inputs
+    produced by torch kernels just before the call are seen, results feed torch ops just after it, and two calls may be
+    in flight back to back; mmee_sync (through `infer`) is the blocking form."""
+    model, g, dims, ee, sd, docs = _engine("tiny_ramp_conf")
+    dev_docs = _cuda(docs)
+    ref = model.infer(**dev_docs, exit_threshold=0.0701)
+    for stream in (torch.cuda.current_stream(), torch.cuda.Stream()):
+        with torch.cuda.stream(stream):
+            # inputs made by torch kernels on this stream immediately before the call
+            shifted = {k: (v.clone() if v.dtype != torch.float32 else v * 1.0) for k, v in dev_docs.items()}
+            r1 = model.infer_device(**shifted, exit_threshold=0.0701)
+            s1 = r1["logits"].sum()                      # consumer on the same stream, no host sync in between
+            l1, e1 = r1["logits"].clone(), r1["exit_index"].clone()
+            r2 = model.infer_device(**shifted, exit_threshold=0.0701)
+            l2 = r2["logits"].clone()
+        stream.synchronize()
+        assert torch.equal(l1, ref.logits) and torch.equal(l2, ref.logits)
+        assert np.array_equal(e1.cpu().numpy(), ref.exits_store)
+        assert torch.isfinite(s1).item()
