@@ -75,6 +75,7 @@ struct AttArgs {
   long long* trace;            // developer trace (kTrace instantiation only): clock64 stamps of CTA 0
   __nv_bfloat16* ctx;          // [M, H]
   int H, heads, seq;
+  int skip_pad_q;              // skip items whose query rows are all padded text tokens (att_skip_dead)
   int tail_j;                  // key tile that holds only <= 16 real keys and is run as a 16-key tile (-1: none)
 };
 
@@ -97,19 +98,37 @@ __device__ __forceinline__ void sub_ref_x2(uint32_t a, uint32_t b, uint64_t nref
 struct AttCursor {
   int item, ii, j, slot, head, q0, doc, first_j, last_j;
   uint32_t live;               // bit j: tile j is processed (not fully padded)
-  uint2 nmeta;                 // slot_meta of the NEXT item of this CTA, loaded one item ahead (latency hidden)
+  int nitem;                   // the NEXT item this CTA processes (>= total_items: none)
+  uint2 nmeta;                 // its slot_meta, loaded one item ahead (latency hidden)
   bool valid;
 };
 
 __device__ __forceinline__ uint2 att_item_meta(int item, int total_items, int n_qt, const AttArgs& args) {
   return (item < total_items) ? __ldg(args.slot_meta + (item / n_qt) / args.heads) : make_uint2(1u, 0u);
 }
+// Items whose 128 query rows are all padded text tokens are skipped: nobody reads those rows' outputs (their keys are
+// masked for every query, exits read the CLS row, mean-pool exits run before the encoder).  The live-tile bits of
+// slot_meta describe KEY tiles of 64 tokens; query tile qt covers key tiles 2 qt and 2 qt + 1.  Query tile 0 holds the
+// CLS row and is always processed.  Every role walks the same (deterministic) sequence.
+__device__ __forceinline__ int att_skip_dead(int item, uint2& meta, int total_items, int n_qt, int stride,
+                                             const AttArgs& args) {
+  if (!args.skip_pad_q) return item;
+  while (item < total_items) {
+    const int qt = item % n_qt;
+    if (qt == 0 || ((meta.x >> (qt * (ATT_BQ / ATT_BKV))) & ((1u << (ATT_BQ / ATT_BKV)) - 1u)) != 0u) break;
+    item += stride;
+    meta = att_item_meta(item, total_items, n_qt, args);
+  }
+  return item;
+}
+// `item` is live (att_skip_dead) or >= total_items
 __device__ __forceinline__ AttCursor att_enter(int item, int ii, uint2 meta, int total_items, int n_qt, int stride,
                                                const AttArgs& args) {
   AttCursor c;
   c.item = item; c.ii = ii; c.valid = item < total_items;
   c.j = 0; c.slot = 0; c.head = 0; c.q0 = 0; c.doc = 0; c.first_j = 0; c.last_j = 0; c.live = 1u;
   c.nmeta = make_uint2(1u, 0u);
+  c.nitem = total_items;
   if (!c.valid) return c;
   const int qt = item % n_qt;
   const int sh = item / n_qt;
@@ -121,16 +140,21 @@ __device__ __forceinline__ AttCursor att_enter(int item, int ii, uint2 meta, int
   c.first_j = __ffs(c.live) - 1;
   c.last_j = 31 - __clz(c.live);
   c.j = c.first_j;
-  c.nmeta = att_item_meta(item + stride, total_items, n_qt, args);
+  c.nitem = item + stride;
+  c.nmeta = att_item_meta(c.nitem, total_items, n_qt, args);
+  c.nitem = att_skip_dead(c.nitem, c.nmeta, total_items, n_qt, stride, args);
   return c;
 }
 __device__ __forceinline__ AttCursor att_first(int total_items, int n_qt, int stride, const AttArgs& args) {
-  return att_enter(blockIdx.x, 0, att_item_meta(blockIdx.x, total_items, n_qt, args), total_items, n_qt, stride, args);
+  int item = blockIdx.x;
+  uint2 meta = att_item_meta(item, total_items, n_qt, args);
+  item = att_skip_dead(item, meta, total_items, n_qt, stride, args);
+  return att_enter(item, 0, meta, total_items, n_qt, stride, args);
 }
 __device__ __forceinline__ AttCursor att_next(AttCursor c, int total_items, int n_qt, int stride, const AttArgs& args) {
   const uint32_t rest = c.live & ~((2u << c.j) - 1u);
   if (rest) { c.j = __ffs(rest) - 1; return c; }
-  return att_enter(c.item + stride, c.ii + 1, c.nmeta, total_items, n_qt, stride, args);
+  return att_enter(c.nitem, c.ii + 1, c.nmeta, total_items, n_qt, stride, args);
 }
 
 // slot_meta[slot] = {live tiles, doc} from the per-document tile flags (keymask_kernel).
@@ -263,7 +287,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         {
           int pj = c.j + PF_DIST, prow0 = row0, pbrow = brow, pvrow = vrow, phead = c.head;
           if (pj > c.last_j) {                    // runs into the next item of this CTA
-            const int nitem = c.item + stride;
+            const int nitem = c.nitem;
             if (nitem < total_items) {
               const int nsh = nitem / n_qt;
               const int nslot = nsh / args.heads;
@@ -440,7 +464,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       tc_fence_after();
       if (tr) { ATT_TRACE(0, t, 1) }
       // last tile of this item: every S MMA that reads the item's Q has completed -> stage the next item's Q
-      if (c.j == c.last_j && c.item + stride < total_items) q_to_tmem(c.ii + 1);
+      if (c.j == c.last_j && c.nitem < total_items) q_to_tmem(c.ii + 1);
 
       float pmax;
       if (c.j == args.tail_j) {

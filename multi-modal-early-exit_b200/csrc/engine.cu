@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <map>
+#include <numeric>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -155,6 +156,7 @@ struct mmee_engine {
   DevBuf<__nv_bfloat16> X[2], QK, VT, CTX, A1, MID, PATCH;
   DevBuf<__nv_bfloat16> Xlo[2], A1lo;       // low parts of the split-bf16 residual stream (precise_residual)
   bool precise_residual = true;
+  bool skip_pad_q = true;          // attention skips query tiles of padded text tokens; MMEE_SKIP_PAD_Q=0 turns it off
   DevBuf<float> Y, VIS, POOL, POOLV, POOLT, TXT, Z, T0, T1;
   bool has_vision_exit = false, has_text_exit = false;
   DevBuf<__half> BIAS, bias_t2;
@@ -804,7 +806,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     }
     AttArgs aa;
     aa.n_active_dev = e->n_dev.p + stage; aa.slot_meta = e->slot_meta.p; aa.ctx = e->CTX.p; aa.H = H;
-    aa.heads = heads; aa.seq = S; aa.tail_j = e->att_tail_j; aa.err_flag = e->att_err.p; aa.trace = e->att_trace.p;
+    aa.heads = heads; aa.seq = S; aa.tail_j = e->att_tail_j; aa.skip_pad_q = e->skip_pad_q ? 1 : 0; aa.err_flag = e->att_err.p; aa.trace = e->att_trace.p;
     {
       static bool configured_dev[64] = {};
       bool& configured = configured_dev[e->device & 63];   // the attribute is per device
@@ -813,12 +815,16 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
         CUDA_OK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
         configured = true;
       }
+      // items are dealt round-robin (item = CTA + k * grid, query tile = item % n_qt): a grid co-prime with n_qt makes
+      // every CTA cycle through all query tiles, so the skipped (padded) ones are spread evenly over the CTAs
+      const int n_qt = (S + ATT_BQ - 1) / ATT_BQ;
+      int att_grid = e->sms * ATT_CTAS_PER_SM;
+      if (e->skip_pad_q)
+        while (att_grid > 1 && std::gcd(att_grid, n_qt) != 1) --att_grid;
       if (e->trace_on && l == 0)
-        attention_kernel<true><<<e->sms * ATT_CTAS_PER_SM, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(
-            e->t_qk, e->t_k64, e->t_vt, e->t_bias, aa);
+        attention_kernel<true><<<att_grid, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(e->t_qk, e->t_k64, e->t_vt, e->t_bias, aa);
       else
-        attention_kernel<false><<<e->sms * ATT_CTAS_PER_SM, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(
-            e->t_qk, e->t_k64, e->t_vt, e->t_bias, aa);
+        attention_kernel<false><<<att_grid, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(e->t_qk, e->t_k64, e->t_vt, e->t_bias, aa);
       CUDA_OK(cudaGetLastError());
       e->launches++;
     }
@@ -967,6 +973,7 @@ int mmee_create(const mmee_model_desc* desc, int device, int max_batch, mmee_eng
   }
   if (e->kv_pitch > 1024) throw std::runtime_error("sequence too long for keymask_kernel");
   e->sms = prop.multiProcessorCount;
+  if (const char* sq = getenv("MMEE_SKIP_PAD_Q")) e->skip_pad_q = sq[0] != '0';                  // developer A/B switch
   if (const char* pr = getenv("MMEE_PRECISE_RESIDUAL")) e->precise_residual = pr[0] != '0';   // developer A/B switch
   e->bn_h = pick_bn(e->H); e->bn_qkv = pick_bn(e->H) ; e->bn_i = pick_bn(e->I);
   if ((2 * e->H) % e->bn_qkv) e->bn_qkv = 128;
