@@ -330,13 +330,15 @@ void launch_nv(int H, F&& f) {   // dispatch on values-per-lane for the warp-per
 
 // LayerNorm of the active rows (fp32 Y -> bf16 X [+ low part]); vectorised when H is a multiple of 128
 void launch_ln(mmee_engine* e, const float* Y, __nv_bfloat16* X, __nv_bfloat16* Xlo, const float* w, const float* b,
-               int B, const int* m_dev, const int* slot_src, cudaStream_t st) {
+               int B, const int* m_dev, const int* slot_src, cudaStream_t st, const int* slot_doc = nullptr) {
   const int H = e->H, S = e->S;
+  if (!e->skip_pad_q) slot_doc = nullptr;          // one developer switch (MMEE_SKIP_PAD_Q) for every padded-row skip
   const float eps = e->d.ln_eps;
   const int rows = B * S;
   auto vec = [&](auto nv4) {
     const int blocks = std::min((rows + 7) / 8, e->sms * 16);      // grid-stride over rows, 8 warps per block
-    ln_rows_vec_kernel<decltype(nv4)::value><<<blocks, 256, 0, st>>>(Y, X, Xlo, w, b, eps, H, S, m_dev, slot_src);
+    ln_rows_vec_kernel<decltype(nv4)::value><<<blocks, 256, 0, st>>>(Y, X, Xlo, w, b, eps, H, S, m_dev, slot_src, slot_doc,
+                                                                       e->maskadd.p, e->kv_pitch, e->T);
   };
   switch (H % 128 == 0 ? H / 128 : 0) {
     case 1: vec(std::integral_constant<int, 1>{}); break;
@@ -835,7 +837,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     ga.resid_lo = x_lo_valid ? e->Xlo[cur].p : nullptr;
     launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_ctx, w.t_wo, ga, st);
     mark(e, "gemm", st);
-    launch_ln(e, e->Y.p, e->A1.p, e->A1lo.p, w.ln1_w.p, w.ln1_b.p, B, mdev, nullptr, st);
+    launch_ln(e, e->Y.p, e->A1.p, e->A1lo.p, w.ln1_w.p, w.ln1_b.p, B, mdev, nullptr, st, e->slot_doc[sd].p);
     e->launches++;
     mark(e, "norm", st);
 
@@ -857,7 +859,8 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
       mark(e, "exit", st);
     }
     if (!last) {
-      launch_ln(e, e->Y.p, e->X[cur ^ 1].p, e->Xlo[cur ^ 1].p, w.ln2_w.p, w.ln2_b.p, B, e->m_dev.p + stage, ln_src, st);
+      launch_ln(e, e->Y.p, e->X[cur ^ 1].p, e->Xlo[cur ^ 1].p, w.ln2_w.p, w.ln2_b.p, B, e->m_dev.p + stage, ln_src, st,
+                e->slot_doc[sd].p);
       e->launches++;
       cur ^= 1;
       x_lo_valid = e->precise_residual;

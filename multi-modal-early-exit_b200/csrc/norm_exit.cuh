@@ -60,7 +60,9 @@ __global__ void __launch_bounds__(256) ln_rows_vec_kernel(const float* __restric
                                                           __nv_bfloat16* __restrict__ Xlo, const float* __restrict__ w,
                                                           const float* __restrict__ b, float eps, int H, int seq,
                                                           const int* __restrict__ m_dst_dev,
-                                                          const int* __restrict__ slot_src) {
+                                                          const int* __restrict__ slot_src,
+                                                          const int* __restrict__ slot_doc,
+                                                          const float* __restrict__ maskadd, int kv_pitch, int n_text) {
   const int lane = threadIdx.x & 31;
   const int M = *m_dst_dev;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
@@ -72,10 +74,11 @@ __global__ void __launch_bounds__(256) ln_rows_vec_kernel(const float* __restric
   }
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps_total) {
     size_t src_row = row;
-    if (slot_src) {
-      const int s = row / seq;
-      src_row = static_cast<size_t>(slot_src[s]) * seq + (row - s * seq);
-    }
+    const int sl = row / seq, t = row - sl * seq;
+    // rows of padded text tokens are not normalised (nor moved): nothing reads them — their keys are masked, exits read
+    // the CLS row (t = 0, always kept) — and the destination keeps whatever finite values it held
+    if (slot_doc && t > 0 && t < n_text && __ldg(maskadd + static_cast<size_t>(__ldg(slot_doc + sl)) * kv_pitch + t) < 0.f) continue;
+    if (slot_src) src_row = static_cast<size_t>(slot_src[sl]) * seq + t;
     const float* y = Y + src_row * H;
     float4 v[NV4];
 #pragma unroll
