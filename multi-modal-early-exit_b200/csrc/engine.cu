@@ -63,8 +63,9 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
   if (i < n) dst[i] = __float2bfloat16_rn(src[i] * scale);
 }
 __global__ void init_forward_kernel(int* slot_doc, int* out_exit, int* n_dev, int* m_dev, unsigned long long* hist,
-                                    int B, int seq, int n_hist) {
+                                    int B, int seq, int n_hist, int* any_pad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *any_pad = 0;
   if (i < B) { slot_doc[i] = i; out_exit[i] = -1; }
   if (i < n_hist) hist[i] = 0ull;
   if (i == 0) { n_dev[0] = B; m_dev[0] = B * seq; }
@@ -120,6 +121,7 @@ struct mmee_engine {
   int H, L, heads, I, T, P, S, K, n_vis, n_patch, kdim_patch;
   int kv_pitch = 768, bias_pitch = 768;
   int att_tail_j = -1, bias_width = 768;
+  DevBuf<int> any_pad;             // [1] set by keymask_kernel when some text token of the batch is padded
   DevBuf<float> lte_w, slot_lte;   // learned-to-exit scorer [H] (optional) and its per-slot scores
   float lte_b = 0.f;
   int m_max = 0;            // padded row capacity of activation buffers
@@ -338,7 +340,7 @@ void launch_ln(mmee_engine* e, const float* Y, __nv_bfloat16* X, __nv_bfloat16* 
   auto vec = [&](auto nv4) {
     const int blocks = std::min((rows + 7) / 8, e->sms * 16);      // grid-stride over rows, 8 warps per block
     ln_rows_vec_kernel<decltype(nv4)::value><<<blocks, 256, 0, st>>>(Y, X, Xlo, w, b, eps, H, S, m_dev, slot_src, slot_doc,
-                                                                       e->maskadd.p, e->kv_pitch, e->T);
+                                                                       e->maskadd.p, e->kv_pitch, e->T, e->any_pad.p);
   };
   switch (H % 128 == 0 ? H / 128 : 0) {
     case 1: vec(std::integral_constant<int, 1>{}); break;
@@ -573,6 +575,7 @@ void allocate(mmee_engine* e) {
   e->all_crit.alloc(static_cast<size_t>(E1) * B);
   e->hist.alloc(E1, true);
   e->slot_lte.alloc(B, true);
+  e->any_pad.alloc(1, true);
   e->hist64.alloc(E1, true);
 }
 
@@ -597,7 +600,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   mark(e, "start", st);
 
   init_forward_kernel<<<(std::max(B, E1) + 255) / 256, 256, 0, st>>>(e->slot_doc[0].p, e->out_exit.p, e->n_dev.p,
-                                                                       e->m_dev.p, e->hist.p, B, S, E1);
+                                                                       e->m_dev.p, e->hist.p, B, S, E1, e->any_pad.p);
   e->launches++;
   const bool want_all = out->all_exit_logits || out->all_head_logits || out->all_criteria;
   if (want_all) {
@@ -645,7 +648,8 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   }
   // pixel-independent work first: on the host path the pixel upload (96 % of the input bytes) overlaps it
   {
-    keymask_kernel<<<B, e->kv_pitch, 0, st>>>(mask, e->maskadd.p, e->tileflag.p, T, S, e->kv_pitch, e->n_kv_tiles, ATT_BKV);
+    keymask_kernel<<<B, e->kv_pitch, 0, st>>>(mask, e->maskadd.p, e->tileflag.p, T, S, e->kv_pitch, e->n_kv_tiles, ATT_BKV,
+                                           e->any_pad.p);
     BiasArgs ba;
     ba.bbox = bbox; ba.vis_bbox = e->vis_bbox.p; ba.t1 = e->bias_t1.p; ba.t2 = e->bias_t2.p;
     ba.lut1 = e->lut1.p; ba.lut2 = e->lut2.p; // every |rel| >= max_distance lands in the last bucket (HF:393-414), so the lookup index is clamped there: far keys

@@ -62,9 +62,11 @@ __global__ void __launch_bounds__(256) ln_rows_vec_kernel(const float* __restric
                                                           const int* __restrict__ m_dst_dev,
                                                           const int* __restrict__ slot_src,
                                                           const int* __restrict__ slot_doc,
-                                                          const float* __restrict__ maskadd, int kv_pitch, int n_text) {
+                                                          const float* __restrict__ maskadd, int kv_pitch, int n_text,
+                                                          const int* __restrict__ any_pad) {
   const int lane = threadIdx.x & 31;
   const int M = *m_dst_dev;
+  if (slot_doc && *any_pad == 0) slot_doc = nullptr;     // unpadded batch: no per-row mask lookups in front of the loads
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   float4 w4[NV4], b4[NV4];
 #pragma unroll
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(BIAS_THREADS, 1) bias_build_kernel(BiasArgs a)
 // (doc, key tile of `tile_keys` keys) flag: 0 = no masked key, 1 = some, 2 = every valid key masked (the tile is skipped).
 // grid B, block = kv_pitch threads (<= 1024)
 __global__ void keymask_kernel(const int64_t* __restrict__ mask, float* __restrict__ maskadd, int* __restrict__ tileflag,
-                               int n_text, int seq, int kv_pitch, int n_tiles, int tile_keys) {
+                               int n_text, int seq, int kv_pitch, int n_tiles, int tile_keys, int* __restrict__ any_pad) {
   __shared__ int s_masked[32], s_valid[32];
   const int doc = blockIdx.x;
   const int j = threadIdx.x;
@@ -303,7 +305,10 @@ __global__ void keymask_kernel(const int64_t* __restrict__ mask, float* __restri
     }
   }
   __syncthreads();
-  if (j < n_tiles) tileflag[doc * n_tiles + j] = (s_masked[j] == 0) ? 0 : (s_masked[j] == s_valid[j] ? 2 : 1);
+  if (j < n_tiles) {
+    tileflag[doc * n_tiles + j] = (s_masked[j] == 0) ? 0 : (s_masked[j] == s_valid[j] ? 2 : 1);
+    if (s_masked[j] != 0) *any_pad = 1;          // batch-wide: some text token is padded (zeroed by init_forward_kernel)
+  }
 }
 
 // ------------------------------------------------------------------ exit head
