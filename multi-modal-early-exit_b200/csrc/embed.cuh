@@ -258,6 +258,43 @@ __global__ void visual_ln_kernel(float* __restrict__ VIS, EmbedWeights W, __nv_b
   }
 }
 
+// Vectorised variant for H = 128 * NV4: float4 loads, 8 B stores, grid-stride over the visual tokens.
+template <int NV4>
+__global__ void __launch_bounds__(256) visual_ln_vec_kernel(float* __restrict__ VIS, EmbedWeights W,
+                                                            __nv_bfloat16* __restrict__ X, int write_pre, int n_docs,
+                                                            int n_vis, int n_text, int seq, int H, float eps_vis,
+                                                            float eps) {
+  const int lane = threadIdx.x & 31;
+  const int total = n_docs * n_vis;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tok < total; tok += warps_total) {
+    const int doc = tok / n_vis, p = tok - doc * n_vis;
+    float* row = VIS + (static_cast<size_t>(doc) * n_vis + p) * H;
+    float4 v[NV4];
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      if (p == 0) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(W.cls_token + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(W.pos_embed + c));
+        v[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      } else {
+        v[i] = *reinterpret_cast<const float4*>(row + c);
+      }
+    }
+    warp_layernorm4<NV4>(v, H, W.ln_vis_w, W.ln_vis_b, eps_vis, lane);
+    if (write_pre) {                                    // visual embeddings after `norm` (vision_avg exit), in place
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) *reinterpret_cast<float4*>(row + 4 * (lane + 32 * i)) = v[i];
+    }
+    warp_layernorm4<NV4>(v, H, W.ln_model_w, W.ln_model_b, eps, lane);
+    __nv_bfloat16* out = X + (static_cast<size_t>(doc) * seq + n_text + p) * H;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i)
+      *reinterpret_cast<uint2*>(out + 4 * (lane + 32 * i)) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+  }
+}
+
 // pool[doc][c] = mean_t X[doc*seq + t][c]; grid (ceil(H/32), n_docs), block 256 (8 warps stride the tokens)
 __global__ void meanpool_kernel(const __nv_bfloat16* __restrict__ X, float* __restrict__ pool, int seq, int H) {
   __shared__ float part[8][33];

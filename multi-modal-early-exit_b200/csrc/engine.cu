@@ -680,10 +680,23 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     ga.m_dev = nullptr; ga.m_static = B * e->n_patch; ga.N = H; ga.K = e->kdim_patch; ga.bias = e->patch_b.p;
     ga.out = e->VIS.p; ga.ld_out = H; ga.pos = e->pos_embed.p; ga.n_patch = e->n_patch; ga.n_vis = e->n_vis;
     launch_gemm<EPI_PATCH>(e, e->bn_h, e->t_patch, e->t_patch_w, ga, st);
-    launch_nv(H, [&](auto nv) {
-      visual_ln_kernel<decltype(nv)::value><<<(B * e->n_vis + 7) / 8, 256, 0, st>>>(
+    auto vln = [&](auto nv4) {
+      const int blocks = std::min((B * e->n_vis + 7) / 8, e->sms * 16);
+      visual_ln_vec_kernel<decltype(nv4)::value><<<blocks, 256, 0, st>>>(
           e->VIS.p, ew, e->X[0].p, e->has_vision_exit ? 1 : 0, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps);
-    });
+    };
+    switch (H % 128 == 0 ? H / 128 : 0) {
+      case 1: vln(std::integral_constant<int, 1>{}); break;
+      case 2: vln(std::integral_constant<int, 2>{}); break;
+      case 4: vln(std::integral_constant<int, 4>{}); break;
+      case 6: vln(std::integral_constant<int, 6>{}); break;
+      case 8: vln(std::integral_constant<int, 8>{}); break;
+      default:
+        launch_nv(H, [&](auto nv) {
+          visual_ln_kernel<decltype(nv)::value><<<(B * e->n_vis + 7) / 8, 256, 0, st>>>(
+              e->VIS.p, ew, e->X[0].p, e->has_vision_exit ? 1 : 0, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps);
+        });
+    }
     e->launches++;
   }
   mark(e, "embed", st);
