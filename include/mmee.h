@@ -44,7 +44,18 @@ typedef struct {
                                               (embedding-level, see above), 1..layers = after that encoder layer */
   int head_kind;                           /* 0 ramp (EarlyExitHead.RAMP), 1 gate (EarlyExitHead.GATE) */
   int head_layers;                         /* exit_head_num_layers: 1 | 2 */
+  int compute_dtype;                       /* MMEE_DTYPE_BF16 (default) | MMEE_DTYPE_FP32, see below */
 } mmee_model_desc;
+
+/* Arithmetic of the dense contractions (QKV / output / MLP projections, patch embedding, attention).  Everything else
+ * (embedding sums, LayerNorm, GELU, softmax, exit heads, criteria) is fp32 in both modes.
+ *   MMEE_DTYPE_BF16  bf16 tensor-core operands, fp32 accumulation: logits within 1e-2 of the reference's fp32 forward
+ *   MMEE_DTYPE_FP32  fp32-parity mode (the reference computes in fp32, EE/utils.py:160-164): every operand is a
+ *                    split-bf16 pair (hi + lo = 16 mantissa bits) and each product runs as hi*hi + lo*hi + hi*lo on
+ *                    the same tensor cores with fp32 accumulation: logits within 1e-4 (measured ~5e-6), ~3x the
+ *                    tensor work of the bf16 mode. */
+#define MMEE_DTYPE_BF16 0
+#define MMEE_DTYPE_FP32 1
 
 /* Exit policy: EarlyExitInference criterion + sign (EE/models/EE_modules.py:116-146), per-exit thresholds
  * (EE/policy.py:17, :71-79) and per-exit temperatures (EE/generic_scaling.py:54-61, EE/eval.py:312-327). */
@@ -129,18 +140,38 @@ double mmee_last_stage_ms(mmee_engine* e, const char* stage);
 int64_t mmee_debug_read(mmee_engine* e, const char* name, void* host_dst, int64_t capacity_bytes);
 
 /* Post-hoc exit policy over stored per-exit logits: the device replacement of the per-sample double loop of
- * Policy.max_confidence_global_thresholding_policy / accuracy_calibration_heuristic (EE/policy.py:12-53, 55-111)
- * and of the threshold sweeps that re-run it once per threshold (EE/eval.py:227-274 full_test_iteration,
- * EE/thresh.py:106-132).  All buffers in HOST memory; fp64 like the reference (scipy softmax on the f64 store).
+ * Policy.max_confidence_global_thresholding_policy / accuracy_calibration_heuristic (EE/policy.py:12-53, 55-111),
+ * of the threshold sweeps that re-run it once per threshold (EE/eval.py:227-274 full_test_iteration,
+ * EE/thresh.py:106-132) and of the per-exit threshold-vector ("mixture") sweeps opt0_2D / check_2D_threshold
+ * (EE/thresh.py:184-215, EE/large_scale.py:42-84: 1.5 M mixtures over the whole test set).
+ *
+ * A policy store holds the criteria of one logits store on the device (fp64 like the reference: scipy softmax on the
+ * f64 store, EE/utils.py:160-164); every scan after that moves only thresholds in and counts out.
  *   logits       f64 [E1, N, K]   per-exit logits incl. the final classifier (EE/utils.py:160-193 `logits_store`)
  *   temperatures f64 [E1] or NULL logits[e] / T_e before the criterion (EE/generic_scaling.py:54-61)
- *   criterion    0 max softmax, exit iff > thr (EE/policy.py:33) ; 1 entropy, exit iff < thr (EE_modules.py:142)
- *   thresholds   f64 [n_thr, E1]  one row per sweep point (a global threshold = a constant row; the last column
- *                                 is ignored: the final classifier always fires, EE/policy.py:40-45)
+ *   criterion    0 max softmax ; 1 entropy (EE/models/EE_modules.py:149-160)
  *   labels       i64 [N] or NULL  enables correct_out
- * Outputs: exits_out i32 [n_thr, N] (`exits_store`), crit_out f64 [E1, N] (nullable), hist_out i64 [n_thr, E1]
- * (nullable; exit_distribution * N), correct_out i64 [n_thr] (nullable; samples whose arg-max class at the exit
- * taken equals the label). */
+ * All buffers in HOST memory. */
+typedef struct mmee_policy_store mmee_policy_store;
+int  mmee_policy_store_create(int device, int n_exits_plus1, int64_t n_samples, int n_labels, const double* logits,
+                              const double* temperatures, int criterion, const int64_t* labels,
+                              mmee_policy_store** out);
+void mmee_policy_store_destroy(mmee_policy_store* store);
+/* crit_out f64 [E1, N]: the criterion of every (exit, sample) as held on the device. */
+int  mmee_policy_store_criteria(mmee_policy_store* store, double* crit_out);
+/* One scan = n_thr sweep points (any number: 1 for Policy, ~50 for full_test_iteration, 1.5 M for large_scale.py).
+ *   thresholds   f64 [n_thr, E1]  one row per sweep point (a global threshold = a constant row)
+ *   mode 0       EE/policy.py:28-45: exit iff crit > thr (entropy: crit < thr), strict; the last column is ignored:
+ *                the final classifier always fires (:40-45)
+ *   mode 1       check_2D_threshold (EE/thresh.py:184-185): (CSF >= thr[:, None]).argmax(0) with CSF = max softmax, or
+ *                the NEGATED entropy (EE/large_scale.py:15); every column is tested, a sample that fires nowhere gets
+ *                exit 0
+ * Outputs, each nullable: exits_out i32 [n_thr, N] (`exits_store`; leave NULL for large sweeps: nothing of that size
+ * is then allocated anywhere), hist_out i64 [n_thr, E1] (exit_distribution * N), correct_out i64 [n_thr] (samples
+ * whose arg-max class at the exit taken equals the label; needs labels). */
+int  mmee_policy_store_scan(mmee_policy_store* store, const double* thresholds, int64_t n_thr, int mode,
+                            int32_t* exits_out, int64_t* hist_out, int64_t* correct_out);
+/* One-shot form (store created, scanned in mode 0 and dropped): crit_out f64 [E1, N] nullable. */
 int  mmee_policy_scan(int device, int n_exits_plus1, int64_t n_samples, int n_labels, const double* logits,
                       const double* temperatures, int criterion, const double* thresholds, int n_thr,
                       const int64_t* labels, int32_t* exits_out, double* crit_out, int64_t* hist_out,

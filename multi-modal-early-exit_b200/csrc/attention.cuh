@@ -46,26 +46,38 @@ constexpr int ATT_MAX_KV_TILES = 16;
 constexpr float ATT_LAZY = 8.0f;   // raise the row reference only when a score exceeds it by more than 2^8
 constexpr float ATT_JUMP = 40.0f;  // ... and immediately (P recomputed) when it exceeds it by more than 2^40
 
-struct AttSmem {
-  static constexpr int Q_BYTES = ATT_BQ * ATT_D * 2;           // 16 KB
-  static constexpr int K_BYTES = ATT_BKV * ATT_D * 2;          //  8 KB
-  static constexpr int V_BYTES = ATT_DV * ATT_BKV * 2;         // 10 KB: [80 rows x 64 keys] bf16, SW128
-  static constexpr int B_BYTES = ATT_BQ * ATT_BKV * 2;         // 16 KB  fp16 [128 x 64], SW128 (A operand of the bias MMA)
-  static constexpr int KB_STAGE = K_BYTES + B_BYTES;           // 24 KB
+// kSplit (fp32 engine mode): Q, K, V^T, the bias and P are split-bf16 / split-fp16 pairs (hi + lo); S, O and the
+// softmax stay fp32, so each tile runs Q_hi K_hi + Q_lo K_hi + Q_hi K_lo (+ B_hi I + B_lo I) and
+// P_hi [V_hi|1] + P_lo [V_hi|1] + P_hi V_lo.  One CTA per SM (twice the operand tiles, 512 TMEM columns).
+template <bool kSplit>
+struct AttSmemT {
+  static constexpr int NP = kSplit ? 2 : 1;                    // operand parts
+  static constexpr int Q_BYTES = ATT_BQ * ATT_D * 2;           // 16 KB per part
+  static constexpr int K_BYTES = ATT_BKV * ATT_D * 2;          //  8 KB per part
+  static constexpr int V_BYTES = ATT_DV * ATT_BKV * 2;         // 10 KB: [80 rows x 64 keys] bf16, SW128 (hi part, with the ones row)
+  static constexpr int VLO_BYTES = kSplit ? ATT_D * ATT_BKV * 2 : 0;   //  8 KB: [64 rows x 64 keys] low part
+  static constexpr int B_BYTES = ATT_BQ * ATT_BKV * 2;         // 16 KB  fp16 [128 x 64] per part, SW128 (A operand of the bias MMA)
+  static constexpr int Q_STAGE = NP * Q_BYTES;
+  static constexpr int KB_STAGE = NP * (K_BYTES + B_BYTES);    // 24 KB (48 KB split): K parts, then bias parts
+  static constexpr int V_STAGE = V_BYTES + VLO_BYTES;
   static constexpr int I_BYTES = ATT_BKV * ATT_BKV * 2;        //  8 KB  fp16 identity [64 x 64], SW128 (B operand)
   static constexpr int Q_OFF = 0;                              // 2 Q buffers
-  static constexpr int KB_OFF = Q_OFF + 2 * Q_BYTES;
+  static constexpr int KB_OFF = Q_OFF + 2 * Q_STAGE;
   static constexpr int V_OFF = KB_OFF + ATT_KB_STAGES * KB_STAGE;
-  static constexpr int I_OFF = V_OFF + ATT_V_STAGES * V_BYTES;
+  static constexpr int I_OFF = V_OFF + ATT_V_STAGES * V_STAGE;
   static constexpr int BAR_OFF = I_OFF + I_BYTES;
   // q_full[2] q_empty[2] kb_full[KB] kb_empty[KB] v_full[V] v_empty[V] s_full[2] p_full[2] o_full[1] qt_full[1]
   static constexpr int N_BARS = 2 + 2 + 2 * ATT_KB_STAGES + 2 * ATT_V_STAGES + 2 + 2 + 1 + 1;
   static constexpr int TOTAL = BAR_OFF + N_BARS * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL;                      // the dynamic smem base itself is 1024 B aligned
+  static constexpr uint32_t TMEM_COLS = kSplit ? 512 : 256;
 };
+using AttSmem = AttSmemT<false>;
 static_assert(AttSmem::DYN_BYTES <= 115712, "two attention CTAs must fit one SM");
+static_assert(AttSmemT<true>::DYN_BYTES <= 232448, "split attention CTA must fit one SM");
 static_assert(AttSmem::KB_STAGE % 1024 == 0 && AttSmem::K_BYTES % 1024 == 0 && AttSmem::V_BYTES % 1024 == 0 &&
-                  AttSmem::V_OFF % 1024 == 0 && AttSmem::I_OFF % 1024 == 0,
+                  AttSmem::V_OFF % 1024 == 0 && AttSmem::I_OFF % 1024 == 0 && AttSmemT<true>::V_STAGE % 1024 == 0 &&
+                  AttSmemT<true>::V_OFF % 1024 == 0 && AttSmemT<true>::I_OFF % 1024 == 0,
               "swizzled tiles need 1024 B alignment");
 
 struct AttArgs {
@@ -74,6 +86,7 @@ struct AttArgs {
   int* err_flag;               // guard: set to 1 if a deferred rescale factor underflowed (unreachable, see ATT_JUMP)
   long long* trace;            // developer trace (kTrace instantiation only): clock64 stamps of CTA 0
   __nv_bfloat16* ctx;          // [M, H]
+  __nv_bfloat16* ctx_lo;       // kSplit: low part of ctx
   int H, heads, seq;
   int skip_pad_q;              // skip items whose query rows are all padded text tokens (att_skip_dead)
   int tail_j;                  // key tile that holds only <= 16 real keys and is run as a 16-key tile (-1: none)
@@ -174,11 +187,19 @@ __global__ void slot_meta_kernel(const int* __restrict__ slot_doc, const int* __
 // tmap_k   : bf16 [M_max, 2H]                    box [ 64 rows x 64 cols]   (SW128)
 // tmap_vt  : bf16 [docs*heads*64, kv_pitch]       box [ 64 rows x 64 cols]   (SW128)
 // tmap_bias: fp16 [docs*heads*seq, bias_pitch]    box [128 rows x 64 cols]   (SW128)
-template <bool kTrace>
-__global__ void __launch_bounds__(ATT_THREADS, ATT_CTAS_PER_SM)
-attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                 const __grid_constant__ CUtensorMap tmap_vt, const __grid_constant__ CUtensorMap tmap_bias,
-                 const AttArgs args) {
+// kSplit: the *_lo maps describe the low parts (same shapes); otherwise they are unused copies
+struct AttMaps {
+  CUtensorMap q, k, vt, bias, q_lo, k_lo, vt_lo, bias_lo;
+};
+
+template <bool kTrace, bool kSplit = false>
+__global__ void __launch_bounds__(ATT_THREADS, kSplit ? 1 : ATT_CTAS_PER_SM)
+attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
+  using SMEM = AttSmemT<kSplit>;
+  const CUtensorMap& tmap_q = maps.q;
+  const CUtensorMap& tmap_k = maps.k;
+  const CUtensorMap& tmap_vt = maps.vt;
+  const CUtensorMap& tmap_bias = maps.bias;
   const int S = args.seq;
   const int n_kv = (S + ATT_BKV - 1) / ATT_BKV;
   const int n_qt = (S + ATT_BQ - 1) / ATT_BQ;
@@ -190,7 +211,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t sb = smem_u32(smem_raw);
   uint8_t* smem = smem_raw;
   if (sb & 1023u) __trap();                       // swizzled TMA / UMMA tiles need 1024 B alignment
-  const uint32_t bar0 = sb + AttSmem::BAR_OFF;
+  const uint32_t bar0 = sb + SMEM::BAR_OFF;
   const uint32_t q_full = bar0;                                  // [2]
   const uint32_t q_empty = q_full + 2 * 8;                       // [2]
   const uint32_t kb_full = q_empty + 2 * 8;                      // [KB_STAGES]
@@ -201,8 +222,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t p_full = s_full + 2 * 8;                        // [2]
   const uint32_t o_full = p_full + 2 * 8;                        // [1]  every P V commit
   const uint32_t qt_full = o_full + 8;                           // [1]  once per item: Q has been copied into TMEM
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttSmem::BAR_OFF);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + AttSmem::N_BARS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM::BAR_OFF);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + SMEM::N_BARS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -217,6 +238,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_vt);
     tma_prefetch_desc(&tmap_bias);
+    if constexpr (kSplit) {
+      tma_prefetch_desc(&maps.q_lo); tma_prefetch_desc(&maps.k_lo); tma_prefetch_desc(&maps.vt_lo); tma_prefetch_desc(&maps.bias_lo);
+    }
     uint64_t* b = bars;
     for (int i = 0; i < 2; ++i) mbar_init(b++, 1);                  // q_full
     for (int i = 0; i < 2; ++i) mbar_init(b++, ATT_SM_WARPS);       // q_empty: the softmax warps copied Q to TMEM
@@ -231,7 +255,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   // constant rows 64..79 of every V^T tile: row 64 = 1.0 (PV then also yields the row sum of P), rest 0
   for (int i = threadIdx.x; i < ATT_V_STAGES * 128; i += blockDim.x) {
     const int stg = i >> 7, chunk = i & 127;                   // 128 x 16 B chunks = rows 64..79
-    uint8_t* base = smem + AttSmem::V_OFF + stg * AttSmem::V_BYTES + ATT_D * 128;
+    uint8_t* base = smem + SMEM::V_OFF + stg * SMEM::V_STAGE + ATT_D * 128;
     const uint32_t val = (chunk < 8) ? 0x3F803F80u : 0u;       // first 8 chunks = row 64
     *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(val, val, val, val);
   }
@@ -240,10 +264,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int n = i >> 3, cchunk = i & 7;
     uint32_t w[4] = {0u, 0u, 0u, 0u};
     if ((n >> 3) == cchunk) w[(n & 7) >> 1] = (n & 1) ? 0x3C000000u : 0x00003C00u;   // fp16 1.0 at element n
-    *reinterpret_cast<uint4*>(smem + AttSmem::I_OFF + n * 128 + ((cchunk ^ (n & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(smem + SMEM::I_OFF + n * 128 + ((cchunk ^ (n & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
   fence_proxy_async_smem();
-  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 1) tmem_alloc<SMEM::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -251,6 +275,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t tmem_S = tmem_base;            // 2 x 64 columns; P_t (bf16 pairs) overwrites columns [0,32) of S_t
   const uint32_t tmem_O = tmem_base + 128;      // 80 columns: 64 dims + row sum + padding
   const uint32_t tmem_Q = tmem_base + 208;      // 32 columns: the item's Q tile (64 bf16 per row) as the TMEM A operand
+  const uint32_t tmem_Qlo = tmem_base + 240;    // kSplit: 32 columns, low part of Q
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -267,8 +292,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           const int qb = c.ii & 1;
           ATT_TRACE(2, t, 2)
           mbar_wait(q_empty + qb * 8, ((c.ii >> 1) & 1) ^ 1);
-          mbar_expect_tx(q_full + qb * 8, AttSmem::Q_BYTES);
-          tma_load_2d(sb + AttSmem::Q_OFF + qb * AttSmem::Q_BYTES, &tmap_q, q_full + qb * 8, c.head * ATT_D, row0 + c.q0);
+          mbar_expect_tx(q_full + qb * 8, SMEM::Q_STAGE);
+          tma_load_2d(sb + SMEM::Q_OFF + qb * SMEM::Q_STAGE, &tmap_q, q_full + qb * 8, c.head * ATT_D, row0 + c.q0);
+          if constexpr (kSplit)
+            tma_load_2d(sb + SMEM::Q_OFF + qb * SMEM::Q_STAGE + SMEM::Q_BYTES, &maps.q_lo, q_full + qb * 8, c.head * ATT_D, row0 + c.q0);
         }
         const int kv0 = c.j * ATT_BKV;
         const int brow = (c.doc * args.heads + c.head) * S + c.q0;
@@ -278,10 +305,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         ATT_TRACE(2, t, 0)
         mbar_wait(kb_empty + st * 8, ((t / ATT_KB_STAGES) & 1) ^ 1);
         ATT_TRACE(2, t, 1)
-        const uint32_t sk = sb + AttSmem::KB_OFF + st * AttSmem::KB_STAGE;
-        mbar_expect_tx(kb_full + st * 8, AttSmem::KB_STAGE);
+        const uint32_t sk = sb + SMEM::KB_OFF + st * SMEM::KB_STAGE;
+        mbar_expect_tx(kb_full + st * 8, SMEM::KB_STAGE);
         tma_load_2d(sk, &tmap_k, kb_full + st * 8, args.H + c.head * ATT_D, row0 + kv0);
-        tma_load_2d(sk + AttSmem::K_BYTES, &tmap_bias, kb_full + st * 8, kv0, brow);
+        tma_load_2d(sk + SMEM::NP * SMEM::K_BYTES, &tmap_bias, kb_full + st * 8, kv0, brow);
+        if constexpr (kSplit) {
+          tma_load_2d(sk + SMEM::K_BYTES, &maps.k_lo, kb_full + st * 8, args.H + c.head * ATT_D, row0 + kv0);
+          tma_load_2d(sk + 2 * SMEM::K_BYTES + SMEM::B_BYTES, &maps.bias_lo, kb_full + st * 8, kv0, brow);
+        }
         // pull the tiles PF_DIST ahead into L2 (bias always comes from DRAM; K / V^T only for the first query tile
         // of a (slot, head)); one tile per step, so demand loads never queue behind a burst of prefetches
         {
@@ -311,8 +342,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (t > 0) {
           const int sv = (t - 1) % ATT_V_STAGES;
           mbar_wait(v_empty + sv * 8, (((t - 1) / ATT_V_STAGES) & 1) ^ 1);
-          mbar_expect_tx(v_full + sv * 8, ATT_D * ATT_BKV * 2);
-          tma_load_2d(sb + AttSmem::V_OFF + sv * AttSmem::V_BYTES, &tmap_vt, v_full + sv * 8, pv_kv0, pv_row);
+          mbar_expect_tx(v_full + sv * 8, SMEM::NP * ATT_D * ATT_BKV * 2);
+          tma_load_2d(sb + SMEM::V_OFF + sv * SMEM::V_STAGE, &tmap_vt, v_full + sv * 8, pv_kv0, pv_row);
+          if constexpr (kSplit)
+            tma_load_2d(sb + SMEM::V_OFF + sv * SMEM::V_STAGE + SMEM::V_BYTES, &maps.vt_lo, v_full + sv * 8, pv_kv0, pv_row);
         }
         pv_row = vrow; pv_kv0 = kv0;
         ++t;
@@ -321,8 +354,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       if (t > 0) {
         const int sv = (t - 1) % ATT_V_STAGES;
         mbar_wait(v_empty + sv * 8, (((t - 1) / ATT_V_STAGES) & 1) ^ 1);
-        mbar_expect_tx(v_full + sv * 8, ATT_D * ATT_BKV * 2);
-        tma_load_2d(sb + AttSmem::V_OFF + sv * AttSmem::V_BYTES, &tmap_vt, v_full + sv * 8, pv_kv0, pv_row);
+        mbar_expect_tx(v_full + sv * 8, SMEM::NP * ATT_D * ATT_BKV * 2);
+        tma_load_2d(sb + SMEM::V_OFF + sv * SMEM::V_STAGE, &tmap_vt, v_full + sv * 8, pv_kv0, pv_row);
+        if constexpr (kSplit)
+          tma_load_2d(sb + SMEM::V_OFF + sv * SMEM::V_STAGE + SMEM::V_BYTES, &maps.vt_lo, v_full + sv * 8, pv_kv0, pv_row);
       }
     }
   } else if (warp == 1) {
@@ -333,7 +368,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, ATT_DV);
       constexpr uint32_t idesc_s16 = umma_idesc_bf16(ATT_BQ, 16);   // the 16-key tail tile (args.tail_j)
       constexpr uint32_t idesc_b16 = umma_idesc_f16(ATT_BQ, 16);
-      const uint64_t di = umma_desc_sw128_kmajor(sb + AttSmem::I_OFF);
+      const uint64_t di = umma_desc_sw128_kmajor(sb + SMEM::I_OFF);
       AttCursor cs = att_first(total_items, n_qt, stride, args);   // next S = Q K^T + B I to issue (one tile ahead)
       AttCursor cp = cs;                                              // next P V to issue
       uint32_t ts = 0;
@@ -344,12 +379,26 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         mbar_wait(kb_full + st * 8, (ts / ATT_KB_STAGES) & 1);
         ATT_TRACE(1, ts, 1)
         tc_fence_after();
-        const uint32_t stage = sb + AttSmem::KB_OFF + st * AttSmem::KB_STAGE;
+        const uint32_t stage = sb + SMEM::KB_OFF + st * SMEM::KB_STAGE;
         const uint64_t dk = umma_desc_sw128_kmajor(stage);
-        const uint64_t db = umma_desc_sw128_kmajor(stage + AttSmem::K_BYTES);
+        const uint64_t db = umma_desc_sw128_kmajor(stage + SMEM::NP * SMEM::K_BYTES);
         const uint32_t d_s = tmem_S + (ts & 1) * ATT_BKV;
         // S buffer ts&1 last held P_{ts-2}; its P V was issued before this point and tcgen05.mma executes in order
-        if (cs.j != args.tail_j) {
+        if constexpr (kSplit) {
+          // S = Q_hi K_hi^T + Q_lo K_hi^T + Q_hi K_lo^T + B_hi I + B_lo I   (the 16-key tail path is off in this mode)
+          const uint64_t dkl = umma_desc_sw128_kmajor(stage + SMEM::K_BYTES);
+          const uint64_t dbl = umma_desc_sw128_kmajor(stage + 2 * SMEM::K_BYTES + SMEM::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ts(d_s, tmem_Q + k * 8, dk + 2 * k, idesc_s, k ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ts(d_s, tmem_Qlo + k * 8, dk + 2 * k, idesc_s, 1u);
+#pragma unroll
+          for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ts(d_s, tmem_Q + k * 8, dkl + 2 * k, idesc_s, 1u);
+#pragma unroll
+          for (int k = 0; k < ATT_BKV / 16; ++k) umma_bf16_ss(d_s, db + 2 * k, di + 2 * k, idesc_b, 1u);
+#pragma unroll
+          for (int k = 0; k < ATT_BKV / 16; ++k) umma_bf16_ss(d_s, dbl + 2 * k, di + 2 * k, idesc_b, 1u);
+        } else if (cs.j != args.tail_j) {
 #pragma unroll
           for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ts(d_s, tmem_Q + k * 8, dk + 2 * k, idesc_s, k ? 1u : 0u);
 #pragma unroll
@@ -377,12 +426,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         ATT_TRACE(1, t, 3)
         mbar_wait(v_full + sv * 8, (t / ATT_V_STAGES) & 1);
         tc_fence_after();
-        const uint64_t dv = umma_desc_sw128_kmajor(sb + AttSmem::V_OFF + sv * AttSmem::V_BYTES);
-        const int pv_steps = (cp.j != args.tail_j) ? ATT_BKV / 16 : 1;      // tail tile: P is [128 x 16]
+        const uint64_t dv = umma_desc_sw128_kmajor(sb + SMEM::V_OFF + sv * SMEM::V_STAGE);
+        const int pv_steps = (kSplit || cp.j != args.tail_j) ? ATT_BKV / 16 : 1;      // tail tile: P is [128 x 16]
 #pragma unroll
         for (int k = 0; k < ATT_BKV / 16; ++k)
           if (k < pv_steps)
             umma_bf16_ts(tmem_O, tmem_S + b * ATT_BKV + k * 8, dv + 2 * k, idesc_o, (k || !first) ? 1u : 0u);
+        if constexpr (kSplit) {
+          // O += P_lo [V_hi | 1] + P_hi V_lo   (P_lo sits in columns [32, 64) of the S buffer; V_lo has no ones row)
+          constexpr uint32_t idesc_o64 = umma_idesc_bf16(ATT_BQ, ATT_D);
+          const uint64_t dvl = umma_desc_sw128_kmajor(sb + SMEM::V_OFF + sv * SMEM::V_STAGE + SMEM::V_BYTES);
+#pragma unroll
+          for (int k = 0; k < ATT_BKV / 16; ++k) umma_bf16_ts(tmem_O, tmem_S + b * ATT_BKV + 32 + k * 8, dv + 2 * k, idesc_o, 1u);
+#pragma unroll
+          for (int k = 0; k < ATT_BKV / 16; ++k) umma_bf16_ts(tmem_O, tmem_S + b * ATT_BKV + k * 8, dvl + 2 * k, idesc_o64, 1u);
+        }
         umma_commit(o_full);
         umma_commit(v_empty + sv * 8);
         cp = att_next(cp, total_items, n_qt, stride, args);
@@ -407,6 +465,30 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       tmem_ld32(tmem_O + lane_addr, v);
       tmem_ld_wait();
       const float inv = 1.0f / __uint_as_float(lsum);
+      if constexpr (kSplit) {
+        // ctx as a split pair: hi = bf16(o / l), lo = bf16(o / l - hi)
+        __nv_bfloat16* lo_row = dst_row ? args.ctx_lo + (dst_row - args.ctx) : nullptr;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          if (hh) { tmem_ld32(tmem_O + lane_addr + 32, v); tmem_ld_wait(); }
+          if (dst_row) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float a = __uint_as_float(v[i * 8 + 2 * j]) * inv, c2 = __uint_as_float(v[i * 8 + 2 * j + 1]) * inv;
+                h[j] = pack_bf16x2(a, c2);
+                const float2 hf = unpack_bf16x2(h[j]);
+                l[j] = pack_bf16x2(a - hf.x, c2 - hf.y);
+              }
+              reinterpret_cast<uint4*>(dst_row)[hh * 4 + i] = make_uint4(h[0], h[1], h[2], h[3]);
+              reinterpret_cast<uint4*>(lo_row)[hh * 4 + i] = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+          }
+        }
+        return;
+      }
       uint4* dst = reinterpret_cast<uint4*>(dst_row);
       if (dst_row) {
 #pragma unroll
@@ -434,7 +516,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     auto q_to_tmem = [&](int ii) {
       const int qb = ii & 1;
       mbar_wait(q_full + qb * 8, (ii >> 1) & 1);
-      const uint32_t qrow = sb + AttSmem::Q_OFF + qb * AttSmem::Q_BYTES + r * 128;
+      const uint32_t qrow = sb + SMEM::Q_OFF + qb * SMEM::Q_STAGE + r * 128;
       uint32_t q[32];
 #pragma unroll
       for (int cch = 0; cch < 8; ++cch) {
@@ -442,6 +524,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         q[4 * cch] = x.x; q[4 * cch + 1] = x.y; q[4 * cch + 2] = x.z; q[4 * cch + 3] = x.w;
       }
       tmem_st32(tmem_Q + lane_addr, q);
+      if constexpr (kSplit) {
+#pragma unroll
+        for (int cch = 0; cch < 8; ++cch) {
+          const uint4 x = lds128(qrow + SMEM::Q_BYTES + ((cch ^ (r & 7)) << 4));
+          q[4 * cch] = x.x; q[4 * cch + 1] = x.y; q[4 * cch + 2] = x.z; q[4 * cch + 3] = x.w;
+        }
+        tmem_st32(tmem_Qlo + lane_addr, q);
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -467,7 +557,51 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       if (c.j == c.last_j && c.nitem < total_items) q_to_tmem(c.ii + 1);
 
       float pmax;
-      if (c.j == args.tail_j) {
+      if constexpr (kSplit) {
+        // fp32 mode: P as a split pair, P_hi (bf16 pairs) in columns [0, 32) and P_lo = bf16(p - P_hi) in [32, 64) of
+        // the S buffer (the row's 64 scores are in registers by then).  Reference handling as in the bf16 path below.
+        uint32_t v0[32], v1[32], ph[32], pl[32];
+        tmem_ld32(tS, v0);
+        tmem_ld32(tS + 32, v1);
+        tmem_ld_wait();
+        if (first) {
+          float m0 = fmaxf(__uint_as_float(v0[0]), __uint_as_float(v0[1]));
+#pragma unroll
+          for (int i = 2; i < 32; i += 2) m0 = fmaxf(m0, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v0[i + 1])));
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) m0 = fmaxf(m0, fmaxf(__uint_as_float(v1[i]), __uint_as_float(v1[i + 1])));
+          ref = m0;
+        }
+        float m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float a0 = __uint_as_float(i < 16 ? v0[2 * i] : v1[2 * i - 32]) - ref;
+          const float a1 = __uint_as_float(i < 16 ? v0[2 * i + 1] : v1[2 * i - 31]) - ref;
+          m = fmaxf(m, fmaxf(a0, a1));
+          const float e0 = fast_exp2(a0), e1 = fast_exp2(a1);
+          ph[i] = pack_bf16x2(e0, e1);
+          const float2 hf = unpack_bf16x2(ph[i]);
+          pl[i] = pack_bf16x2(e0 - hf.x, e1 - hf.y);
+        }
+        pmax = m;
+        if (pmax > ATT_JUMP) {
+          const float dq = ceilf(pmax);
+          ref += dq;
+          alpha_pend *= fast_exp2(-dq);
+          pmax -= dq;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e0 = fast_exp2(__uint_as_float(i < 16 ? v0[2 * i] : v1[2 * i - 32]) - ref);
+            const float e1 = fast_exp2(__uint_as_float(i < 16 ? v0[2 * i + 1] : v1[2 * i - 31]) - ref);
+            ph[i] = pack_bf16x2(e0, e1);
+            const float2 hf = unpack_bf16x2(ph[i]);
+            pl[i] = pack_bf16x2(e0 - hf.x, e1 - hf.y);
+          }
+        }
+        __syncwarp();
+        tmem_st32(tS, ph);
+        tmem_st32(tS + 32, pl);
+      } else if (c.j == args.tail_j) {
         // 16-key tail tile: a quarter of the loads, exponentials and stores
         uint32_t v[16], pq[8];
         tmem_ld16(tS, v);
@@ -604,7 +738,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<SMEM::TMEM_COLS>(tmem_base);
   }
 }
 

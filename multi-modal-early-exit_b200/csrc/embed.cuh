@@ -4,8 +4,14 @@
 //                         reference call EE/models/LayoutLMv3.py:511-517, 565)
 //   im2col_kernel       : 16x16/s16 patches -> bf16 rows for the patch GEMM (HF:70-82)
 //   visual_ln_kernel    : cls|patch + pos_embed -> norm (eps 1e-6) -> model LayerNorm (EE/models/LayoutLMv3.py:358-373, 565)
+//   embed_finish_vec_kernel : model LayerNorm of the survivors' text / visual embeddings after an embedding-level exit
+//                         (vision_avg / text_avg, EE/models/LayoutLMv3.py:465-483, 519-534): documents that left there
+//                         never get text embeddings, a fused row or an attention bias
 //   meanpool_kernel     : mean over the 709 fused tokens for the text_visual_concat exit (EE/models/LayoutLMv3.py:582)
 // Each token is LayerNormed twice, exactly as the reference does.
+// The text kernels check input_ids / bbox against the table sizes (the reference raises IndexError on such input):
+// out-of-range values are clamped and reported through an error flag that the synchronous entry points turn into an
+// error (mmee_last_error).
 #pragma once
 #include "ptx.cuh"
 
@@ -94,23 +100,72 @@ __device__ __forceinline__ void warp_layernorm4(float4 (&v)[NV4], int H, const f
   }
 }
 
-// one warp per text token; X row = doc*seq + t.  Vectorised variant: H = 128*NV4 and the six spatial segments
+// four consecutive values -> bf16 (8 B store) and, when lo != nullptr, the low parts bf16(v - bf16(v)) of the split
+// representation (hi + lo carries 16 mantissa bits; the fp32 engine mode feeds both to the tensor cores)
+__device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, const float4& v) {
+  const uint32_t h01 = pack_bf16x2(v.x, v.y), h23 = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(hi) = make_uint2(h01, h23);
+  if (lo) {
+    const float2 f01 = unpack_bf16x2(h01), f23 = unpack_bf16x2(h23);
+    *reinterpret_cast<uint2*>(lo) = make_uint2(pack_bf16x2(v.x - f01.x, v.y - f01.y), pack_bf16x2(v.z - f23.x, v.w - f23.y));
+  }
+}
+
+// one warp per text token; X row = slot*seq + t.  Vectorised variant: H = 128*NV4 and the six spatial segments
 // (4 x coord + 2 x shape) are multiples of 4 columns, so every lane gathers whole float4s (base: 6 per table).
+struct TextEmbedArgs {
+  const int64_t* ids;      // [B, n_text]
+  const int64_t* bbox;     // [B, n_text, 4]
+  const int* posid;        // [B, n_text]
+  __nv_bfloat16* X;        // [*, seq, H] fused rows (model LayerNorm applied), row = slot*seq + t; nullptr: not written
+  __nv_bfloat16* Xlo;      // optional low part of X (split-bf16, fp32 engine mode)
+  float* pre;              // [*, n_text, H] text embeddings BEFORE the model LayerNorm (text_avg exit), or nullptr
+  const int* slot_doc;     // slot -> document (inputs are read by document, outputs written by slot); nullptr: identity
+  const int* n_active_dev; // number of slots (nullptr: n_docs)
+  int n_docs, n_text, seq, H, coord, shape, vocab, max_2d;
+  float eps;
+  int* err_flag;           // set to 1 when an input id / box coordinate is outside its table
+};
+
+// token -> (slot, t, source token index); false when past the active slots
+__device__ __forceinline__ bool text_embed_locate(const TextEmbedArgs& a, int tok, int& slot, int& t, int& src_tok) {
+  const int n_slots = a.n_active_dev ? *a.n_active_dev : a.n_docs;
+  if (tok >= n_slots * a.n_text) return false;
+  slot = tok / a.n_text;
+  t = tok - slot * a.n_text;
+  const int doc = a.slot_doc ? a.slot_doc[slot] : slot;
+  src_tok = doc * a.n_text + t;
+  return true;
+}
+// range check of one token's gather indices (clamped in place)
+__device__ __forceinline__ void text_embed_check(const TextEmbedArgs& a, int64_t& id, int& x0, int& y0, int& x1, int& y1) {
+  const bool bad = id < 0 || id >= a.vocab || (x0 | y0 | x1 | y1) < 0 || x0 >= a.max_2d || y0 >= a.max_2d ||
+                   x1 >= a.max_2d || y1 >= a.max_2d;
+  if (bad) {
+    *a.err_flag = 1;
+    id = min(max(id, static_cast<int64_t>(0)), static_cast<int64_t>(a.vocab - 1));
+    x0 = min(max(x0, 0), a.max_2d - 1); y0 = min(max(y0, 0), a.max_2d - 1);
+    x1 = min(max(x1, 0), a.max_2d - 1); y1 = min(max(y1, 0), a.max_2d - 1);
+  }
+}
+__device__ __forceinline__ int clamp_coord64(long long v) {       // int64 -> int without wrap-around
+  return static_cast<int>(min(max(v, -1ll), 1ll << 20));
+}
+
 template <int NV4>
-__global__ void text_embed_vec_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ bbox,
-                                      const int* __restrict__ posid, EmbedWeights W, __nv_bfloat16* __restrict__ X,
-                                      float* __restrict__ pre, int n_docs, int n_text, int seq, int H, int coord,
-                                      int shape, float eps) {
+__global__ void text_embed_vec_kernel(const TextEmbedArgs a, EmbedWeights W) {
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (tok >= n_docs * n_text) return;
+  int slot, t, src_tok;
+  if (!text_embed_locate(a, tok, slot, t, src_tok)) return;
   const int lane = threadIdx.x & 31;
-  const int doc = tok / n_text, t = tok - doc * n_text;
-  const int64_t id = ids[tok];
-  const int pos = posid[tok];
-  const longlong2 b01 = __ldg(reinterpret_cast<const longlong2*>(bbox + static_cast<size_t>(tok) * 4));
-  const longlong2 b23 = __ldg(reinterpret_cast<const longlong2*>(bbox + static_cast<size_t>(tok) * 4) + 1);
-  const int x0 = static_cast<int>(b01.x), y0 = static_cast<int>(b01.y), x1 = static_cast<int>(b23.x),
-            y1 = static_cast<int>(b23.y);
+  const int n_text = a.n_text, seq = a.seq, H = a.H, coord = a.coord, shape = a.shape;
+  const float eps = a.eps;
+  int64_t id = a.ids[src_tok];
+  const int pos = a.posid[src_tok];
+  const longlong2 b01 = __ldg(reinterpret_cast<const longlong2*>(a.bbox + static_cast<size_t>(src_tok) * 4));
+  const longlong2 b23 = __ldg(reinterpret_cast<const longlong2*>(a.bbox + static_cast<size_t>(src_tok) * 4) + 1);
+  int x0 = clamp_coord64(b01.x), y0 = clamp_coord64(b01.y), x1 = clamp_coord64(b23.x), y1 = clamp_coord64(b23.y);
+  text_embed_check(a, id, x0, y0, x1, y1);
   const int hh = min(max(y1 - y0, 0), 1023), ww = min(max(x1 - x0, 0), 1023);
   const float* wrow = W.word + static_cast<size_t>(id) * H;
   const float* prow = W.pos + static_cast<size_t>(pos) * H;
@@ -140,33 +195,33 @@ __global__ void text_embed_vec_kernel(const int64_t* __restrict__ ids, const int
     v[i].w = ((wv[i].w + tv[i].w) + pv[i].w) + sv[i].w;
   }
   warp_layernorm4<NV4>(v, H, W.ln_emb_w, W.ln_emb_b, eps, lane);
-  if (pre) {                                            // text embeddings before the model LayerNorm (text_avg exit)
+  if (a.pre) {                                          // text embeddings before the model LayerNorm (text_avg exit)
 #pragma unroll
-    for (int i = 0; i < NV4; ++i) *reinterpret_cast<float4*>(pre + static_cast<size_t>(tok) * H + 4 * (lane + 32 * i)) = v[i];
+    for (int i = 0; i < NV4; ++i)
+      *reinterpret_cast<float4*>(a.pre + (static_cast<size_t>(slot) * n_text + t) * H + 4 * (lane + 32 * i)) = v[i];
   }
+  if (!a.X) return;
   warp_layernorm4<NV4>(v, H, W.ln_model_w, W.ln_model_b, eps, lane);
-  __nv_bfloat16* out = X + (static_cast<size_t>(doc) * seq + t) * H;
+  const size_t orow = (static_cast<size_t>(slot) * seq + t) * H;
 #pragma unroll
-  for (int i = 0; i < NV4; ++i)
-    *reinterpret_cast<uint2*>(out + 4 * (lane + 32 * i)) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+  for (int i = 0; i < NV4; ++i) store_split4(a.X + orow + 4 * (lane + 32 * i), a.Xlo ? a.Xlo + orow + 4 * (lane + 32 * i) : nullptr, v[i]);
 }
 
 // generic (scalar) variant for shapes the vectorised kernel does not cover (e.g. large: coord 171 / shape 170)
 // one warp per text token; X row = doc*seq + t
 template <int NV>
-__global__ void text_embed_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ bbox,
-                                  const int* __restrict__ posid, EmbedWeights W, __nv_bfloat16* __restrict__ X,
-                                  float* __restrict__ pre, int n_docs, int n_text, int seq, int H, int coord, int shape,
-                                  float eps) {
+__global__ void text_embed_kernel(const TextEmbedArgs a, EmbedWeights W) {
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (tok >= n_docs * n_text) return;
+  int slot, t, src_tok;
+  if (!text_embed_locate(a, tok, slot, t, src_tok)) return;
   const int lane = threadIdx.x & 31;
-  const int doc = tok / n_text, t = tok - doc * n_text;
-  const int64_t id = ids[tok];
-  const int pos = posid[tok];
-  const int64_t* bb = bbox + static_cast<size_t>(tok) * 4;
-  const int x0 = static_cast<int>(bb[0]), y0 = static_cast<int>(bb[1]), x1 = static_cast<int>(bb[2]),
-            y1 = static_cast<int>(bb[3]);
+  const int n_text = a.n_text, seq = a.seq, H = a.H, coord = a.coord, shape = a.shape;
+  const float eps = a.eps;
+  int64_t id = a.ids[src_tok];
+  const int pos = a.posid[src_tok];
+  const int64_t* bb = a.bbox + static_cast<size_t>(src_tok) * 4;
+  int x0 = clamp_coord64(bb[0]), y0 = clamp_coord64(bb[1]), x1 = clamp_coord64(bb[2]), y1 = clamp_coord64(bb[3]);
+  text_embed_check(a, id, x0, y0, x1, y1);
   const int hh = min(max(y1 - y0, 0), 1023), ww = min(max(x1 - x0, 0), 1023);
   const float* wrow = W.word + static_cast<size_t>(id) * H;
   const float* prow = W.pos + static_cast<size_t>(pos) * H;
@@ -191,22 +246,28 @@ __global__ void text_embed_kernel(const int64_t* __restrict__ ids, const int64_t
     v[i] = e;
   }
   warp_layernorm<NV>(v, H, W.ln_emb_w, W.ln_emb_b, eps, lane);
-  if (pre) {
+  if (a.pre) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) if (lane + 32 * i < H) pre[static_cast<size_t>(tok) * H + lane + 32 * i] = v[i];
+    for (int i = 0; i < NV; ++i)
+      if (lane + 32 * i < H) a.pre[(static_cast<size_t>(slot) * n_text + t) * H + lane + 32 * i] = v[i];
   }
+  if (!a.X) return;
   warp_layernorm<NV>(v, H, W.ln_model_w, W.ln_model_b, eps, lane);
-  __nv_bfloat16* out = X + (static_cast<size_t>(doc) * seq + t) * H;
+  const size_t orow = (static_cast<size_t>(slot) * seq + t) * H;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = lane + 32 * i;
-    if (c < H) out[c] = __float2bfloat16_rn(v[i]);
+    if (c < H) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v[i]);
+      a.X[orow + c] = hi;
+      if (a.Xlo) a.Xlo[orow + c] = __float2bfloat16_rn(v[i] - __bfloat162float(hi));
+    }
   }
 }
 
 // pixels f32 [B,3,img,img] -> patches bf16 [B*np*np, 3*16*16], k = c*256 + kh*16 + kw (conv weight order)
-__global__ void im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ out, int n_docs, int img,
-                              int patch, int chans) {
+__global__ void im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ out,
+                              __nv_bfloat16* __restrict__ out_lo, int n_docs, int img, int patch, int chans) {
   const int np = img / patch;
   const int kdim = chans * patch * patch;
   // grid.y = document: all index arithmetic stays 32-bit (the 64-bit divisions of a flat index cost more than the copy)
@@ -222,15 +283,14 @@ __global__ void im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __res
   const int pr = p / np, pc = p % np;
   const float4 v = *reinterpret_cast<const float4*>(
       px + ((static_cast<size_t>(doc) * chans + c) * img + (pr * patch + kh)) * img + pc * patch + kw);
-  uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-  *reinterpret_cast<uint2*>(out + e) = o;
+  store_split4(out + e, out_lo ? out_lo + e : nullptr, v);
 }
 
 // one warp per visual token (doc, p); VIS rows 1..n_patch hold conv + bias + pos_embed (written by the patch GEMM)
 template <int NV>
 __global__ void visual_ln_kernel(float* __restrict__ VIS, EmbedWeights W, __nv_bfloat16* __restrict__ X,
-                                 int write_pre, int n_docs, int n_vis, int n_text, int seq, int H, float eps_vis,
-                                 float eps) {
+                                 __nv_bfloat16* __restrict__ Xlo, int write_pre, int n_docs, int n_vis, int n_text,
+                                 int seq, int H, float eps_vis, float eps) {
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= n_docs * n_vis) return;
   const int lane = threadIdx.x & 31;
@@ -249,19 +309,25 @@ __global__ void visual_ln_kernel(float* __restrict__ VIS, EmbedWeights W, __nv_b
 #pragma unroll
     for (int i = 0; i < NV; ++i) if (lane + 32 * i < H) VIS[(static_cast<size_t>(doc) * n_vis + p) * H + lane + 32 * i] = v[i];
   }
+  if (!X) return;                                       // embedding-level exits pending: embed_finish_vec_kernel writes X
   warp_layernorm<NV>(v, H, W.ln_model_w, W.ln_model_b, eps, lane);
-  __nv_bfloat16* out = X + (static_cast<size_t>(doc) * seq + n_text + p) * H;
+  const size_t orow = (static_cast<size_t>(doc) * seq + n_text + p) * H;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = lane + 32 * i;
-    if (c < H) out[c] = __float2bfloat16_rn(v[i]);
+    if (c < H) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v[i]);
+      X[orow + c] = hi;
+      if (Xlo) Xlo[orow + c] = __float2bfloat16_rn(v[i] - __bfloat162float(hi));
+    }
   }
 }
 
 // Vectorised variant for H = 128 * NV4: float4 loads, 8 B stores, grid-stride over the visual tokens.
 template <int NV4>
 __global__ void __launch_bounds__(256) visual_ln_vec_kernel(float* __restrict__ VIS, EmbedWeights W,
-                                                            __nv_bfloat16* __restrict__ X, int write_pre, int n_docs,
+                                                            __nv_bfloat16* __restrict__ X,
+                                                            __nv_bfloat16* __restrict__ Xlo, int write_pre, int n_docs,
                                                             int n_vis, int n_text, int seq, int H, float eps_vis,
                                                             float eps) {
   const int lane = threadIdx.x & 31;
@@ -287,23 +353,57 @@ __global__ void __launch_bounds__(256) visual_ln_vec_kernel(float* __restrict__ 
 #pragma unroll
       for (int i = 0; i < NV4; ++i) *reinterpret_cast<float4*>(row + 4 * (lane + 32 * i)) = v[i];
     }
+    if (!X) continue;                                   // embedding-level exits pending: embed_finish_vec_kernel writes X
     warp_layernorm4<NV4>(v, H, W.ln_model_w, W.ln_model_b, eps, lane);
-    __nv_bfloat16* out = X + (static_cast<size_t>(doc) * seq + n_text + p) * H;
+    const size_t orow = (static_cast<size_t>(doc) * seq + n_text + p) * H;
 #pragma unroll
     for (int i = 0; i < NV4; ++i)
-      *reinterpret_cast<uint2*>(out + 4 * (lane + 32 * i)) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+      store_split4(X + orow + 4 * (lane + 32 * i), Xlo ? Xlo + orow + 4 * (lane + 32 * i) : nullptr, v[i]);
+  }
+}
+
+// Model LayerNorm of already-embedded rows for the SURVIVORS of an embedding-level exit: X[slot*seq + dst_off + r] =
+// LN_model(src[src_map(slot)*src_rows + r]) for the active slots.  src = the text embeddings after embeddings.LayerNorm
+// (TXT, indexed by the slot numbering they were computed under; src_map = new -> old slot of the text_avg compaction,
+// or nullptr) or the visual embeddings after `norm` (VIS, indexed by document; src_map = slot -> document).
+// H = 128 * NV4.  EE/models/LayoutLMv3.py:549-566 (cat + LayerNorm) restricted to the documents that are still there.
+template <int NV4>
+__global__ void __launch_bounds__(256) embed_finish_vec_kernel(const float* __restrict__ src, int src_rows,
+                                                               const int* __restrict__ src_map, EmbedWeights W,
+                                                               __nv_bfloat16* __restrict__ X,
+                                                               __nv_bfloat16* __restrict__ Xlo, int dst_off, int seq,
+                                                               int H, float eps, const int* __restrict__ n_active_dev) {
+  const int lane = threadIdx.x & 31;
+  const int total = *n_active_dev * src_rows;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < total; row += warps_total) {
+    const int slot = row / src_rows, r = row - slot * src_rows;
+    const int sidx = src_map ? src_map[slot] : slot;
+    const float* in = src + (static_cast<size_t>(sidx) * src_rows + r) * H;
+    float4 v[NV4];
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) v[i] = *reinterpret_cast<const float4*>(in + 4 * (lane + 32 * i));
+    warp_layernorm4<NV4>(v, H, W.ln_model_w, W.ln_model_b, eps, lane);
+    const size_t orow = (static_cast<size_t>(slot) * seq + dst_off + r) * H;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i)
+      store_split4(X + orow + 4 * (lane + 32 * i), Xlo ? Xlo + orow + 4 * (lane + 32 * i) : nullptr, v[i]);
   }
 }
 
 // pool[doc][c] = mean_t X[doc*seq + t][c]; grid (ceil(H/32), n_docs), block 256 (8 warps stride the tokens)
-__global__ void meanpool_kernel(const __nv_bfloat16* __restrict__ X, float* __restrict__ pool, int seq, int H) {
+__global__ void meanpool_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ Xlo,
+                                float* __restrict__ pool, int seq, int H) {
   __shared__ float part[8][33];
   const int doc = blockIdx.y;
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int w = threadIdx.x >> 5;
   float s = 0.f;
   if (c < H)
-    for (int t = w; t < seq; t += 8) s += __bfloat162float(X[(static_cast<size_t>(doc) * seq + t) * H + c]);
+    for (int t = w; t < seq; t += 8) {
+      const size_t i = (static_cast<size_t>(doc) * seq + t) * H + c;
+      s += Xlo ? __bfloat162float(X[i]) + __bfloat162float(Xlo[i]) : __bfloat162float(X[i]);
+    }
   part[w][threadIdx.x & 31] = s;
   __syncthreads();
   if (w == 0 && c < H) {

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <map>
+#include <memory>
 #include <numeric>
 #include <stdexcept>
 #include <string>
@@ -62,6 +63,17 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i < n) dst[i] = __float2bfloat16_rn(src[i] * scale);
 }
+// split-bf16 conversion of a weight: hi = bf16(v), lo = bf16(v - hi)   (fp32 engine mode)
+__global__ void f32_to_bf16_split_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                         __nv_bfloat16* __restrict__ lo, size_t n, float scale) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n) {
+    const float v = src[i] * scale;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
 __global__ void init_forward_kernel(int* slot_doc, int* out_exit, int* n_dev, int* m_dev, unsigned long long* hist,
                                     int B, int seq, int n_hist, int* any_pad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,8 +105,10 @@ __global__ void hist_to_i64_kernel(const unsigned long long* h, long long* out, 
 
 struct LayerW {
   DevBuf<__nv_bfloat16> wqkv, wo, wi, wo2;
+  DevBuf<__nv_bfloat16> wqkv_lo, wo_lo, wi_lo, wo2_lo;      // fp32 engine mode: low parts of the split-bf16 weights
   DevBuf<float> bqkv, bo, bi, bo2, ln1_w, ln1_b, ln2_w, ln2_b;
   CUtensorMap t_wqkv, t_wo, t_wi, t_wo2;
+  CUtensorMap t_wqkv_lo, t_wo_lo, t_wi_lo, t_wo2_lo;
 };
 
 struct HeadW {
@@ -121,6 +135,7 @@ struct mmee_engine {
   int H, L, heads, I, T, P, S, K, n_vis, n_patch, kdim_patch;
   int kv_pitch = 768, bias_pitch = 768;
   int att_tail_j = -1, bias_width = 768;
+  bool split = false;              // fp32 engine mode (mmee_model_desc.compute_dtype == MMEE_DTYPE_FP32): split-bf16 operands
   DevBuf<int> any_pad;             // [1] set by keymask_kernel when some text token of the batch is padded
   DevBuf<float> lte_w, slot_lte;   // learned-to-exit scorer [H] (optional) and its per-slot scores
   float lte_b = 0.f;
@@ -146,8 +161,8 @@ struct mmee_engine {
   std::vector<LayerW> layers;
   DevBuf<float> word, type0, pos, x_emb, y_emb, h_emb, w_emb, ln_emb_w, ln_emb_b, ln_model_w, ln_model_b, ln_vis_w,
       ln_vis_b, cls_token, pos_embed, patch_b, w1d, wx, wy;
-  DevBuf<__nv_bfloat16> patch_w;
-  CUtensorMap t_patch_w;
+  DevBuf<__nv_bfloat16> patch_w, patch_w_lo;
+  CUtensorMap t_patch_w, t_patch_w_lo;
   std::vector<HeadW> exit_heads;     // one per configured exit (concat first if present)
   HeadW classifier;
   DevBuf<uint8_t> lut1, lut2;
@@ -157,13 +172,16 @@ struct mmee_engine {
   // activations
   DevBuf<__nv_bfloat16> X[2], QK, VT, CTX, A1, MID, PATCH;
   DevBuf<__nv_bfloat16> Xlo[2], A1lo;       // low parts of the split-bf16 residual stream (precise_residual)
+  DevBuf<__nv_bfloat16> QKlo, VTlo, CTXlo, MIDlo, PATCHlo;   // fp32 engine mode: low parts of every other GEMM / attention operand
+  DevBuf<__half> BIASlo;                    // fp32 engine mode: low part of the attention bias
   bool precise_residual = true;
   bool skip_pad_q = true;          // attention skips query tiles of padded text tokens; MMEE_SKIP_PAD_Q=0 turns it off
   DevBuf<float> Y, VIS, POOL, POOLV, POOLT, TXT, Z, T0, T1;
   bool has_vision_exit = false, has_text_exit = false;
   DevBuf<__half> BIAS, bias_t2;
-  DevBuf<float> maskadd, bias_t1;
-  DevBuf<int> tileflag, att_err;
+  DevBuf<float> maskadd, bias_t1, bias_tx, bias_ty;     // bias_tx / bias_ty: fp32 engine mode (bias_build_split_kernel)
+  DevBuf<int> tileflag, err_flags;          // err_flags: [0] attention online-softmax guard, [1] input id / box out of range
+  cudaEvent_t last_done = nullptr;          // end of the last forward: the next one (any stream) is ordered after it
   DevBuf<uint2> slot_meta;
   DevBuf<long long> att_trace;
   bool trace_on = false;
@@ -171,6 +189,7 @@ struct mmee_engine {
   int n_kv_tiles = 6;
   DevBuf<int> posid;
   CUtensorMap t_x[2], t_qk, t_k64, t_vt, t_bias, t_ctx, t_a1, t_mid, t_patch;
+  CUtensorMap t_x_lo[2], t_qk_lo, t_k64_lo, t_vt_lo, t_bias_lo, t_ctx_lo, t_a1_lo, t_mid_lo, t_patch_lo;   // fp32 engine mode
 
   // bookkeeping (device)
   DevBuf<int> n_dev, m_dev;                 // [stages]
@@ -206,6 +225,7 @@ struct mmee_engine {
     if (stream) cudaStreamDestroy(stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (px_ready) cudaEventDestroy(px_ready);
+    if (last_done) cudaEventDestroy(last_done);
     if (fwd_start) cudaEventDestroy(fwd_start);
   }
 };
@@ -267,6 +287,16 @@ void upload_bf16(__nv_bfloat16* dst, const std::vector<float>& src, float scale 
   CUDA_OK(cudaDeviceSynchronize());
 }
 
+// hi[...] = bf16(src * scale), lo[...] = bf16(src * scale - hi)
+void upload_bf16_split(__nv_bfloat16* hi, __nv_bfloat16* lo, const std::vector<float>& src, float scale = 1.f) {
+  DevBuf<float> tmp;
+  tmp.alloc(src.size());
+  CUDA_OK(cudaMemcpy(tmp.p, src.data(), src.size() * 4, cudaMemcpyHostToDevice));
+  f32_to_bf16_split_kernel<<<static_cast<unsigned>((src.size() + 255) / 256), 256>>>(tmp.p, hi, lo, src.size(), scale);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaDeviceSynchronize());
+}
+
 void load_head(mmee_engine* e, HeadW& h, const std::string& prefix, int n_out) {
   const int H = e->H;
   h.n_out = n_out;
@@ -279,25 +309,27 @@ void load_head(mmee_engine* e, HeadW& h, const std::string& prefix, int n_out) {
   upload_f32(h.out_b, need(e, prefix + ".out_proj.bias", {n_out}));
 }
 
-template <int BN, int EPI>
-void launch_gemm_t(mmee_engine* e, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<BN, EPI>;
+template <int BN, int EPI, bool SPLIT>
+void launch_gemm_t(mmee_engine* e, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta_lo,
+                   const CUtensorMap& tb_lo, const GemmArgs& a, cudaStream_t st) {
+  auto kern = gemm_tc_kernel<BN, EPI, SPLIT>;
   static bool configured_dev[64] = {};
   bool& configured = configured_dev[e->device & 63];   // the attribute is per device
   if (!configured) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::DYN_BYTES));
     configured = true;
   }
-  kern<<<e->sms, GEMM_THREADS, GemmSmem<BN>::DYN_BYTES, st>>>(ta, tb, a);
+  kern<<<e->sms, GEMM_THREADS, GemmSmem<BN>::DYN_BYTES, st>>>(ta, tb, ta_lo, tb_lo, a);
   CUDA_OK(cudaGetLastError());
   e->launches++;
 }
 
 // BLOCK_N = 256 shapes run on the CTA-pair (cta_group::2) kernel; its weight tensor maps use 128-row boxes
 // (each CTA of the pair stages half of the 256 output columns), see wbox().
-template <int EPI>
-void launch_gemm_pair(mmee_engine* e, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t st) {
-  auto kern = gemm_tc_pair_kernel<EPI>;
+template <int EPI, bool SPLIT>
+void launch_gemm_pair(mmee_engine* e, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta_lo,
+                      const CUtensorMap& tb_lo, const GemmArgs& a, cudaStream_t st) {
+  auto kern = gemm_tc_pair_kernel<EPI, SPLIT>;
   using PS = GemmPairSmemT<gemm_pair_epi_warps<EPI>()>;
   static bool configured_dev[64] = {};
   bool& configured = configured_dev[e->device & 63];   // the attribute is per device
@@ -305,16 +337,23 @@ void launch_gemm_pair(mmee_engine* e, const CUtensorMap& ta, const CUtensorMap& 
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PS::DYN_BYTES));
     configured = true;
   }
-  kern<<<e->sms & ~1, PS::THREADS, PS::DYN_BYTES, st>>>(ta, tb, a);
+  kern<<<e->sms & ~1, PS::THREADS, PS::DYN_BYTES, st>>>(ta, tb, ta_lo, tb_lo, a);
   CUDA_OK(cudaGetLastError());
   e->launches++;
 }
 
+// ta_lo / tb_lo: tensor maps of the operands' low parts; both given = fp32 engine mode (three k segments)
 template <int EPI>
 void launch_gemm(mmee_engine* e, int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a,
-                 cudaStream_t st) {
-  if (bn == 256) launch_gemm_pair<EPI>(e, ta, tb, a, st);
-  else launch_gemm_t<128, EPI>(e, ta, tb, a, st);
+                 cudaStream_t st, const CUtensorMap* ta_lo = nullptr, const CUtensorMap* tb_lo = nullptr) {
+  if (e->split) {
+    if (!ta_lo || !tb_lo) throw std::runtime_error("fp32 mode: GEMM launched without the low-part tensor maps");
+    if (bn == 256) launch_gemm_pair<EPI, true>(e, ta, tb, *ta_lo, *tb_lo, a, st);
+    else launch_gemm_t<128, EPI, true>(e, ta, tb, *ta_lo, *tb_lo, a, st);
+  } else {
+    if (bn == 256) launch_gemm_pair<EPI, false>(e, ta, tb, ta, tb, a, st);
+    else launch_gemm_t<128, EPI, false>(e, ta, tb, ta, tb, a, st);
+  }
 }
 
 int wbox(int bn) { return bn == 256 ? 128 : bn; }   // weight TMA box rows for a GEMM family with BLOCK_N = bn
@@ -391,8 +430,17 @@ void finalize(mmee_engine* e) {
   upload_f32(e->cls_token, need(e, p + "cls_token", {H}));
   upload_f32(e->pos_embed, need(e, p + "pos_embed", {e->n_vis, H}));
   upload_f32(e->patch_b, need(e, p + "patch_embed.proj.bias", {H}));
-  e->patch_w.alloc(static_cast<size_t>(H) * e->kdim_patch);
-  upload_bf16(e->patch_w.p, need(e, p + "patch_embed.proj.weight", {H, e->kdim_patch}));
+  const bool split = e->split;
+  // one GEMM weight: bf16 (bf16 mode) or the split pair (fp32 mode)
+  auto upload_w = [&](DevBuf<__nv_bfloat16>& hi, DevBuf<__nv_bfloat16>& lo, size_t offset, size_t total,
+                      const std::vector<float>& src, float scale = 1.f) {
+    if (!hi.p) hi.alloc(total);
+    if (split && !lo.p) lo.alloc(total);
+    if (split) upload_bf16_split(hi.p + offset, lo.p + offset, src, scale);
+    else upload_bf16(hi.p + offset, src, scale);
+  };
+  upload_w(e->patch_w, e->patch_w_lo, 0, static_cast<size_t>(H) * e->kdim_patch,
+           need(e, p + "patch_embed.proj.weight", {H, e->kdim_patch}));
   upload_f32(e->w1d, need(e, p + "encoder.rel_pos_bias.weight", {h, d.rel_bins}));
   upload_f32(e->wx, need(e, p + "encoder.rel_pos_x_bias.weight", {h, d.rel2d_bins}));
   upload_f32(e->wy, need(e, p + "encoder.rel_pos_y_bias.weight", {h, d.rel2d_bins}));
@@ -417,6 +465,16 @@ void finalize(mmee_engine* e) {
           T2[(static_cast<size_t>(bx) * d.rel2d_bins + by) * t2p + hh] = __float2half_rn(
               (tx[static_cast<size_t>(hh) * d.rel2d_bins + bx] + ty[static_cast<size_t>(hh) * d.rel2d_bins + by]) * qscale);
     upload_f32(e->bias_t1, T1);
+    if (e->split) {                                // fp32 tables for the split bias builder
+      std::vector<float> TX(static_cast<size_t>(d.rel2d_bins) * t2p, 0.f), TY(TX.size(), 0.f);
+      for (int b2 = 0; b2 < d.rel2d_bins; ++b2)
+        for (int hh = 0; hh < h; ++hh) {
+          TX[static_cast<size_t>(b2) * t2p + hh] = tx[static_cast<size_t>(hh) * d.rel2d_bins + b2] * qscale;
+          TY[static_cast<size_t>(b2) * t2p + hh] = ty[static_cast<size_t>(hh) * d.rel2d_bins + b2] * qscale;
+        }
+      upload_f32(e->bias_tx, TX);
+      upload_f32(e->bias_ty, TY);
+    }
     e->bias_t2.alloc(T2.size());
     CUDA_OK(cudaMemcpy(e->bias_t2.p, T2.data(), T2.size() * 2, cudaMemcpyHostToDevice));
   }
@@ -424,10 +482,10 @@ void finalize(mmee_engine* e) {
   for (int i = 0; i < e->L; ++i) {
     LayerW& w = e->layers[i];
     const std::string lp = p + "encoder.layer." + std::to_string(i) + ".";
-    w.wqkv.alloc(static_cast<size_t>(3) * H * H);
-    upload_bf16(w.wqkv.p, need(e, lp + "attention.self.query.weight", {H, H}), qscale);
-    upload_bf16(w.wqkv.p + static_cast<size_t>(H) * H, need(e, lp + "attention.self.key.weight", {H, H}));
-    upload_bf16(w.wqkv.p + static_cast<size_t>(2) * H * H, need(e, lp + "attention.self.value.weight", {H, H}));
+    const size_t hh = static_cast<size_t>(H) * H;
+    upload_w(w.wqkv, w.wqkv_lo, 0, 3 * hh, need(e, lp + "attention.self.query.weight", {H, H}), qscale);
+    upload_w(w.wqkv, w.wqkv_lo, hh, 3 * hh, need(e, lp + "attention.self.key.weight", {H, H}));
+    upload_w(w.wqkv, w.wqkv_lo, 2 * hh, 3 * hh, need(e, lp + "attention.self.value.weight", {H, H}));
     {
       std::vector<float> b(3 * H);
       const auto& bq = need(e, lp + "attention.self.query.bias", {H});
@@ -436,16 +494,13 @@ void finalize(mmee_engine* e) {
       for (int j = 0; j < H; ++j) { b[j] = bq[j] * qscale; b[H + j] = bk[j]; b[2 * H + j] = bv[j]; }
       upload_f32(w.bqkv, b);
     }
-    w.wo.alloc(static_cast<size_t>(H) * H);
-    upload_bf16(w.wo.p, need(e, lp + "attention.output.dense.weight", {H, H}));
+    upload_w(w.wo, w.wo_lo, 0, hh, need(e, lp + "attention.output.dense.weight", {H, H}));
     upload_f32(w.bo, need(e, lp + "attention.output.dense.bias", {H}));
     upload_f32(w.ln1_w, need(e, lp + "attention.output.LayerNorm.weight", {H}));
     upload_f32(w.ln1_b, need(e, lp + "attention.output.LayerNorm.bias", {H}));
-    w.wi.alloc(static_cast<size_t>(I) * H);
-    upload_bf16(w.wi.p, need(e, lp + "intermediate.dense.weight", {I, H}));
+    upload_w(w.wi, w.wi_lo, 0, static_cast<size_t>(I) * H, need(e, lp + "intermediate.dense.weight", {I, H}));
     upload_f32(w.bi, need(e, lp + "intermediate.dense.bias", {I}));
-    w.wo2.alloc(static_cast<size_t>(H) * I);
-    upload_bf16(w.wo2.p, need(e, lp + "output.dense.weight", {H, I}));
+    upload_w(w.wo2, w.wo2_lo, 0, static_cast<size_t>(H) * I, need(e, lp + "output.dense.weight", {H, I}));
     upload_f32(w.bo2, need(e, lp + "output.dense.bias", {H}));
     upload_f32(w.ln2_w, need(e, lp + "output.LayerNorm.weight", {H}));
     upload_f32(w.ln2_b, need(e, lp + "output.LayerNorm.bias", {H}));
@@ -453,8 +508,15 @@ void finalize(mmee_engine* e) {
     w.t_wo = make_tmap_2d_sw128(w.wo.p, H, H, H, wbox(e->bn_h));
     w.t_wi = make_tmap_2d_sw128(w.wi.p, I, H, H, wbox(e->bn_i));
     w.t_wo2 = make_tmap_2d_sw128(w.wo2.p, H, I, I, wbox(e->bn_h));
+    if (split) {
+      w.t_wqkv_lo = make_tmap_2d_sw128(w.wqkv_lo.p, 3 * H, H, H, wbox(e->bn_qkv));
+      w.t_wo_lo = make_tmap_2d_sw128(w.wo_lo.p, H, H, H, wbox(e->bn_h));
+      w.t_wi_lo = make_tmap_2d_sw128(w.wi_lo.p, I, H, H, wbox(e->bn_i));
+      w.t_wo2_lo = make_tmap_2d_sw128(w.wo2_lo.p, H, I, I, wbox(e->bn_h));
+    }
   }
   e->t_patch_w = make_tmap_2d_sw128(e->patch_w.p, H, e->kdim_patch, e->kdim_patch, wbox(e->bn_h));
+  if (split) e->t_patch_w_lo = make_tmap_2d_sw128(e->patch_w_lo.p, H, e->kdim_patch, e->kdim_patch, wbox(e->bn_h));
 
   const int n_head_out = d.head_kind == 0 ? d.n_labels : 2;
   e->exit_heads.resize(d.n_exits);
@@ -515,10 +577,17 @@ void allocate(mmee_engine* e) {
   if (e->precise_residual) {
     e->Xlo[0].alloc(M * H, true); e->Xlo[1].alloc(M * H, true); e->A1lo.alloc(M * H, true);
   }
+  if (e->split) {
+    e->QKlo.alloc(M * 2 * H, true);
+    e->VTlo.alloc(static_cast<size_t>(B) * heads * 64 * e->kv_pitch, true);
+    e->CTXlo.alloc(M * H, true);
+    e->MIDlo.alloc(M * I, true);
+  }
   e->MID.alloc(M * I, true);
   e->Y.alloc(M * H, true);
   const size_t mp = (static_cast<size_t>(B) * e->n_patch + 255) / 256 * 256 + 128;
   e->PATCH.alloc(mp * e->kdim_patch, true);
+  if (e->split) e->PATCHlo.alloc(mp * e->kdim_patch, true);
   e->VIS.alloc(static_cast<size_t>(B) * e->n_vis * H, true);
   e->POOL.alloc(static_cast<size_t>(B) * H, true);
   for (int x = 0; x < e->d.n_exits; ++x) {
@@ -526,14 +595,14 @@ void allocate(mmee_engine* e) {
     if (e->d.exit_after_layer[x] == MMEE_EXIT_TEXT_AVG) e->has_text_exit = true;
   }
   if (e->has_vision_exit) e->POOLV.alloc(static_cast<size_t>(B) * H, true);
-  if (e->has_text_exit) {
-    e->POOLT.alloc(static_cast<size_t>(B) * H, true);
-    e->TXT.alloc(static_cast<size_t>(B) * e->T * H, true);
-  }
+  if (e->has_text_exit) e->POOLT.alloc(static_cast<size_t>(B) * H, true);
+  if (e->has_vision_exit || e->has_text_exit)            // text embeddings before the model LayerNorm (survivors finish later)
+    e->TXT.alloc(static_cast<size_t>(B) * std::max(e->T, 1) * H, true);
   e->Z.alloc(static_cast<size_t>(B) * H, true);
   e->T0.alloc(static_cast<size_t>(B) * H, true);
   e->T1.alloc(static_cast<size_t>(B) * H, true);
   e->BIAS.alloc(static_cast<size_t>(B) * heads * S * e->bias_pitch + 64 * 1024, true);   // 12.3 MB / base document
+  if (e->split) e->BIASlo.alloc(static_cast<size_t>(B) * heads * S * e->bias_pitch + 64 * 1024, true);
   e->posid.alloc(static_cast<size_t>(B) * e->T);
 
   e->t_x[0] = make_tmap_2d_sw128(e->X[0].p, M, H, H, 128);
@@ -543,17 +612,30 @@ void allocate(mmee_engine* e) {
   e->t_k64 = make_tmap_2d_sw128(e->QK.p, M, 2 * H, 2 * H, ATT_BKV);
   e->t_bias = make_tmap_2d_sw128(e->BIAS.p, static_cast<uint64_t>(B) * heads * S, e->bias_width, e->bias_pitch, ATT_BQ,
                                  CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
-  if (e->n_kv_tiles > ATT_MAX_KV_TILES) throw std::runtime_error("too many key tiles");
   e->n_kv_tiles = (S + ATT_BKV - 1) / ATT_BKV;
+  if (e->n_kv_tiles > ATT_MAX_KV_TILES) throw std::runtime_error("too many key tiles");
   e->maskadd.alloc(static_cast<size_t>(B) * e->kv_pitch, true);
   e->tileflag.alloc(static_cast<size_t>(B) * e->n_kv_tiles, true);
-  e->att_err.alloc(1, true);
+  e->err_flags.alloc(2, true);
   e->slot_meta.alloc(B, true);
   e->att_trace.alloc(4096, true);
   e->t_ctx = make_tmap_2d_sw128(e->CTX.p, M, H, H, 128);
   e->t_a1 = make_tmap_2d_sw128(e->A1.p, M, H, H, 128);
   e->t_mid = make_tmap_2d_sw128(e->MID.p, M, I, I, 128);
   e->t_patch = make_tmap_2d_sw128(e->PATCH.p, mp, e->kdim_patch, e->kdim_patch, 128);
+  if (e->split) {
+    e->t_x_lo[0] = make_tmap_2d_sw128(e->Xlo[0].p, M, H, H, 128);
+    e->t_x_lo[1] = make_tmap_2d_sw128(e->Xlo[1].p, M, H, H, 128);
+    e->t_qk_lo = make_tmap_2d_sw128(e->QKlo.p, M, 2 * H, 2 * H, 128);
+    e->t_k64_lo = make_tmap_2d_sw128(e->QKlo.p, M, 2 * H, 2 * H, ATT_BKV);
+    e->t_vt_lo = make_tmap_2d_sw128(e->VTlo.p, static_cast<uint64_t>(B) * heads * 64, e->kv_pitch, e->kv_pitch, 64);
+    e->t_bias_lo = make_tmap_2d_sw128(e->BIASlo.p, static_cast<uint64_t>(B) * heads * S, e->bias_width, e->bias_pitch, ATT_BQ,
+                                      CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    e->t_ctx_lo = make_tmap_2d_sw128(e->CTXlo.p, M, H, H, 128);
+    e->t_a1_lo = make_tmap_2d_sw128(e->A1lo.p, M, H, H, 128);
+    e->t_mid_lo = make_tmap_2d_sw128(e->MIDlo.p, M, I, I, 128);
+    e->t_patch_lo = make_tmap_2d_sw128(e->PATCHlo.p, mp, e->kdim_patch, e->kdim_patch, 128);
+  }
 
   const int st = n_stages(e);
   e->n_dev.alloc(st, true);
@@ -597,6 +679,9 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   e->launches = 0;
   for (auto& x : e->ev) cudaEventDestroy(x.second);
   e->ev.clear();
+  // the engine has ONE set of scratch buffers: a forward on any stream is ordered after the previous forward (recorded
+  // at its end below), whichever stream that one ran on
+  CUDA_OK(cudaStreamWaitEvent(st, e->last_done, 0));
   mark(e, "start", st);
 
   init_forward_kernel<<<(std::max(B, E1) + 255) / 256, 256, 0, st>>>(e->slot_doc[0].p, e->out_exit.p, e->n_dev.p,
@@ -611,102 +696,14 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     e->launches += 3;
   }
 
-  // ---- embeddings
-  EmbedWeights ew;
-  ew.word = e->word.p; ew.type0 = e->type0.p; ew.pos = e->pos.p; ew.x_emb = e->x_emb.p; ew.y_emb = e->y_emb.p;
-  ew.h_emb = e->h_emb.p; ew.w_emb = e->w_emb.p; ew.ln_emb_w = e->ln_emb_w.p; ew.ln_emb_b = e->ln_emb_b.p;
-  ew.ln_model_w = e->ln_model_w.p; ew.ln_model_b = e->ln_model_b.p; ew.ln_vis_w = e->ln_vis_w.p;
-  ew.ln_vis_b = e->ln_vis_b.p; ew.cls_token = e->cls_token.p; ew.pos_embed = e->pos_embed.p;
-
-  if (T > 0) {   // image-only engines (n_text = 0, BASELINE config 5) have no text tokens
-  posid_kernel<<<(B + 7) / 8, 256, 0, st>>>(ids, e->posid.p, B, T, d.pad_id);
-  e->launches++;
-  if (H % 128 == 0 && d.coord % 4 == 0 && d.shape % 4 == 0 && H / 128 <= 8) {
-    auto go = [&](auto nv4) {
-      text_embed_vec_kernel<decltype(nv4)::value><<<(B * T + 7) / 8, 256, 0, st>>>(
-          ids, bbox, e->posid.p, ew, e->X[0].p, e->TXT.p, B, T, S, H, d.coord, d.shape, d.ln_eps);
-    };
-    switch (H / 128) {
-      case 1: go(std::integral_constant<int, 1>{}); break;
-      case 2: go(std::integral_constant<int, 2>{}); break;
-      case 4: go(std::integral_constant<int, 4>{}); break;
-      case 6: go(std::integral_constant<int, 6>{}); break;
-      case 8: go(std::integral_constant<int, 8>{}); break;
-      default:
-        launch_nv(H, [&](auto nv) {
-          text_embed_kernel<decltype(nv)::value><<<(B * T + 7) / 8, 256, 0, st>>>(
-              ids, bbox, e->posid.p, ew, e->X[0].p, e->TXT.p, B, T, S, H, d.coord, d.shape, d.ln_eps);
-        });
-    }
-  } else {
-    launch_nv(H, [&](auto nv) {
-      text_embed_kernel<decltype(nv)::value><<<(B * T + 7) / 8, 256, 0, st>>>(
-          ids, bbox, e->posid.p, ew, e->X[0].p, e->TXT.p, B, T, S, H, d.coord, d.shape, d.ln_eps);
-    });
-  }
-  e->launches++;
-  }
-  // pixel-independent work first: on the host path the pixel upload (96 % of the input bytes) overlaps it
-  {
-    keymask_kernel<<<B, e->kv_pitch, 0, st>>>(mask, e->maskadd.p, e->tileflag.p, T, S, e->kv_pitch, e->n_kv_tiles, ATT_BKV,
-                                           e->any_pad.p);
-    BiasArgs ba;
-    ba.bbox = bbox; ba.vis_bbox = e->vis_bbox.p; ba.t1 = e->bias_t1.p; ba.t2 = e->bias_t2.p;
-    ba.lut1 = e->lut1.p; ba.lut2 = e->lut2.p; // every |rel| >= max_distance lands in the last bucket (HF:393-414), so the lookup index is clamped there: far keys
-    // (most of them) then read the same table word, which the shared-memory crossbar broadcasts without a conflict
-    ba.lut1_n = std::min(static_cast<int>(e->lut1.n), d.max_rel + 1);
-    ba.lut2_n = std::min(static_cast<int>(e->lut2.n), d.max_rel2d + 1);
-    ba.maskadd = e->maskadd.p;
-    ba.bins1 = d.rel_bins; ba.bins2 = d.rel2d_bins; ba.heads = heads; ba.t2_pitch = bias_table_pitch(heads); ba.n_text = T; ba.seq = S; ba.pitch = e->bias_pitch;
-    ba.kv_pitch = e->kv_pitch; ba.B = B; ba.out = e->BIAS.p;
-    const size_t smem = bias_build_smem(ba);
-    static bool configured_dev[64] = {};
-    bool& configured = configured_dev[e->device & 63];   // the attribute is per device
-    if (!configured) {
-      CUDA_OK(cudaFuncSetAttribute(bias_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
-    }
-    if (smem > 200 * 1024) throw std::runtime_error("relative-position tables do not fit shared memory");
-    bias_build_kernel<<<e->sms, BIAS_THREADS, smem, st>>>(ba);
-    CUDA_OK(cudaGetLastError());
-    e->launches += 2;
-  }
-  {
-    const int per_doc = e->n_patch * e->kdim_patch / 4;
-    if (e->px_async) CUDA_OK(cudaStreamWaitEvent(st, e->px_wait ? e->px_wait : e->px_ready, 0));
-    im2col_kernel<<<dim3((per_doc + 255) / 256, B), 256, 0, st>>>(px, e->PATCH.p, B, d.image, d.patch, d.channels);
-    e->launches++;
-    GemmArgs ga{};
-    ga.m_dev = nullptr; ga.m_static = B * e->n_patch; ga.N = H; ga.K = e->kdim_patch; ga.bias = e->patch_b.p;
-    ga.out = e->VIS.p; ga.ld_out = H; ga.pos = e->pos_embed.p; ga.n_patch = e->n_patch; ga.n_vis = e->n_vis;
-    launch_gemm<EPI_PATCH>(e, e->bn_h, e->t_patch, e->t_patch_w, ga, st);
-    auto vln = [&](auto nv4) {
-      const int blocks = std::min((B * e->n_vis + 7) / 8, e->sms * 16);
-      visual_ln_vec_kernel<decltype(nv4)::value><<<blocks, 256, 0, st>>>(
-          e->VIS.p, ew, e->X[0].p, e->has_vision_exit ? 1 : 0, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps);
-    };
-    switch (H % 128 == 0 ? H / 128 : 0) {
-      case 1: vln(std::integral_constant<int, 1>{}); break;
-      case 2: vln(std::integral_constant<int, 2>{}); break;
-      case 4: vln(std::integral_constant<int, 4>{}); break;
-      case 6: vln(std::integral_constant<int, 6>{}); break;
-      case 8: vln(std::integral_constant<int, 8>{}); break;
-      default:
-        launch_nv(H, [&](auto nv) {
-          visual_ln_kernel<decltype(nv)::value><<<(B * e->n_vis + 7) / 8, 256, 0, st>>>(
-              e->VIS.p, ew, e->X[0].p, e->has_vision_exit ? 1 : 0, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps);
-        });
-    }
-    e->launches++;
-  }
-  mark(e, "embed", st);
-
+  // ---- bookkeeping of the exit stages
   e->meta_stage = -1;
   int stage = 0;       // index into n_dev / m_dev
   int cur = 0;         // X buffer holding the current layer input
   int sd = 0;          // slot_doc ping-pong index
   int exit_no = 0;     // next exit to evaluate
-  bool x_lo_valid = false;   // X[cur] has a low part (false for the embedding output: a single bf16 rounding)
+  const bool split = e->split;                    // fp32 engine mode: every GEMM operand carries a low part
+  bool x_lo_valid = split;   // X[cur] has a low part (bf16 mode: not for the embedding output, a single bf16 rounding)
 
   auto run_exit = [&](const float* rows, size_t row_stride, const float* ln_w, const float* ln_b,
                       const HeadW& head, bool is_final, const int* rows_slot_src) {
@@ -775,35 +772,180 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     stage += 1; sd ^= 1; exit_no += 1;
   };
 
-  // ---- embedding-level exits, in the reference's order (EE/models/LayoutLMv3.py:465-483 vision_avg: mean of the
-  // visual embeddings after `norm`; :519-534 text_avg: mean of the text embeddings, pads included; :581-606
-  // text_visual_concat: mean over the 709 fused tokens after the model LayerNorm).  The pooled rows are indexed by
-  // document, so each exit reads them through the slot -> document map of the survivors so far.
-  bool any_embedding_exit = false;
-  while (exit_no < E && d.exit_after_layer[exit_no] <= 0) {
-    const int code = d.exit_after_layer[exit_no];
-    const float* pool;
-    if (code == MMEE_EXIT_VISION_AVG) {
-      meanpool_f32_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->VIS.p, e->POOLV.p, e->n_vis, H);
-      pool = e->POOLV.p;
-    } else if (code == MMEE_EXIT_TEXT_AVG) {
-      meanpool_f32_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->TXT.p, e->POOLT.p, T, H);
-      pool = e->POOLT.p;
+  // ---- embeddings
+  EmbedWeights ew;
+  ew.word = e->word.p; ew.type0 = e->type0.p; ew.pos = e->pos.p; ew.x_emb = e->x_emb.p; ew.y_emb = e->y_emb.p;
+  ew.h_emb = e->h_emb.p; ew.w_emb = e->w_emb.p; ew.ln_emb_w = e->ln_emb_w.p; ew.ln_emb_b = e->ln_emb_b.p;
+  ew.ln_model_w = e->ln_model_w.p; ew.ln_model_b = e->ln_model_b.p; ew.ln_vis_w = e->ln_vis_w.p;
+  ew.ln_vis_b = e->ln_vis_b.p; ew.cls_token = e->cls_token.p; ew.pos_embed = e->pos_embed.p;
+  __nv_bfloat16* const x0_lo = split ? e->Xlo[0].p : nullptr;
+
+  // text embeddings of the documents in `slots` (nullptr: all B): X rows (fused, model LayerNorm applied) and / or the
+  // rows before the model LayerNorm (`pre`, indexed by slot)
+  auto text_embed = [&](const int* slots, const int* n_act, __nv_bfloat16* X, __nv_bfloat16* Xlo, float* pre) {
+    TextEmbedArgs ta{};
+    ta.ids = ids; ta.bbox = bbox; ta.posid = e->posid.p; ta.X = X; ta.Xlo = Xlo; ta.pre = pre; ta.slot_doc = slots;
+    ta.n_active_dev = n_act; ta.n_docs = B; ta.n_text = T; ta.seq = S; ta.H = H; ta.coord = d.coord; ta.shape = d.shape;
+    ta.vocab = d.vocab; ta.max_2d = d.max_2d; ta.eps = d.ln_eps; ta.err_flag = e->err_flags.p + 1;
+    const int blocks = (B * T + 7) / 8;
+    auto scalar = [&]() {
+      launch_nv(H, [&](auto nv) { text_embed_kernel<decltype(nv)::value><<<blocks, 256, 0, st>>>(ta, ew); });
+    };
+    if (H % 128 == 0 && d.coord % 4 == 0 && d.shape % 4 == 0) {
+      switch (H / 128) {
+        case 1: text_embed_vec_kernel<1><<<blocks, 256, 0, st>>>(ta, ew); break;
+        case 2: text_embed_vec_kernel<2><<<blocks, 256, 0, st>>>(ta, ew); break;
+        case 4: text_embed_vec_kernel<4><<<blocks, 256, 0, st>>>(ta, ew); break;
+        case 6: text_embed_vec_kernel<6><<<blocks, 256, 0, st>>>(ta, ew); break;
+        case 8: text_embed_vec_kernel<8><<<blocks, 256, 0, st>>>(ta, ew); break;
+        default: scalar();
+      }
     } else {
-      meanpool_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->X[cur].p, e->POOL.p, S, H);
-      pool = e->POOL.p;
+      scalar();
     }
+    CUDA_OK(cudaGetLastError());
     e->launches++;
-    const int* doc_map = e->slot_doc[sd].p;
-    run_exit(pool, H, nullptr, nullptr, e->exit_heads[exit_no], false, doc_map);
-    any_embedding_exit = true;
-  }
-  if (any_embedding_exit) {
-    if (leave) {   // X is still in document order: move the survivors' rows to their slots
-      gather_slots_kernel<<<dim3(32, B), 256, 0, st>>>(e->X[cur].p, e->X[cur ^ 1].p, e->slot_doc[sd].p, e->n_dev.p + stage, S, H);
-      e->launches++;
-      cur ^= 1;
+  };
+  // attention bias of the documents in `slots` (nullptr: all B)
+  auto bias_build = [&](const int* slots, const int* n_act) {
+    BiasArgs ba{};
+    ba.bbox = bbox; ba.vis_bbox = e->vis_bbox.p; ba.t1 = e->bias_t1.p; ba.t2 = e->bias_t2.p;
+    ba.lut1 = e->lut1.p; ba.lut2 = e->lut2.p; // every |rel| >= max_distance lands in the last bucket (HF:393-414), so the lookup index is clamped there: far keys
+    // (most of them) then read the same table word, which the shared-memory crossbar broadcasts without a conflict
+    ba.lut1_n = std::min(static_cast<int>(e->lut1.n), d.max_rel + 1);
+    ba.lut2_n = std::min(static_cast<int>(e->lut2.n), d.max_rel2d + 1);
+    ba.maskadd = e->maskadd.p;
+    ba.bins1 = d.rel_bins; ba.bins2 = d.rel2d_bins; ba.heads = heads; ba.t2_pitch = bias_table_pitch(heads); ba.n_text = T; ba.seq = S; ba.pitch = e->bias_pitch;
+    ba.kv_pitch = e->kv_pitch; ba.B = B; ba.out = e->BIAS.p; ba.slot_doc = slots; ba.n_active_dev = n_act;
+    const size_t smem = bias_build_smem(ba);
+    static bool configured_dev[64] = {};
+    bool& configured = configured_dev[e->device & 63];   // the attribute is per device
+    if (!configured) {
+      CUDA_OK(cudaFuncSetAttribute(bias_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
     }
+    if (smem > 200 * 1024) throw std::runtime_error("relative-position tables do not fit shared memory");
+    if (split) {
+      const int work = S * (e->bias_pitch >> 3);
+      bias_build_split_kernel<<<dim3((work + 255) / 256, B), 256, 0, st>>>(ba, e->bias_tx.p, e->bias_ty.p, e->BIASlo.p);
+    } else {
+      bias_build_kernel<<<e->sms, BIAS_THREADS, smem, st>>>(ba);
+    }
+    CUDA_OK(cudaGetLastError());
+    e->launches++;
+  };
+  // vision branch for all B documents (EE/models/LayoutLMv3.py:358-373): patches -> conv GEMM (+bias, +pos_embed) ->
+  // `norm`; X != nullptr: also the model LayerNorm into the fused rows
+  auto vision = [&](__nv_bfloat16* X, __nv_bfloat16* Xlo, bool keep_normed) {
+    const int per_doc = e->n_patch * e->kdim_patch / 4;
+    if (e->px_async) CUDA_OK(cudaStreamWaitEvent(st, e->px_wait ? e->px_wait : e->px_ready, 0));
+    im2col_kernel<<<dim3((per_doc + 255) / 256, B), 256, 0, st>>>(px, e->PATCH.p, split ? e->PATCHlo.p : nullptr, B,
+                                                                 d.image, d.patch, d.channels);
+    e->launches++;
+    GemmArgs ga{};
+    ga.m_dev = nullptr; ga.m_static = B * e->n_patch; ga.N = H; ga.K = e->kdim_patch; ga.bias = e->patch_b.p;
+    ga.out = e->VIS.p; ga.ld_out = H; ga.pos = e->pos_embed.p; ga.n_patch = e->n_patch; ga.n_vis = e->n_vis;
+    launch_gemm<EPI_PATCH>(e, e->bn_h, e->t_patch, e->t_patch_w, ga, st, &e->t_patch_lo, &e->t_patch_w_lo);
+    const int blocks = std::min((B * e->n_vis + 7) / 8, e->sms * 16);
+    const int wp = keep_normed ? 1 : 0;
+    switch (H % 128 == 0 ? H / 128 : 0) {
+      case 1: visual_ln_vec_kernel<1><<<blocks, 256, 0, st>>>(e->VIS.p, ew, X, Xlo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps); break;
+      case 2: visual_ln_vec_kernel<2><<<blocks, 256, 0, st>>>(e->VIS.p, ew, X, Xlo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps); break;
+      case 4: visual_ln_vec_kernel<4><<<blocks, 256, 0, st>>>(e->VIS.p, ew, X, Xlo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps); break;
+      case 6: visual_ln_vec_kernel<6><<<blocks, 256, 0, st>>>(e->VIS.p, ew, X, Xlo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps); break;
+      case 8: visual_ln_vec_kernel<8><<<blocks, 256, 0, st>>>(e->VIS.p, ew, X, Xlo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps); break;
+      default:
+        launch_nv(H, [&](auto nv) {
+          visual_ln_kernel<decltype(nv)::value><<<(B * e->n_vis + 7) / 8, 256, 0, st>>>(
+              e->VIS.p, ew, X, Xlo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps);
+        });
+    }
+    CUDA_OK(cudaGetLastError());
+    e->launches++;
+  };
+  // X[slot, off .. off+rows) = LN_model(src rows of the survivors)  (H % 128 == 0 is checked at mmee_create)
+  auto embed_finish = [&](const float* src, int rows, const int* map, int off, const int* n_act) {
+    const int blocks = std::min((B * rows + 7) / 8, e->sms * 16);
+    switch (H / 128) {
+      case 1: embed_finish_vec_kernel<1><<<blocks, 256, 0, st>>>(src, rows, map, ew, e->X[cur].p, x0_lo ? e->Xlo[cur].p : nullptr, off, S, H, d.ln_eps, n_act); break;
+      case 2: embed_finish_vec_kernel<2><<<blocks, 256, 0, st>>>(src, rows, map, ew, e->X[cur].p, x0_lo ? e->Xlo[cur].p : nullptr, off, S, H, d.ln_eps, n_act); break;
+      case 4: embed_finish_vec_kernel<4><<<blocks, 256, 0, st>>>(src, rows, map, ew, e->X[cur].p, x0_lo ? e->Xlo[cur].p : nullptr, off, S, H, d.ln_eps, n_act); break;
+      case 6: embed_finish_vec_kernel<6><<<blocks, 256, 0, st>>>(src, rows, map, ew, e->X[cur].p, x0_lo ? e->Xlo[cur].p : nullptr, off, S, H, d.ln_eps, n_act); break;
+      case 8: embed_finish_vec_kernel<8><<<blocks, 256, 0, st>>>(src, rows, map, ew, e->X[cur].p, x0_lo ? e->Xlo[cur].p : nullptr, off, S, H, d.ln_eps, n_act); break;
+      default: throw std::runtime_error("embedding-level exits need hidden % 128 == 0 and hidden <= 1024");
+    }
+    CUDA_OK(cudaGetLastError());
+    e->launches++;
+  };
+
+  if (T > 0) {   // image-only engines (n_text = 0, BASELINE config 5) have no text tokens
+    posid_kernel<<<(B + 7) / 8, 256, 0, st>>>(ids, e->posid.p, B, T, d.pad_id);
+    e->launches++;
+  }
+  keymask_kernel<<<B, e->kv_pitch, 0, st>>>(mask, e->maskadd.p, e->tileflag.p, T, S, e->kv_pitch, e->n_kv_tiles, ATT_BKV,
+                                         e->any_pad.p);
+  e->launches++;
+
+  const bool modality_exits = e->has_vision_exit || e->has_text_exit;
+  bool any_embedding_exit = false;
+  if (!modality_exits) {
+    // pixel-independent work first: on the host path the pixel upload (96 % of the input bytes) overlaps it
+    if (T > 0) text_embed(nullptr, nullptr, e->X[0].p, x0_lo, nullptr);
+    bias_build(nullptr, nullptr);
+    vision(e->X[0].p, x0_lo, false);
+    mark(e, "embed", st);
+    // text_visual_concat exit (EE/models/LayoutLMv3.py:581-606): mean over the 709 fused tokens after the model LayerNorm
+    if (exit_no < E && d.exit_after_layer[exit_no] == 0) {
+      meanpool_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->X[cur].p, x0_lo ? e->Xlo[cur].p : nullptr, e->POOL.p, S, H);
+      e->launches++;
+      run_exit(e->POOL.p, H, nullptr, nullptr, e->exit_heads[exit_no], false, nullptr);
+      any_embedding_exit = true;
+    }
+  } else {
+    // Embedding-level exits in the reference's order (EE/models/LayoutLMv3.py:441-606): vision branch -> vision_avg
+    // exit -> text embeddings -> text_avg exit -> cat + model LayerNorm -> text_visual_concat exit.  In early-exit mode
+    // every step after an exit runs on the survivors only: a document that leaves at vision_avg never gets text
+    // embeddings, fused rows or an attention bias (true skipping).
+    vision(nullptr, nullptr, true);                                   // VIS = norm(cls | patches + pos_embed), all documents
+    if (exit_no < E && d.exit_after_layer[exit_no] == MMEE_EXIT_VISION_AVG) {
+      meanpool_f32_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->VIS.p, e->POOLV.p, e->n_vis, H);   // :465-468, by document
+      e->launches++;
+      run_exit(e->POOLV.p, H, nullptr, nullptr, e->exit_heads[exit_no], false, e->slot_doc[sd].p);
+    }
+    // text embeddings of the survivors (before the model LayerNorm), indexed by their current slot
+    const int* txt_map = nullptr;
+    if (T > 0) text_embed(e->slot_doc[sd].p, e->n_dev.p + stage, nullptr, nullptr, e->TXT.p);
+    if (exit_no < E && d.exit_after_layer[exit_no] == MMEE_EXIT_TEXT_AVG) {
+      meanpool_f32_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->TXT.p, e->POOLT.p, T, H);           // :519-521, by slot
+      e->launches++;
+      run_exit(e->POOLT.p, H, nullptr, nullptr, e->exit_heads[exit_no], false, nullptr);
+      if (leave) txt_map = e->slot_src.p;                             // new slot -> slot the TXT rows were written under
+    }
+    // fused rows of the survivors: [text | visual] -> model LayerNorm (:549-566)
+    if (T > 0) embed_finish(e->TXT.p, T, txt_map, 0, e->n_dev.p + stage);
+    embed_finish(e->VIS.p, e->n_vis, e->slot_doc[sd].p, T, e->n_dev.p + stage);
+    mark(e, "embed", st);
+    if (exit_no < E && d.exit_after_layer[exit_no] == 0) {
+      meanpool_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->X[cur].p, x0_lo ? e->Xlo[cur].p : nullptr, e->POOL.p, S, H);   // by slot
+      e->launches++;
+      run_exit(e->POOL.p, H, nullptr, nullptr, e->exit_heads[exit_no], false, nullptr);
+      any_embedding_exit = true;
+    }
+  }
+  if (any_embedding_exit && leave) {
+    // the concat exit compacted the slots: move the survivors' fused rows to their new slots (new -> old: slot_src)
+    gather_slots_kernel<<<dim3(32, B), 256, 0, st>>>(e->X[cur].p, e->X[cur ^ 1].p, e->slot_src.p, e->n_dev.p + stage, S, H);
+    e->launches++;
+    if (x0_lo) {
+      gather_slots_kernel<<<dim3(32, B), 256, 0, st>>>(e->Xlo[cur].p, e->Xlo[cur ^ 1].p, e->slot_src.p, e->n_dev.p + stage, S, H);
+      e->launches++;
+    }
+    cur ^= 1;
+  }
+  if (modality_exits) {
+    bias_build(e->slot_doc[sd].p, e->n_dev.p + stage);               // survivors only
+    mark(e, "embed", st);                                             // (the embedding-level exits are part of this stage)
+  } else if (any_embedding_exit) {
     mark(e, "exit", st);
   }
 
@@ -812,9 +954,9 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     LayerW& w = e->layers[l];
     const int* mdev = e->m_dev.p + stage;
     GemmArgs ga{};
-    ga.m_dev = mdev; ga.N = 3 * H; ga.K = H; ga.bias = w.bqkv.p; ga.out = e->QK.p; ga.ld_out = 2 * H;
-    ga.vt = e->VT.p; ga.qk_cols = 2 * H; ga.seq = S; ga.kv_pitch = e->kv_pitch; ga.heads = heads;
-    launch_gemm<EPI_QKV>(e, e->bn_qkv, e->t_x[cur], w.t_wqkv, ga, st);
+    ga.m_dev = mdev; ga.N = 3 * H; ga.K = H; ga.bias = w.bqkv.p; ga.out = e->QK.p; ga.out_lo = e->QKlo.p; ga.ld_out = 2 * H;
+    ga.vt = e->VT.p; ga.vt_lo = e->VTlo.p; ga.qk_cols = 2 * H; ga.seq = S; ga.kv_pitch = e->kv_pitch; ga.heads = heads;
+    launch_gemm<EPI_QKV>(e, e->bn_qkv, e->t_x[cur], w.t_wqkv, ga, st, &e->t_x_lo[cur], &w.t_wqkv_lo);
     mark(e, "gemm", st);
 
     if (e->meta_stage != stage) {   // survivors changed since the last layer (or first layer): refresh slot -> (doc, tile flags)
@@ -824,26 +966,33 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
       e->meta_stage = stage;
     }
     AttArgs aa;
-    aa.n_active_dev = e->n_dev.p + stage; aa.slot_meta = e->slot_meta.p; aa.ctx = e->CTX.p; aa.H = H;
-    aa.heads = heads; aa.seq = S; aa.tail_j = e->att_tail_j; aa.skip_pad_q = e->skip_pad_q ? 1 : 0; aa.err_flag = e->att_err.p; aa.trace = e->att_trace.p;
+    aa.n_active_dev = e->n_dev.p + stage; aa.slot_meta = e->slot_meta.p; aa.ctx = e->CTX.p; aa.ctx_lo = e->CTXlo.p; aa.H = H;
+    aa.heads = heads; aa.seq = S; aa.tail_j = e->att_tail_j; aa.skip_pad_q = e->skip_pad_q ? 1 : 0; aa.err_flag = e->err_flags.p; aa.trace = e->att_trace.p;
     {
       static bool configured_dev[64] = {};
       bool& configured = configured_dev[e->device & 63];   // the attribute is per device
       if (!configured) {
-        CUDA_OK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
-        CUDA_OK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
+        CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
+        CUDA_OK(cudaFuncSetAttribute(attention_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
+        CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmemT<true>::DYN_BYTES));
         configured = true;
       }
+      AttMaps am;
+      am.q = e->t_qk; am.k = e->t_k64; am.vt = e->t_vt; am.bias = e->t_bias;
+      if (split) { am.q_lo = e->t_qk_lo; am.k_lo = e->t_k64_lo; am.vt_lo = e->t_vt_lo; am.bias_lo = e->t_bias_lo; }
+      else { am.q_lo = e->t_qk; am.k_lo = e->t_k64; am.vt_lo = e->t_vt; am.bias_lo = e->t_bias; }
       // items are dealt round-robin (item = CTA + k * grid, query tile = item % n_qt): a grid co-prime with n_qt makes
       // every CTA cycle through all query tiles, so the skipped (padded) ones are spread evenly over the CTAs
       const int n_qt = (S + ATT_BQ - 1) / ATT_BQ;
-      int att_grid = e->sms * ATT_CTAS_PER_SM;
+      int att_grid = e->sms * (split ? 1 : ATT_CTAS_PER_SM);
       if (e->skip_pad_q)
         while (att_grid > 1 && std::gcd(att_grid, n_qt) != 1) --att_grid;
-      if (e->trace_on && l == 0)
-        attention_kernel<true><<<att_grid, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(e->t_qk, e->t_k64, e->t_vt, e->t_bias, aa);
+      if (split)
+        attention_kernel<false, true><<<att_grid, ATT_THREADS, AttSmemT<true>::DYN_BYTES, st>>>(am, aa);
+      else if (e->trace_on && l == 0)
+        attention_kernel<true, false><<<att_grid, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(am, aa);
       else
-        attention_kernel<false><<<att_grid, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(e->t_qk, e->t_k64, e->t_vt, e->t_bias, aa);
+        attention_kernel<false, false><<<att_grid, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(am, aa);
       CUDA_OK(cudaGetLastError());
       e->launches++;
     }
@@ -852,19 +1001,19 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     ga = GemmArgs{};
     ga.m_dev = mdev; ga.N = H; ga.K = H; ga.bias = w.bo.p; ga.out = e->Y.p; ga.ld_out = H; ga.resid = e->X[cur].p;
     ga.resid_lo = x_lo_valid ? e->Xlo[cur].p : nullptr;
-    launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_ctx, w.t_wo, ga, st);
+    launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_ctx, w.t_wo, ga, st, &e->t_ctx_lo, &w.t_wo_lo);
     mark(e, "gemm", st);
     launch_ln(e, e->Y.p, e->A1.p, e->A1lo.p, w.ln1_w.p, w.ln1_b.p, B, mdev, nullptr, st, e->slot_doc[sd].p);
     e->launches++;
     mark(e, "norm", st);
 
     ga = GemmArgs{};
-    ga.m_dev = mdev; ga.N = I; ga.K = H; ga.bias = w.bi.p; ga.out = e->MID.p; ga.ld_out = I;
-    launch_gemm<EPI_GELU_BF16>(e, e->bn_i, e->t_a1, w.t_wi, ga, st);
+    ga.m_dev = mdev; ga.N = I; ga.K = H; ga.bias = w.bi.p; ga.out = e->MID.p; ga.out_lo = e->MIDlo.p; ga.ld_out = I;
+    launch_gemm<EPI_GELU_BF16>(e, e->bn_i, e->t_a1, w.t_wi, ga, st, &e->t_a1_lo, &w.t_wi_lo);
     ga = GemmArgs{};
     ga.m_dev = mdev; ga.N = H; ga.K = I; ga.bias = w.bo2.p; ga.out = e->Y.p; ga.ld_out = H; ga.resid = e->A1.p;
     ga.resid_lo = e->A1lo.p;
-    launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_mid, w.t_wo2, ga, st);
+    launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_mid, w.t_wo2, ga, st, &e->t_mid_lo, &w.t_wo2_lo);
     mark(e, "gemm", st);
 
     const bool last = (l == e->L - 1);
@@ -904,15 +1053,20 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   d2d(out->all_criteria, e->all_crit.p, static_cast<size_t>(E1) * B * 4);
   d2d(out->exit_hist, e->hist64.p, static_cast<size_t>(E1) * 8);
   mark(e, "end", st);
+  CUDA_OK(cudaEventRecord(e->last_done, st));
 }
 
-// Guard flag of the attention kernel's online softmax (a deferred rescale factor underflowed; unreachable by
-// construction, see ATT_JUMP in attention.cuh): synchronous calls turn it into an error instead of returning NaNs.
-void check_attention_flag(mmee_engine* e) {
-  int flag = 0;
-  CUDA_OK(cudaMemcpy(&flag, e->att_err.p, sizeof(int), cudaMemcpyDeviceToHost));
-  if (flag) {
-    CUDA_OK(cudaMemset(e->att_err.p, 0, sizeof(int)));
+// Device-side error flags, turned into errors by the synchronous entry points instead of returning garbage:
+// [0] guard of the attention kernel's online softmax (a deferred rescale factor underflowed; unreachable by
+// construction, see ATT_JUMP in attention.cuh); [1] an input_id / bbox coordinate outside its embedding table (the
+// reference raises IndexError there; the kernels clamp, so no out-of-bounds read happens).
+void check_error_flags(mmee_engine* e) {
+  int flags[2] = {0, 0};
+  CUDA_OK(cudaMemcpy(flags, e->err_flags.p, sizeof(flags), cudaMemcpyDeviceToHost));
+  if (flags[0] || flags[1]) {
+    CUDA_OK(cudaMemset(e->err_flags.p, 0, sizeof(flags)));
+    if (flags[1])
+      throw std::runtime_error("input out of range: input_ids must lie in [0, vocab) and bbox coordinates in [0, max_2d)");
     throw std::runtime_error("attention online-softmax guard tripped (rescale factor underflow)");
   }
 }
@@ -976,6 +1130,9 @@ int mmee_create(const mmee_model_desc* desc, int device, int max_batch, mmee_eng
   e->d = d;
   e->device = device;
   e->max_batch = max_batch;
+  if (d.compute_dtype != MMEE_DTYPE_BF16 && d.compute_dtype != MMEE_DTYPE_FP32) throw std::runtime_error("compute_dtype must be MMEE_DTYPE_BF16 or MMEE_DTYPE_FP32");
+  if (d.n_text > 0 && d.n_text + d.pad_id + 1 > d.max_pos) throw std::runtime_error("n_text + pad_id + 1 exceeds max_pos (position table too small)");
+  e->split = d.compute_dtype == MMEE_DTYPE_FP32;
   e->H = d.hidden; e->L = d.layers; e->heads = d.heads; e->I = d.inter; e->T = d.n_text; e->K = d.n_labels;
   e->n_patch = (d.image / d.patch) * (d.image / d.patch);
   e->n_vis = e->n_patch + 1;
@@ -995,6 +1152,11 @@ int mmee_create(const mmee_model_desc* desc, int device, int max_batch, mmee_eng
   e->sms = prop.multiProcessorCount;
   if (const char* sq = getenv("MMEE_SKIP_PAD_Q")) e->skip_pad_q = sq[0] != '0';                  // developer A/B switch
   if (const char* pr = getenv("MMEE_PRECISE_RESIDUAL")) e->precise_residual = pr[0] != '0';   // developer A/B switch
+  if (e->split) {                       // fp32 engine mode: split operands everywhere, full 64-key tiles in attention
+    e->precise_residual = true;
+    e->att_tail_j = -1;
+    e->bias_width = e->bias_pitch;
+  }
   e->bn_h = pick_bn(e->H); e->bn_qkv = pick_bn(e->H) ; e->bn_i = pick_bn(e->I);
   if ((2 * e->H) % e->bn_qkv) e->bn_qkv = 128;
   try {
@@ -1002,6 +1164,7 @@ int mmee_create(const mmee_model_desc* desc, int device, int max_batch, mmee_eng
     CUDA_OK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&e->px_ready, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&e->fwd_start, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&e->last_done, cudaEventDisableTiming));
     allocate(e);
   } catch (...) {
     delete e;
@@ -1071,7 +1234,7 @@ int mmee_forward_device(mmee_engine* e, int B, const int64_t* input_ids, const i
   if (!cuda_stream) {
     CUDA_OK(cudaStreamSynchronize(st));
     collect_profile(e);
-    check_attention_flag(e);
+    check_error_flags(e);
   }
   return 0;
   MMEE_CATCH
@@ -1124,7 +1287,7 @@ int mmee_forward(mmee_engine* e, int B, const int64_t* input_ids, const int64_t*
   if (out->all_criteria) CUDA_OK(cudaMemcpyAsync(out->all_criteria, dv.all_criteria, static_cast<size_t>(E1) * B * 4, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   collect_profile(e);
-  check_attention_flag(e);
+  check_error_flags(e);
   return 0;
   MMEE_CATCH
 }
@@ -1196,7 +1359,7 @@ int mmee_forward_collect(mmee_engine* e, int ticket, const mmee_outputs* out) {
   CUDA_OK(cudaMemcpy(out->exit_index, sl.exit_index.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost));
   if (out->criterion) CUDA_OK(cudaMemcpy(out->criterion, sl.crit.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost));
   if (out->exit_hist) CUDA_OK(cudaMemcpy(out->exit_hist, sl.hist.p, static_cast<size_t>(E1) * 8, cudaMemcpyDeviceToHost));
-  check_attention_flag(e);
+  check_error_flags(e);
   return 0;
   MMEE_CATCH
 }
@@ -1209,7 +1372,7 @@ int mmee_sync(mmee_engine* e, void* cuda_stream) {
   CUDA_OK(cudaSetDevice(e->device));
   CUDA_OK(cudaStreamSynchronize(cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->stream));
   collect_profile(e);
-  check_attention_flag(e);
+  check_error_flags(e);
   return 0;
   MMEE_CATCH
 }
@@ -1244,6 +1407,11 @@ int64_t mmee_debug_read(mmee_engine* e, const char* name, void* host_dst, int64_
     else if (n == "POOL") { src = e->POOL.p; bytes = e->POOL.n * 4; }
     else if (n == "ATT_TRACE") { src = e->att_trace.p; bytes = e->att_trace.n * 8; }
     else if (n == "BIAS") { src = e->BIAS.p; bytes = e->BIAS.n * 2; }
+    else if (n == "BIASlo") { src = e->BIASlo.p; bytes = e->BIASlo.n * 2; }
+    else if (n == "X0lo") { src = e->Xlo[0].p; bytes = e->Xlo[0].n * 2; }
+    else if (n == "QKlo") { src = e->QKlo.p; bytes = e->QKlo.n * 2; }
+    else if (n == "CTXlo") { src = e->CTXlo.p; bytes = e->CTXlo.n * 2; }
+    else if (n == "MIDlo") { src = e->MIDlo.p; bytes = e->MIDlo.n * 2; }
     else throw std::runtime_error("unknown buffer " + n);
     if (static_cast<int64_t>(bytes) > capacity_bytes) bytes = static_cast<size_t>(capacity_bytes);
     CUDA_OK(cudaMemcpy(host_dst, src, bytes, cudaMemcpyDeviceToHost));
@@ -1254,52 +1422,187 @@ int64_t mmee_debug_read(mmee_engine* e, const char* name, void* host_dst, int64_
   }
 }
 
-int mmee_policy_scan(int device, int n_exits_plus1, int64_t n_samples, int n_labels, const double* logits,
-                     const double* temperatures, int criterion, const double* thresholds, int n_thr,
-                     const int64_t* labels, int32_t* exits_out, double* crit_out, int64_t* hist_out,
-                     int64_t* correct_out) {
-  MMEE_TRY
-  const int E1 = n_exits_plus1, K = n_labels;
-  const int64_t N = n_samples;
-  if (!logits || !thresholds || !exits_out) throw std::runtime_error("null argument");
-  if (E1 < 1 || N < 1 || K < 1 || n_thr < 1) throw std::runtime_error("bad shape");
+}  // extern "C"
+
+// Device-resident store of per-exit criteria: the logits go up once, every sweep after that only
+// moves thresholds in and histograms out.
+struct mmee_policy_store {
+  int device = 0, E1 = 0, K = 0, criterion = 0;
+  int64_t N = 0;
+  bool has_labels = false;
+  DevBuf<double> crit;
+  DevBuf<int> argmax;
+  DevBuf<int64_t> labels;
+  DevBuf<unsigned long long> cmask;
+};
+
+namespace {
+
+template <int NE>
+void launch_policy_hist(bool strict, unsigned blocks, size_t smem, const mmee_policy_store* ps, const double* thr,
+                        int64_t n_thr, int cmp, int n_test, int fallback, long long* hist, long long* correct) {
+  const unsigned long long* cm = ps->has_labels ? ps->cmask.p : nullptr;
+  if (strict)
+    policy_hist_kernel<NE, true><<<blocks, POLICY_HIST_THREADS, smem>>>(ps->crit.p, cm, thr, ps->E1, ps->N, n_thr, cmp,
+                                                                        n_test, fallback, hist, correct);
+  else
+    policy_hist_kernel<NE, false><<<blocks, POLICY_HIST_THREADS, smem>>>(ps->crit.p, cm, thr, ps->E1, ps->N, n_thr, cmp,
+                                                                         n_test, fallback, hist, correct);
+}
+
+void policy_store_scan(mmee_policy_store* ps, const double* thresholds, int64_t n_thr, int mode, int32_t* exits_out,
+                       int64_t* hist_out, int64_t* correct_out) {
+  if (!ps || !thresholds) throw std::runtime_error("null argument");
+  if (n_thr < 1) throw std::runtime_error("bad shape");
+  if (mode != 0 && mode != 1) throw std::runtime_error("mode must be 0 (policy.py) or 1 (check_2D_threshold)");
+  if (correct_out && !ps->has_labels) throw std::runtime_error("correct_out needs a store created with labels");
+  CUDA_OK(cudaSetDevice(ps->device));
+  const int E1 = ps->E1;
+  const int64_t N = ps->N;
+  // mode 0: EE/policy.py:28-45 (strict, last exit unconditional); mode 1: EE/thresh.py:184-185 (>=, every exit
+  // tested, nothing fired -> exit 0; the entropy CSF is the negated entropy, EE/large_scale.py:15)
+  const int cmp = mode == 0 ? (ps->criterion == 0 ? POLICY_GT : POLICY_LT) : (ps->criterion == 0 ? POLICY_GE : POLICY_LE);
+  const int n_test = mode == 0 ? E1 - 1 : E1;
+  const int fallback = mode == 0 ? E1 - 1 : 0;
+  std::vector<double> neg;
+  if (mode == 1 && ps->criterion == 1) {            // -H >= thr  <=>  H <= -thr
+    neg.assign(thresholds, thresholds + static_cast<size_t>(n_thr) * E1);
+    for (auto& v : neg) v = -v;
+    thresholds = neg.data();
+  }
+  DevBuf<double> d_thr;
+  d_thr.alloc(static_cast<size_t>(n_thr) * E1);
+  CUDA_OK(cudaMemcpy(d_thr.p, thresholds, static_cast<size_t>(n_thr) * E1 * 8, cudaMemcpyHostToDevice));
+  const bool by_threshold = !exits_out && E1 <= 64 && n_thr >= 2048;
+  if (by_threshold) {
+    // thread = sweep point: no [n_thr, N] index matrix, no atomics (policy_hist_kernel)
+    DevBuf<long long> d_hist, d_correct;
+    d_hist.alloc(static_cast<size_t>(n_thr) * E1);
+    if (correct_out) d_correct.alloc(n_thr);
+    const unsigned blocks = static_cast<unsigned>((n_thr + POLICY_HIST_THREADS - 1) / POLICY_HIST_THREADS);
+    const size_t smem = static_cast<size_t>(POLICY_HIST_CHUNK) * (E1 + 1) * 8;
+    const bool strict = mode == 0;
+    if (E1 <= 8) launch_policy_hist<8>(strict, blocks, smem, ps, d_thr.p, n_thr, cmp, n_test, fallback, d_hist.p, d_correct.p);
+    else if (E1 <= 16) launch_policy_hist<16>(strict, blocks, smem, ps, d_thr.p, n_thr, cmp, n_test, fallback, d_hist.p, d_correct.p);
+    else if (E1 <= 32) launch_policy_hist<32>(strict, blocks, smem, ps, d_thr.p, n_thr, cmp, n_test, fallback, d_hist.p, d_correct.p);
+    else launch_policy_hist<64>(strict, blocks, smem, ps, d_thr.p, n_thr, cmp, n_test, fallback, d_hist.p, d_correct.p);
+    CUDA_OK(cudaGetLastError());
+    if (hist_out) CUDA_OK(cudaMemcpy(hist_out, d_hist.p, static_cast<size_t>(n_thr) * E1 * 8, cudaMemcpyDeviceToHost));
+    if (correct_out) CUDA_OK(cudaMemcpy(correct_out, d_correct.p, static_cast<size_t>(n_thr) * 8, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaDeviceSynchronize());
+    return;
+  }
+  // thread = sample, sweep points along grid.y in chunks of <= 65535 (the grid limit)
+  DevBuf<int32_t> d_exits;
+  DevBuf<unsigned long long> d_hist, d_correct;
+  const int64_t chunk_max = 65535;
+  const int64_t rows_buf = std::min<int64_t>(n_thr, chunk_max);
+  if (exits_out) d_exits.alloc(static_cast<size_t>(rows_buf) * N);
+  d_hist.alloc(static_cast<size_t>(n_thr) * E1, true);
+  d_correct.alloc(n_thr, true);
+  for (int64_t t0 = 0; t0 < n_thr; t0 += chunk_max) {
+    const int64_t nt = std::min<int64_t>(chunk_max, n_thr - t0);
+    policy_scan_kernel<<<dim3(static_cast<unsigned>((N + 255) / 256), static_cast<unsigned>(nt)), 256,
+                         (E1 + 1) * sizeof(unsigned int)>>>(
+        ps->crit.p, ps->argmax.p, d_thr.p + static_cast<size_t>(t0) * E1, ps->has_labels ? ps->labels.p : nullptr, E1, N, cmp,
+        n_test, fallback, exits_out ? d_exits.p : nullptr, d_hist.p + static_cast<size_t>(t0) * E1, d_correct.p + t0);
+    CUDA_OK(cudaGetLastError());
+    if (exits_out)
+      CUDA_OK(cudaMemcpy(exits_out + static_cast<size_t>(t0) * N, d_exits.p, static_cast<size_t>(nt) * N * 4, cudaMemcpyDeviceToHost));
+  }
+  if (hist_out) CUDA_OK(cudaMemcpy(hist_out, d_hist.p, static_cast<size_t>(n_thr) * E1 * 8, cudaMemcpyDeviceToHost));
+  if (correct_out) CUDA_OK(cudaMemcpy(correct_out, d_correct.p, static_cast<size_t>(n_thr) * 8, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaDeviceSynchronize());
+}
+
+mmee_policy_store* policy_store_create(int device, int E1, int64_t N, int K, const double* logits, const double* temperatures,
+                                       int criterion, const int64_t* labels) {
+  if (!logits) throw std::runtime_error("null argument");
+  if (E1 < 1 || N < 1 || K < 1) throw std::runtime_error("bad shape");
   if (criterion != 0 && criterion != 1) throw std::runtime_error("criterion must be 0 (max_confidence) or 1 (entropy)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     throw std::runtime_error("no CUDA device: libmmee has no CPU fallback");
   CUDA_OK(cudaSetDevice(device));
+  std::unique_ptr<mmee_policy_store> ps(new mmee_policy_store());
+  ps->device = device; ps->E1 = E1; ps->N = N; ps->K = K; ps->criterion = criterion;
   const size_t n_log = static_cast<size_t>(E1) * N * K, n_en = static_cast<size_t>(E1) * N;
-  DevBuf<double> d_logits, d_temps, d_thr, d_crit;
-  DevBuf<int> d_arg;
-  DevBuf<int32_t> d_exits;
-  DevBuf<int64_t> d_labels;
-  DevBuf<unsigned long long> d_hist, d_correct;
-  d_logits.alloc(n_log); d_crit.alloc(n_en); d_arg.alloc(n_en);
-  d_thr.alloc(static_cast<size_t>(n_thr) * E1); d_exits.alloc(static_cast<size_t>(n_thr) * N);
-  d_hist.alloc(static_cast<size_t>(n_thr) * E1, true); d_correct.alloc(n_thr, true);
+  DevBuf<double> d_logits, d_temps;
+  d_logits.alloc(n_log);
+  ps->crit.alloc(n_en);
+  ps->argmax.alloc(n_en);
   CUDA_OK(cudaMemcpy(d_logits.p, logits, n_log * 8, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(d_thr.p, thresholds, static_cast<size_t>(n_thr) * E1 * 8, cudaMemcpyHostToDevice));
   if (temperatures) {
     d_temps.alloc(E1);
     CUDA_OK(cudaMemcpy(d_temps.p, temperatures, static_cast<size_t>(E1) * 8, cudaMemcpyHostToDevice));
   }
-  if (labels) {
-    d_labels.alloc(N);
-    CUDA_OK(cudaMemcpy(d_labels.p, labels, static_cast<size_t>(N) * 8, cudaMemcpyHostToDevice));
-  }
   policy_crit_kernel<<<static_cast<unsigned>((n_en + 255) / 256), 256>>>(d_logits.p, d_temps.p, E1, N, K, criterion,
-                                                                          d_crit.p, d_arg.p);
+                                                                          ps->crit.p, ps->argmax.p);
   CUDA_OK(cudaGetLastError());
-  policy_scan_kernel<<<dim3(static_cast<unsigned>((N + 255) / 256), n_thr), 256, (E1 + 1) * sizeof(unsigned int)>>>(
-      d_crit.p, d_arg.p, d_thr.p, d_labels.p, E1, N, criterion, d_exits.p, d_hist.p, d_correct.p);
-  CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaMemcpy(exits_out, d_exits.p, static_cast<size_t>(n_thr) * N * 4, cudaMemcpyDeviceToHost));
-  if (crit_out) CUDA_OK(cudaMemcpy(crit_out, d_crit.p, n_en * 8, cudaMemcpyDeviceToHost));
-  if (hist_out) CUDA_OK(cudaMemcpy(hist_out, d_hist.p, static_cast<size_t>(n_thr) * E1 * 8, cudaMemcpyDeviceToHost));
-  if (correct_out) CUDA_OK(cudaMemcpy(correct_out, d_correct.p, static_cast<size_t>(n_thr) * 8, cudaMemcpyDeviceToHost));
+  if (labels) {
+    ps->has_labels = true;
+    ps->labels.alloc(N);
+    ps->cmask.alloc(N);
+    CUDA_OK(cudaMemcpy(ps->labels.p, labels, static_cast<size_t>(N) * 8, cudaMemcpyHostToDevice));
+    policy_cmask_kernel<<<static_cast<unsigned>((N + 255) / 256), 256>>>(ps->argmax.p, ps->labels.p, E1, N, ps->cmask.p);
+    CUDA_OK(cudaGetLastError());
+  }
+  CUDA_OK(cudaDeviceSynchronize());
+  return ps.release();
+}
+
+}  // namespace
+
+extern "C" {
+
+int mmee_policy_store_create(int device, int n_exits_plus1, int64_t n_samples, int n_labels, const double* logits,
+                             const double* temperatures, int criterion, const int64_t* labels, mmee_policy_store** out) {
+  MMEE_TRY
+  if (!out) throw std::runtime_error("null argument");
+  *out = policy_store_create(device, n_exits_plus1, n_samples, n_labels, logits, temperatures, criterion, labels);
   return 0;
   MMEE_CATCH
 }
+
+void mmee_policy_store_destroy(mmee_policy_store* ps) {
+  if (!ps) return;
+  cudaSetDevice(ps->device);
+  delete ps;
+}
+
+int mmee_policy_store_criteria(mmee_policy_store* ps, double* crit_out) {
+  MMEE_TRY
+  if (!ps || !crit_out) throw std::runtime_error("null argument");
+  CUDA_OK(cudaSetDevice(ps->device));
+  CUDA_OK(cudaMemcpy(crit_out, ps->crit.p, static_cast<size_t>(ps->E1) * ps->N * 8, cudaMemcpyDeviceToHost));
+  return 0;
+  MMEE_CATCH
+}
+
+int mmee_policy_store_scan(mmee_policy_store* ps, const double* thresholds, int64_t n_thr, int mode, int32_t* exits_out,
+                           int64_t* hist_out, int64_t* correct_out) {
+  MMEE_TRY
+  policy_store_scan(ps, thresholds, n_thr, mode, exits_out, hist_out, correct_out);
+  return 0;
+  MMEE_CATCH
+}
+
+int mmee_policy_scan(int device, int n_exits_plus1, int64_t n_samples, int n_labels, const double* logits,
+                     const double* temperatures, int criterion, const double* thresholds, int n_thr,
+                     const int64_t* labels, int32_t* exits_out, double* crit_out, int64_t* hist_out,
+                     int64_t* correct_out) {
+  MMEE_TRY
+  if (!thresholds) throw std::runtime_error("null argument");
+  std::unique_ptr<mmee_policy_store> ps(
+      policy_store_create(device, n_exits_plus1, n_samples, n_labels, logits, temperatures, criterion, labels));
+  policy_store_scan(ps.get(), thresholds, n_thr, 0, exits_out, hist_out, labels ? correct_out : nullptr);
+  if (crit_out)
+    CUDA_OK(cudaMemcpy(crit_out, ps->crit.p, static_cast<size_t>(ps->E1) * ps->N * 8, cudaMemcpyDeviceToHost));
+  return 0;
+  MMEE_CATCH
+}
+
+}  // extern "C"
 
 namespace {
 // shared body of mmee_temperature_fit / mmee_calibration_stats: logits + labels to the device, `iters` Newton
@@ -1361,6 +1664,8 @@ void calibration_run(int device, int E1, int64_t N, int K, const double* logits,
   }
 }
 }  // namespace
+
+extern "C" {
 
 int mmee_temperature_fit(int device, int n_exits_plus1, int64_t n_samples, int n_labels, const double* logits,
                          const int64_t* labels, const double* t_init, int max_iter, double* t_out, double* nll_before,

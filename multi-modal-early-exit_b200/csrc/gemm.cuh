@@ -9,6 +9,11 @@
 // 32x32 chunk through a private swizzled smem slab so global stores are row-contiguous (coalesced).  M (the surviving-token count) is read from
 // device memory so the grid never depends on a host round-trip: grid = #SMs, static round-robin tiles.
 //
+// SPLIT (fp32 engine mode): every operand is a split-bf16 pair (hi = bf16(v), lo = bf16(v - hi): 16 mantissa bits) and
+// the k loop runs three segments into the same fp32 accumulator: A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T (the lo x lo
+// term is below 2^-18 relative and dropped).  Same tiles, same pipeline, three times the MMAs; bf16 outputs are written
+// as (hi, lo) pairs too.  Logit error vs the fp32 reference drops from ~3e-3 to ~5e-6 (tests).
+//
 // Replaces the nn.Linear call sites of HF LayoutLMv3 used by the reference: query/key/value
 // (HF modeling_layoutlmv3.py:245-259), SelfOutput.dense (:300-304), Intermediate.dense + GELU
 // (:495-498), Output.dense (:509-513), and the patch-embedding conv as a GEMM (:70-82).
@@ -38,11 +43,13 @@ struct GemmArgs {
   int N, K;
   const float* bias;       // [N]
   void* out;               // bf16 or f32 [*, ld_out]
+  __nv_bfloat16* out_lo;   // SPLIT: low parts of a bf16 output (same layout as out)
   int ld_out;
   const __nv_bfloat16* resid;   // EPI_RESID_F32: [*, N]
   const __nv_bfloat16* resid_lo;   // optional low part of a split-bf16 residual (resid + resid_lo = 16-bit mantissa), or nullptr
   // EPI_QKV
   __nv_bfloat16* vt;       // [docs][heads][64][kv_pitch]
+  __nv_bfloat16* vt_lo;    // SPLIT: low parts of V^T
   int qk_cols;             // 2*H
   int seq;                 // tokens per document (709)
   int kv_pitch;            // padded token pitch of V^T rows
@@ -118,7 +125,7 @@ __device__ __forceinline__ void gelu_erf_fast2(float x0, float x1, float& y0, fl
 
 // Epilogue of one 128-row x BLOCK_N accumulator for one epilogue warp (TMEM lane quarter `quarter`, column half
 // `half` of PARTS column parts): TMEM -> registers -> (+bias, activation) -> per-warp swizzled smem transpose -> coalesced global stores.
-template <int BLOCK_N, int EPI, int PARTS = 2>
+template <int BLOCK_N, int EPI, int PARTS = 2, bool SPLIT = false>
 __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, int m0, int n0, uint32_t tmem_acc,
                                                    uint8_t* stg, int quarter, int half, int lane) {
       const int row_base = m0 + quarter * 32;     // first row of this warp's 32-row slab
@@ -161,31 +168,40 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
           bool transposed_v = false;
           if constexpr (EPI == EPI_QKV) transposed_v = (n >= args.qk_cols);
           if (!transposed_v) {
-            // bf16 row slab: 64 B per row; thread = row writes 4 x 16 B chunks (chunk ^ ((row>>1)&3): conflict-free)
-            __syncwarp();
+            if constexpr (EPI == EPI_GELU_BF16) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float g[8];
-              if constexpr (EPI == EPI_GELU_BF16) {
-#pragma unroll
-                for (int j = 0; j < 8; j += 2) gelu_erf_fast2(f[q * 8 + j], f[q * 8 + j + 1], g[j], g[j + 1]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) g[j] = f[q * 8 + j];
-              }
-              *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
-                  make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
-                             pack_bf16x2(g[6], g[7]));
+              for (int j = 0; j < 32; j += 2) gelu_erf_fast2(f[j], f[j + 1], f[j], f[j + 1]);
             }
-            __syncwarp();
-            // 4 lanes cover one row's 64 B; 8 rows per store instruction
-            __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(args.out);
+            // bf16 row slab: 64 B per row; thread = row writes 4 x 16 B chunks (chunk ^ ((row>>1)&3): conflict-free)
+            // SPLIT: a second pass moves the low parts f - bf16(f) the same way
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = (lane >> 2) + 8 * i, q = lane & 3;
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
-              if (row_base + r < M)
-                *reinterpret_cast<uint4*>(outp + static_cast<size_t>(row_base + r) * args.ld_out + n + q * 8) = val;
+            for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+              __syncwarp();
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t hi = pack_bf16x2(f[q * 8 + 2 * j], f[q * 8 + 2 * j + 1]);
+                  if (part == 0) {
+                    w[j] = hi;
+                  } else {
+                    const float2 hf = unpack_bf16x2(hi);
+                    w[j] = pack_bf16x2(f[q * 8 + 2 * j] - hf.x, f[q * 8 + 2 * j + 1] - hf.y);
+                  }
+                }
+                *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+              __syncwarp();
+              // 4 lanes cover one row's 64 B; 8 rows per store instruction
+              __nv_bfloat16* outp = part == 0 ? static_cast<__nv_bfloat16*>(args.out) : args.out_lo;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int r = (lane >> 2) + 8 * i, q = lane & 3;
+                const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
+                if (row_base + r < M)
+                  *reinterpret_cast<uint4*>(outp + static_cast<size_t>(row_base + r) * args.ld_out + n + q * 8) = val;
+              }
             }
           } else if (row_ok) {
             // V is stored transposed per (doc, head): vt[d][token] so that P*V takes a K-major B operand.
@@ -194,10 +210,15 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
             const int nv = n - args.qk_cols;        // 32-aligned => one head per chunk
             const int head = nv >> 6;
             const int d0 = nv & 63;
-            __nv_bfloat16* dst = args.vt +
-                (static_cast<size_t>(doc * args.heads + head) * 64 + d0) * args.kv_pitch + tok;
+            const size_t voff = (static_cast<size_t>(doc * args.heads + head) * 64 + d0) * args.kv_pitch + tok;
+            __nv_bfloat16* dst = args.vt + voff;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dst[static_cast<size_t>(j) * args.kv_pitch] = __float2bfloat16_rn(f[j]);
+            for (int j = 0; j < 32; ++j) {
+              const __nv_bfloat16 hi = __float2bfloat16_rn(f[j]);
+              dst[static_cast<size_t>(j) * args.kv_pitch] = hi;
+              if constexpr (SPLIT)
+                args.vt_lo[voff + static_cast<size_t>(j) * args.kv_pitch] = __float2bfloat16_rn(f[j] - __bfloat162float(hi));
+            }
           }
         } else {
           // fp32 row slab: 128 B per row; thread = row writes 8 x 16 B chunks (chunk ^ (row&7): conflict-free)
@@ -233,9 +254,10 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
       }
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool SPLIT = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_a_lo, const __grid_constant__ CUtensorMap tmap_b_lo,
                const GemmArgs args) {
   using SM = GemmSmem<BLOCK_N>;
   constexpr int STAGES = SM::STAGES;
@@ -256,11 +278,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int m_blocks = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int n_blocks = args.N / BLOCK_N;
   const int k_blocks = args.K / GEMM_BLOCK_K;
+  const int k_iters = SPLIT ? 3 * k_blocks : k_blocks;       // SPLIT: A_hi W_hi, A_lo W_hi, A_hi W_lo over the same k range
   const int total_tiles = m_blocks * n_blocks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if constexpr (SPLIT) { tma_prefetch_desc(&tmap_a_lo); tma_prefetch_desc(&tmap_b_lo); }
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -285,13 +309,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_blocks) * GEMM_BLOCK_M;
         const int n0 = (tile % n_blocks) * BLOCK_N;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int it = 0; it < k_iters; ++it) {
+          const int seg = SPLIT ? it / k_blocks : 0, kb = it - seg * k_blocks;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * SM::STAGE_BYTES;
           uint8_t* sb = sa + SM::A_BYTES;
           mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+          tma_load_2d(sa, seg == 1 ? &tmap_a_lo : &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
+          tma_load_2d(sb, seg == 2 ? &tmap_b_lo : &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -308,7 +333,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = 0; kb < k_iters; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
@@ -354,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      gemm_epilogue_warp<BLOCK_N, EPI>(args, M, m0, n0, tmem_base + acc * BLOCK_N, stg, quarter, half, lane);
+      gemm_epilogue_warp<BLOCK_N, EPI, 2, SPLIT>(args, M, m0, n0, tmem_base + acc * BLOCK_N, stg, quarter, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -395,9 +420,10 @@ using GemmPairSmem = GemmPairSmemT<8>;
 template <int EPI>
 __host__ __device__ constexpr int gemm_pair_epi_warps() { return EPI == EPI_RESID_F32 ? 8 : 16; }
 
-template <int EPI>
+template <int EPI, bool SPLIT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + gemm_pair_epi_warps<EPI>() * 32, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_a_lo, const __grid_constant__ CUtensorMap tmap_b_lo,
                     const GemmArgs args) {
   constexpr int EPI_WARPS = gemm_pair_epi_warps<EPI>();
   constexpr int PARTS = EPI_WARPS / 4;
@@ -423,12 +449,14 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int m_blocks = (M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);      // 256-row tiles
   const int n_blocks = args.N / BLOCK_N;
   const int k_blocks = args.K / GEMM_BLOCK_K;
+  const int k_iters = SPLIT ? 3 * k_blocks : k_blocks;       // SPLIT: A_hi W_hi, A_lo W_hi, A_hi W_lo over the same k range
   const int total_tiles = m_blocks * n_blocks;
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if constexpr (SPLIT) { tma_prefetch_desc(&tmap_a_lo); tma_prefetch_desc(&tmap_b_lo); }
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(bars + i, 1);                       // full: the leader's expect_tx arrival
       mbar_init(bars + STAGES + i, 1);              // empty: multicast commit
@@ -453,12 +481,13 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
         const int m0 = (tile / n_blocks) * 2 * GEMM_BLOCK_M + static_cast<int>(rank) * GEMM_BLOCK_M;
         const int n0 = (tile % n_blocks) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int it = 0; it < k_iters; ++it) {
+          const int seg = SPLIT ? it / k_blocks : 0, kb = it - seg * k_blocks;
           mbar_wait(empty_bar + stage * 8, phase ^ 1);
           const uint32_t sa = sb + stage * SM::STAGE_BYTES;
           if (leader) mbar_expect_tx(full_bar + stage * 8, 2 * SM::STAGE_BYTES);   // both CTAs' bytes land on it
-          tma_load_2d_pair(sa, &tmap_a, full_bar + stage * 8, kb * GEMM_BLOCK_K, m0);
-          tma_load_2d_pair(sa + SM::A_BYTES, &tmap_b, full_bar + stage * 8, kb * GEMM_BLOCK_K, n0);
+          tma_load_2d_pair(sa, seg == 1 ? &tmap_a_lo : &tmap_a, full_bar + stage * 8, kb * GEMM_BLOCK_K, m0);
+          tma_load_2d_pair(sa + SM::A_BYTES, seg == 2 ? &tmap_b_lo : &tmap_b, full_bar + stage * 8, kb * GEMM_BLOCK_K, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -475,7 +504,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(tmem_empty + acc * 8, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = 0; kb < k_iters; ++kb) {
           mbar_wait(full_bar + stage * 8, phase);
           tc_fence_after();
           const uint32_t sa = sb + stage * SM::STAGE_BYTES;
@@ -503,7 +532,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int n0 = (tile % n_blocks) * BLOCK_N;
       mbar_wait(tmem_full + acc * 8, acc_phase);
       tc_fence_after();
-      gemm_epilogue_warp<BLOCK_N, EPI, PARTS>(args, M, m0, n0, tmem_base + acc * BLOCK_N, stg, quarter, half, lane);
+      gemm_epilogue_warp<BLOCK_N, EPI, PARTS, SPLIT>(args, M, m0, n0, tmem_base + acc * BLOCK_N, stg, quarter, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tmem_empty + acc * 8, 0);

@@ -141,7 +141,9 @@ struct BiasArgs {
   int lut1_n, lut2_n;
   int bins1, bins2;          // rel_pos_bins, rel_2d_pos_bins
   int heads, t2_pitch, n_text, seq, pitch, kv_pitch, B;
-  __half* out;               // [B][heads][seq][pitch]
+  const int* slot_doc;       // survivors of the embedding-level exits: only their documents get a bias (nullptr: all B)
+  const int* n_active_dev;
+  __half* out;               // [B][heads][seq][pitch], indexed by DOCUMENT (the attention kernel maps slot -> doc)
 };
 
 constexpr int BIAS_THREADS = 768;
@@ -176,7 +178,8 @@ __global__ void __launch_bounds__(BIAS_THREADS, 1) bias_build_kernel(BiasArgs a)
   const int chunks = a.pitch >> 3;                      // threads per row
   const int rows_pp = blockDim.x / chunks;              // rows per pass
   const int passes = (a.seq + rows_pp - 1) / rows_pp;   // per document
-  const int units = a.B * passes;
+  const int n_docs = a.n_active_dev ? *a.n_active_dev : a.B;
+  const int units = n_docs * passes;
   const int u_lo = static_cast<int>(static_cast<long long>(units) * blockIdx.x / gridDim.x);
   const int u_hi = static_cast<int>(static_cast<long long>(units) * (blockIdx.x + 1) / gridDim.x);
   const int rl = threadIdx.x / chunks;                  // row within the pass
@@ -185,8 +188,9 @@ __global__ void __launch_bounds__(BIAS_THREADS, 1) bias_build_kernel(BiasArgs a)
   const int half1 = a.bins1 >> 1, half2 = a.bins2 >> 1;
   int cur_doc = -1;
   for (int u = u_lo; u < u_hi; ++u) {
-    const int doc = u / passes;
-    const int i = (u - doc * passes) * rows_pp + rl;
+    const int dslot = u / passes;
+    const int doc = a.slot_doc ? a.slot_doc[dslot] : dslot;
+    const int i = (u - dslot * passes) * rows_pp + rl;
     if (doc != cur_doc) {                               // (re)load this document's key coordinates
       __syncthreads();
       for (int t = threadIdx.x; t < a.pitch; t += blockDim.x) {
@@ -282,6 +286,64 @@ __global__ void __launch_bounds__(BIAS_THREADS, 1) bias_build_kernel(BiasArgs a)
       *reinterpret_cast<uint4*>(out + (h + 1) * head_stride) =
           make_uint4(pack(v1[0], v1[1]), pack(v1[2], v1[3]), pack(v1[4], v1[5]), pack(v1[6], v1[7]));
     }
+  }
+}
+
+// fp32 engine mode: the same bias as a split-fp16 pair (hi + lo carries 22 mantissa bits), from fp32 tables
+// T1[b1][head], TX[bx][head], TY[by][head] (each already times log2(e)/sqrt(d); 8 KB together, L1-resident) instead of
+// the fp16 2-D table: v = T1 + (TX + TY) in fp32 as the reference sums them (HF:416-458), hi = fp16(v), lo = fp16(v - hi).
+// Not on the throughput path: one thread per (query row, 8 keys), grid.y = survivor slot.
+__global__ void bias_build_split_kernel(BiasArgs a, const float* __restrict__ tx, const float* __restrict__ ty,
+                                        __half* __restrict__ out_lo) {
+  const int dslot = blockIdx.y;
+  if (dslot >= (a.n_active_dev ? *a.n_active_dev : a.B)) return;
+  const int doc = a.slot_doc ? a.slot_doc[dslot] : dslot;
+  const int chunks = a.pitch >> 3;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.seq * chunks) return;
+  const int i = idx / chunks, j0 = (idx - i * chunks) * 8;
+  auto coords = [&](int t, int& pos, int& x0, int& y1) {
+    if (t < a.n_text) {
+      const int64_t* bb = a.bbox + (static_cast<size_t>(doc) * a.n_text + t) * 4;
+      pos = t; x0 = static_cast<int>(bb[0]); y1 = static_cast<int>(bb[3]);
+    } else {
+      const int p = t - a.n_text;
+      pos = p; x0 = a.vis_bbox[p * 4 + 0]; y1 = a.vis_bbox[p * 4 + 3];
+    }
+  };
+  int pi, xi, yi;
+  coords(i, pi, xi, yi);
+  const int half1 = a.bins1 >> 1, half2 = a.bins2 >> 1;
+  int i1[8], ix[8], iy[8];
+  bool masked[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int j = j0 + k;
+    masked[k] = true;
+    i1[k] = ix[k] = iy[k] = 0;
+    if (j < a.seq) {
+      int pj, xj, yj;
+      coords(j, pj, xj, yj);
+      const int r1 = pj - pi, rx = xj - xi, ry = yj - yi;
+      i1[k] = ((r1 > 0 ? half1 : 0) + a.lut1[min(abs(r1), a.lut1_n - 1)]) * a.t2_pitch;
+      ix[k] = ((rx > 0 ? half2 : 0) + a.lut2[min(abs(rx), a.lut2_n - 1)]) * a.t2_pitch;
+      iy[k] = ((ry > 0 ? half2 : 0) + a.lut2[min(abs(ry), a.lut2_n - 1)]) * a.t2_pitch;
+      masked[k] = a.maskadd[static_cast<size_t>(doc) * a.kv_pitch + j] < 0.f;
+    }
+  }
+  const size_t head_stride = static_cast<size_t>(a.seq) * a.pitch;
+  const size_t base = ((static_cast<size_t>(doc) * a.heads) * a.seq + i) * a.pitch + j0;
+  for (int h = 0; h < a.heads; ++h) {
+    __align__(16) __half hi[8], lo[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = __ldg(a.t1 + i1[k] + h) + (__ldg(tx + ix[k] + h) + __ldg(ty + iy[k] + h));
+      if (masked[k]) v = BIAS_MASKED;
+      hi[k] = __float2half_rn(v);
+      lo[k] = masked[k] ? __float2half_rn(0.f) : __float2half_rn(v - __half2float(hi[k]));
+    }
+    *reinterpret_cast<uint4*>(a.out + base + h * head_stride) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(out_lo + base + h * head_stride) = *reinterpret_cast<const uint4*>(lo);
   }
 }
 

@@ -11,6 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MMEE_LIB", os.path.join(_HERE, "libmmee.so"))   # MMEE_LIB: developer override for A/B runs
 MMEE_MAX_EXITS = 64
+COMPUTE_DTYPES = {"bf16": 0, "fp32": 1}      # include/mmee.h MMEE_DTYPE_*
 
 EXPORTED_SYMBOLS = [
     "mmee_create", "mmee_destroy", "mmee_set_weight", "mmee_set_bucket_lut", "mmee_get_bucket_lut",
@@ -18,6 +19,7 @@ EXPORTED_SYMBOLS = [
     "mmee_set_profiling", "mmee_collect_profile", "mmee_last_stage_ms", "mmee_debug_read", "mmee_last_error",
     "mmee_version", "mmee_policy_scan", "mmee_forward_submit", "mmee_forward_collect",
     "mmee_temperature_fit", "mmee_calibration_stats", "mmee_sync",
+    "mmee_policy_store_create", "mmee_policy_store_destroy", "mmee_policy_store_criteria", "mmee_policy_store_scan",
 ]
 
 
@@ -30,7 +32,7 @@ class ModelDesc(C.Structure):
         ("rel_bins", C.c_int), ("max_rel", C.c_int), ("rel2d_bins", C.c_int), ("max_rel2d", C.c_int),
         ("pad_id", C.c_int), ("ln_eps", C.c_float), ("vis_ln_eps", C.c_float),
         ("n_exits", C.c_int), ("exit_after_layer", C.c_int * MMEE_MAX_EXITS),
-        ("head_kind", C.c_int), ("head_layers", C.c_int),
+        ("head_kind", C.c_int), ("head_layers", C.c_int), ("compute_dtype", C.c_int),
     ]
 
 
@@ -96,6 +98,15 @@ def load() -> C.CDLL:
     lib.mmee_policy_scan.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mmee_policy_scan.restype = C.c_int
+    lib.mmee_policy_store_create.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                             C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.mmee_policy_store_create.restype = C.c_int
+    lib.mmee_policy_store_destroy.argtypes = [C.c_void_p]
+    lib.mmee_policy_store_destroy.restype = None
+    lib.mmee_policy_store_criteria.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mmee_policy_store_criteria.restype = C.c_int
+    lib.mmee_policy_store_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mmee_policy_store_scan.restype = C.c_int
     lib.mmee_temperature_fit.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mmee_temperature_fit.restype = C.c_int

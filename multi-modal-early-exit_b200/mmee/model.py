@@ -82,9 +82,15 @@ CRITERION_CODES = {"max_confidence": 0, "entropy": 1, "lte": 2}                 
 
 class B200EEForSequenceClassification:
     def __init__(self, dims: ModelDims, ee: Union[ExitConfig, dict], state_dict: Dict[str, torch.Tensor],
-                 device: int = 0, max_batch: int = 256):
+                 device: int = 0, max_batch: int = 256, dtype: str = "bf16"):
+        """dtype: arithmetic of the dense contractions — "bf16" (default: bf16 tensor-core operands, logits within
+        1e-2 of the reference) or "fp32" (fp32-parity mode: split-bf16 operands, three tensor-core products per
+        contraction, logits within 1e-4; the reference itself computes in fp32, EE/utils.py:160-164)."""
         if isinstance(ee, dict):
             ee = ExitConfig.from_dict(ee)
+        if dtype not in _lib.COMPUTE_DTYPES:
+            raise ValueError(f"dtype must be one of {sorted(_lib.COMPUTE_DTYPES)}")
+        self.dtype = dtype
         dims.check()
         for x in ee.exits:
             if isinstance(x, str) and x not in EMBEDDING_EXIT_CODES:
@@ -109,6 +115,7 @@ class B200EEForSequenceClassification:
             d.exit_after_layer[i] = l
         d.head_kind = 0 if ee.encoder_layer_strategy == "ramp" else 1
         d.head_layers = ee.exit_head_num_layers
+        d.compute_dtype = _lib.COMPUTE_DTYPES[dtype]
         self._h = C.c_void_p()
         _lib.check(self._lib.mmee_create(C.byref(d), device, max_batch, C.byref(self._h)))
         self._load_weights(state_dict)
@@ -132,10 +139,10 @@ class B200EEForSequenceClassification:
         return dims, ee, sd
 
     @classmethod
-    def from_reference(cls, model, device: int = 0, max_batch: int = 256):
+    def from_reference(cls, model, device: int = 0, max_batch: int = 256, dtype: str = "bf16"):
         """Build the engine from a constructed reference model (reads HF dims, `config.EE_config`, weights)."""
         dims, ee, sd = cls.spec_from_reference(model)
-        return cls(dims, ee, sd, device=device, max_batch=max_batch)
+        return cls(dims, ee, sd, device=device, max_batch=max_batch, dtype=dtype)
 
     def _load_weights(self, sd: Dict[str, torch.Tensor]) -> None:
         keep = []

@@ -87,3 +87,50 @@ def exit_policy_vectorised(logits, thresholds, kind="max_confidence"):
     fire[-1, :] = True
     idx = fire.argmax(axis=0).astype(np.int32)
     return idx, logits[idx, np.arange(N)], crit
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Per-exit threshold-vector ("mixture") sweeps: EE/thresh.py:184-233 and EE/large_scale.py:12-128.
+def csf(logits: np.ndarray, name: str = "msp") -> np.ndarray:
+    """CSF_dict of EE/large_scale.py:12-18 / EE/thresh.py:56-62 on [E1, N, K] -> [E1, N]: "msp" = max softmax,
+    "entropy" = NEGATED entropy (so that larger = more confident for both)."""
+    if name == "msp":
+        return softmax64(logits).max(axis=-1)
+    if name == "entropy":
+        return -entropy64(logits)
+    raise NotImplementedError(name)
+
+
+def check_2d_threshold(csf_logits: np.ndarray, threshold: np.ndarray) -> np.ndarray:
+    """EE/thresh.py:184-185 = EE/large_scale.py:42-43: `(CSF_logits >= threshold[:, None]).argmax(0)` — non-strict,
+    every exit tested (the last one too), 0 when no exit fires."""
+    return (csf_logits >= np.asarray(threshold)[:, None]).argmax(0)
+
+
+def opt0_2d(csf_logits: np.ndarray, thresholds_2d: np.ndarray) -> np.ndarray:
+    """EE/thresh.py:188-215 (`opt0_2D`, serial: the reference maps check_2D_threshold over the rows with joblib)."""
+    return np.stack([check_2d_threshold(csf_logits, t) for t in thresholds_2d]).astype(np.int32)
+
+
+def evaluate_exit_logits(logits: np.ndarray, references: np.ndarray, exits: np.ndarray):
+    """EE/thresh.py:225-233 / EE/large_scale.py:87-107: accuracy of the logits at the exit taken, average exit, and
+    the exit distribution."""
+    n = len(references)
+    accuracy = np.mean(np.argmax(logits[exits, np.arange(n)], axis=-1) == references)
+    average_exit = np.mean(exits)
+    dist = {e: np.count_nonzero(exits == e) / n for e in range(logits.shape[0])}
+    return accuracy, average_exit, dist
+
+
+def generate_thresholds(csf_logits: np.ndarray, num_per_exit: int, num_mixtures: int, seed: int = 42) -> np.ndarray:
+    """EE/large_scale.py:46-62: percentile thresholds per exit (last exit's row stays 0), `num_mixtures` random picks
+    (np.random.seed(42), one randint(0, num_per_exit, num_exits) per mixture)."""
+    np.random.seed(seed)
+    num_exits = csf_logits.shape[0]
+    exit_thresholds = np.zeros((num_exits, num_per_exit))
+    percentiles = np.linspace(0, 100, num_per_exit)
+    for exit_id in range(num_exits - 1):
+        for p, perc in enumerate(percentiles):
+            exit_thresholds[exit_id, p] = np.percentile(csf_logits[exit_id], perc)
+    mixture_selection = [np.random.randint(0, num_per_exit, num_exits) for _ in range(num_mixtures)]
+    return exit_thresholds[np.arange(num_exits), mixture_selection]

@@ -34,11 +34,13 @@ def test_struct_layout_matches_header():
     names = [f[0] for f in _lib.ModelDesc._fields_]
     for tok in ["hidden", "layers", "heads", "inter", "n_text", "image", "patch", "channels", "n_labels", "coord",
                 "shape", "vocab", "max_pos", "max_2d", "rel_bins", "max_rel", "rel2d_bins", "max_rel2d", "pad_id",
-                "ln_eps", "vis_ln_eps", "n_exits", "exit_after_layer", "head_kind", "head_layers"]:
+                "ln_eps", "vis_ln_eps", "n_exits", "exit_after_layer", "head_kind", "head_layers", "compute_dtype"]:
         assert tok in names and tok in desc
     pos = [desc.index(t) for t in names]
     assert pos == sorted(pos), "ctypes ModelDesc field order differs from the header"
-    assert C.sizeof(_lib.ModelDesc) == 4 * (21 + 1 + 64 + 2)
+    assert C.sizeof(_lib.ModelDesc) == 4 * (21 + 1 + 64 + 3)
+    assert _lib.COMPUTE_DTYPES == {"bf16": int(re.search(r"#define MMEE_DTYPE_BF16 (\d+)", hdr).group(1)),
+                                   "fp32": int(re.search(r"#define MMEE_DTYPE_FP32 (\d+)", hdr).group(1))}
     assert [f[0] for f in _lib.Outputs._fields_] == ["logits", "exit_index", "criterion", "all_exit_logits",
                                                      "all_head_logits", "all_criteria", "exit_hist"]
 
@@ -212,6 +214,21 @@ def test_policy_host_logic_and_loud_failure():
     metrics = np.array([1 - 0.5 / 0.2, 1 - 0.7 / 0.1, 1 - 0.9 / 0.05])
     want = (metrics - (metrics.min() - 0.1)) / ((metrics.max() + 0.1) - (metrics.min() - 0.1))
     assert np.allclose(thr, want) and (thr > 0).all() and (thr < 1).all()
+    # threshold shapes are explicit, never guessed from a length: 1-D = T global thresholds, always
+    from mmee.policy import _threshold_rows, generate_thresholds
+    assert _threshold_rows(0.5, 4, False).shape == (1, 4)
+    rows = _threshold_rows(np.array([0.1, 0.2, 0.3, 0.4]), 4, False)            # T == E1: still 4 sweep points
+    assert rows.shape == (4, 4) and (rows == rows[:, :1]).all()
+    assert np.array_equal(_threshold_rows(np.array([0.1, 0.2, 0.3, 0.4]), 4, True), [[0.1, 0.2, 0.3, 0.4]])
+    assert _threshold_rows(np.zeros((7, 4)), 4, True).shape == (7, 4)
+    with pytest.raises(ValueError):
+        _threshold_rows(np.zeros(3), 4, True)
+    with pytest.raises(ValueError):
+        _threshold_rows(np.zeros((2, 5)), 4, False)
+    # mixtures: same numpy stream as the reference's generate_thresholds (restated in the oracle)
+    from oracle import policy_port
+    csf = np.random.default_rng(0).random((5, 300))
+    assert np.array_equal(generate_thresholds(csf, 10, 257), policy_port.generate_thresholds(csf, 10, 257))
     with pytest.raises(ValueError):
         policy_scan(np.zeros((3, 4)), 0.5)
     with pytest.raises(ValueError):

@@ -114,3 +114,25 @@ def test_lte_port_matches_reference_golden(name):
     assert r["exit_layer"].tolist() == g["exit_layer"].tolist()
     assert len(set(g["exit_layer"].tolist())) >= 2                   # the case exercises several exits
     assert np.abs(r["logits"].numpy() - g["logits"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("tag", ["mix_a_msp", "mix_a_entropy", "mix_b_msp", "mix_b_entropy"])
+def test_mixture_port_matches_reference_golden(tag):
+    """oracle check_2d_threshold / opt0_2d / generate_thresholds / evaluate_exit_logits against what the reference's
+    own functions produced (tests/golden/make_mixture_golden.py runs them unmodified)."""
+    import sys
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mixtures.npz"))
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_mixture_golden import synthetic_store
+    seed, E1, N, K, npe, M = (int(v) for v in g[tag + "_shape"])
+    lg, labels = synthetic_store(seed, E1, N, K)
+    csf = policy_port.csf(lg, tag.split("_")[-1])
+    assert np.allclose(csf.sum(1), g[tag + "_csf_sum"], rtol=1e-13)
+    thr2d = policy_port.generate_thresholds(csf, npe, M)
+    assert np.array_equal(thr2d, g[tag + "_thr2d"])
+    exits = policy_port.opt0_2d(csf, thr2d)
+    assert np.array_equal(exits, g[tag + "_exits"])
+    for t in (0, 1, M // 2, M - 1):
+        acc, avg, dist = policy_port.evaluate_exit_logits(lg, labels, exits[t])
+        assert acc == g[tag + "_acc"][t] and avg == g[tag + "_avg_exit"][t]
+        assert abs(sum(dist.values()) - 1.0) < 1e-12

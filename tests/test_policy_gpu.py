@@ -63,7 +63,7 @@ def test_entropy_and_per_exit_thresholds_and_edges():
     rng = np.random.default_rng(0)
     lg = rng.normal(size=(5, 777, 16)) * 3
     thr = np.array([0.5, 1.0, 1.5, 2.0, 0.0])
-    res = policy_scan(lg, thr, "entropy")
+    res = policy_scan(lg, thr, "entropy", per_exit=True)
     want, pred, crit = policy_port.exit_policy_vectorised(lg, thr, "entropy")
     ok = _decisive(crit, thr)
     assert np.array_equal(res.exits[0][ok], want[ok])
@@ -90,6 +90,141 @@ def test_accuracy_calibration_heuristic_matches_loop():
     assert np.array_equal(ex, want) and np.array_equal(pred.numpy(), wpred)
     with pytest.raises(Exception, match="calibration_metrics"):
         Policy(lg, {"epsilon": 0.1}).accuracy_calibration_heuristic()
+
+
+def test_sweep_length_equal_to_exit_count_is_still_a_sweep():
+    """14 global thresholds on a 14-exit store are 14 sweep points, not one per-exit vector."""
+    rng = np.random.default_rng(8)
+    E1, N, K = 14, 300, 16
+    lg = rng.normal(size=(E1, N, K)) * 2
+    thrs = np.arange(0.3, 1.0, 0.05)
+    assert len(thrs) == E1
+    res = Policy(lg, {"device": "cpu"}).sweep(thrs)
+    assert res.exits.shape == (E1, N) and res.thresholds.shape == (E1, E1)
+    for t, thr in enumerate(thrs):
+        want, _, crit = policy_port.exit_policy_vectorised(lg, thr, "max_confidence")
+        ok = _decisive(crit, np.full(E1, thr))
+        assert np.array_equal(res.exits[t][ok], want[ok])
+    one = Policy(lg, {"device": "cpu"}).sweep(thrs, per_exit=True)          # the explicit per-exit form
+    assert one.exits.shape == (1, N)
+    want, _, _ = policy_port.exit_policy_vectorised(lg, thrs, "max_confidence")
+    assert np.array_equal(one.exits[0], want)
+
+
+def test_entropy_criterion_is_stable_at_small_temperatures():
+    """exp(x / T) overflows fp64 once max|x| / T > 709; the max-shifted form does not (and equals the
+    reference's formula wherever that one is finite)."""
+    rng = np.random.default_rng(2)
+    lg = rng.normal(size=(3, 200, 16))
+    temps = np.array([1.0, 0.01, 0.001])                # x / T up to ~4000
+    res = policy_scan(lg, 0.5, "entropy", temperatures=temps)
+    assert np.isfinite(res.criteria).all() and (res.criteria >= -1e-12).all()
+    cal = policy_port.temperature_scale(lg, temps)
+    ref = policy_port.entropy64(cal[0])
+    assert np.abs(res.criteria[0] - ref).max() < 1e-12
+    y = cal - cal.max(-1, keepdims=True)
+    shifted = np.log(np.exp(y).sum(-1)) - (y * np.exp(y)).sum(-1) / np.exp(y).sum(-1)
+    assert np.abs(res.criteria - shifted).max() < 1e-12
+    assert (res.exits[0][res.criteria[0] < 0.5] == 0).all()
+
+
+# ------------------------------------------------------------------ mixture sweeps (check_2D_threshold / opt0_2D)
+def _mixture_case(tag):
+    import os
+    import sys
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mixtures.npz"))
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_mixture_golden import synthetic_store
+    seed, E1, N, K, npe, M = (int(v) for v in g[tag + "_shape"])
+    lg, labels = synthetic_store(seed, E1, N, K)
+    return g, lg, labels
+
+
+@pytest.mark.parametrize("tag", ["mix_a_msp", "mix_a_entropy", "mix_b_msp", "mix_b_entropy"])
+def test_mixture_sweep_matches_reference_golden(tag):
+    """Device `check_2D_threshold` semantics (>=, every exit tested, argmax-0 fallback, negated entropy) against the
+    exits / accuracy / average exit the REFERENCE's opt0_2D + evaluate_exit_logits produced
+    (tests/golden/make_mixture_golden.py)."""
+    from mmee.policy import PolicyStore, generate_thresholds
+    g, lg, labels = _mixture_case(tag)
+    crit_name = "max_confidence" if tag.endswith("msp") else "entropy"
+    thr2d, want = g[tag + "_thr2d"], g[tag + "_exits"]
+    N = lg.shape[1]
+    with PolicyStore(lg, crit_name, labels=labels) as st:
+        csf = st.criteria() if crit_name == "max_confidence" else -st.criteria()
+        assert np.allclose(csf.sum(1), g[tag + "_csf_sum"], rtol=1e-12)
+        # the same mixtures as the reference's generate_thresholds from the device criteria (percentiles of the same
+        # values; the last ulp of a criterion can move a percentile by an ulp)
+        mine = generate_thresholds(csf, int(g[tag + "_shape"][4]), int(g[tag + "_shape"][5]))
+        assert mine.shape == thr2d.shape and np.abs(mine - thr2d).max() < 1e-12
+        full = st.scan(thr2d, per_exit=True, mode="check_2D_threshold", want_exits=True)
+        # thresholds ARE criterion values (percentiles): ties are the rule, so a last-ulp difference between the device
+        # exp() and numpy's can flip `>=` for the tied sample; everything else must be identical
+        tie = (np.abs(csf[None, :, :] - thr2d[:, :, None]) < 1e-13).any(axis=1)
+        assert np.array_equal(full.exits[~tie], want[~tie]) and (~tie).mean() > 0.97
+        counts = st.mixture_sweep(thr2d)                                   # counts only (n_thr < 2048: sample-parallel)
+        assert counts.exits is None and np.array_equal(counts.hist, full.hist) and np.array_equal(counts.correct, full.correct)
+        for t in range(thr2d.shape[0]):
+            assert np.array_equal(np.bincount(full.exits[t], minlength=lg.shape[0]), full.hist[t])
+            assert full.correct[t] == int((lg[full.exits[t], np.arange(N)].argmax(-1) == labels).sum())
+        clean = ~tie.any(axis=1)
+        assert np.allclose(full.accuracy[clean], g[tag + "_acc"][clean], atol=1e-15)
+        assert np.allclose(full.mean_exit[clean], g[tag + "_avg_exit"][clean], atol=1e-12)
+
+
+@pytest.mark.parametrize("crit_name", ["max_confidence", "entropy"])
+def test_large_mixture_sweep_equals_oracle(crit_name):
+    """large_scale.py-shaped sweep: 120 000 per-exit threshold vectors (> the 65 535 grid limit, thread-per-mixture
+    kernel, no index matrix) on a 14-exit store against the oracle's check_2d_threshold, row by row."""
+    from mmee.policy import PolicyStore
+    rng = np.random.default_rng(11)
+    E1, N, K, M = 14, 2000, 16, 120000
+    labels = rng.integers(0, K, size=N)
+    lg = rng.normal(size=(E1, N, K)) * np.linspace(0.8, 3.0, E1)[:, None, None]
+    lg[:, np.arange(N), labels] += np.linspace(0.3, 2.5, E1)[:, None]
+    with PolicyStore(lg, crit_name, labels=labels) as st:
+        crit = st.criteria()
+        csf = crit if crit_name == "max_confidence" else -crit
+        assert np.abs(csf - policy_port.csf(lg, "msp" if crit_name == "max_confidence" else "entropy")).max() < 1e-12
+        # thresholds strictly between criterion values: no ties, so the comparison is exact on both sides
+        lo, hi = np.percentile(csf, 1, axis=1), np.percentile(csf, 99, axis=1)
+        thr2d = lo[None, :] + rng.random((M, E1)) * (hi - lo)[None, :]
+        thr2d[rng.random((M, E1)) < 0.05] = np.inf                       # some exits never fire
+        thr2d[:7, :] = np.inf                                            # nothing fires -> argmax of all-False = 0
+        res = st.mixture_sweep(thr2d)
+        assert res.exits is None and res.hist.shape == (M, E1) and (res.hist.sum(1) == N).all()
+        assert (res.hist[:7, 0] == N).all()
+        correct_at = (lg.argmax(-1) == labels[None, :])                  # [E1, N]
+        for t0 in range(0, M, 4000):
+            fire = csf[None, :, :] >= thr2d[t0:t0 + 4000, :, None]       # [m, E1, N]
+            ex = fire.argmax(1)
+            want_hist = (ex[:, :, None] == np.arange(E1)[None, None, :]).sum(1)
+            assert np.array_equal(res.hist[t0:t0 + 4000], want_hist)
+            want_corr = np.take_along_axis(correct_at.T[None, :, :].repeat(ex.shape[0], 0), ex[:, :, None], 2)[:, :, 0].sum(1)
+            assert np.array_equal(res.correct[t0:t0 + 4000], want_corr)
+        # the policy.py mode through the same kernel: strict, last exit unconditional
+        pol = st.scan(thr2d[:5000], per_exit=True, mode="policy", want_exits=False)
+        for t in (0, 7, 100, 4999):
+            want, _, _ = policy_port.exit_policy_vectorised(
+                policy_port.temperature_scale(lg, None), thr2d[t], crit_name)
+            assert np.array_equal(pol.hist[t], np.bincount(want, minlength=E1))
+
+
+def test_sweep_with_exits_beyond_grid_limit():
+    """n_thr > 65 535 with the index matrix requested: chunked over grid.y."""
+    from mmee.policy import PolicyStore
+    rng = np.random.default_rng(4)
+    lg = rng.normal(size=(4, 50, 8)) * 2
+    thrs = np.linspace(0.2, 0.999, 70000)
+    with PolicyStore(lg, "max_confidence") as st:
+        res = st.scan(thrs, want_exits=True)
+        crit = st.criteria()
+    assert res.exits.shape == (70000, 50)
+    for t in (0, 65534, 65535, 65536, 69999):
+        want, _, _ = policy_port.exit_policy_vectorised(lg, thrs[t], "max_confidence")
+        ok = np.abs(crit[:-1] - thrs[t]).min(axis=0) > MARGIN
+        assert np.array_equal(res.exits[t][ok], want[ok])
+        assert np.array_equal(np.bincount(res.exits[t], minlength=4), res.hist[t])
 
 
 # ------------------------------------------------------------------ temperature calibration (mmee_temperature_fit)
