@@ -54,6 +54,9 @@ CASES = {
     "base2_image_only": ("base", {"n_text": 0, "layers": 2}, dict(exits=["text_visual_concat", 1, 2],
                                                                   encoder_layer_strategy="ramp",
                                                                   inference_strategy="max_confidence"), 3, 0, 11, True),
+    # BASELINE.json configs[0] exactly: LayoutLMv3-base, ramps after every layer (+ concat), confidence policy, 16 documents
+    "config0_base_ramp16": ("base", {}, dict(exits=["text_visual_concat"] + list(range(1, 13)),
+                                             encoder_layer_strategy="ramp", inference_strategy="max_confidence"), 16, 2, 21, True),
     # BASELINE.json configs[3]: LayoutLMv3-large, all 24 layers, ramps every 2 layers
     "large24_ramp2": ("large", {}, dict(exits=["text_visual_concat"] + list(range(2, 25, 2)),
                                         encoder_layer_strategy="ramp", inference_strategy="max_confidence"), 2, 0, 7, True),

@@ -1,93 +1,108 @@
 """GPU parity tests (B200): the CUDA engine, called through the C ABI, against the golden vectors
 (outputs of the unmodified reference) and the oracle port / policy port on the same seeded inputs.
 
-Tolerances (north_star): logits within 1e-2 absolute (bf16 engine); predicted classes identical wherever
-the reference's top-2 logit gap exceeds 2x that tolerance; exit indices bit-exact for every document
-whose criterion margin to its threshold exceeds DELTA (stated per criterion below).
+Tolerances (north_star): logits within 1e-2 absolute in the bf16 engine mode and 1e-4 in the fp32 mode; predicted
+classes identical wherever the reference's top-2 logit gap exceeds 2x that tolerance; exit indices bit-exact for
+every document that is decisive in the sense of `helpers.exit_agreement` (the criterion margin to the threshold
+exceeds 1.5x the engine's own criterion error at every exit), with the agreement over ALL documents and the decisive
+fraction printed and — in the fp32 mode, where the error is small enough for the notion to be non-vacuous at the
+calibration temperatures of random-init heads — floored.
 """
 import numpy as np
 import pytest
 import torch
 
-from helpers import ALL_CASES, load_case
+from helpers import ALL_CASES, exit_agreement, load_case, port_forward_chunked
 from mmee import synth
 from mmee.calibration import spread_temperatures, thresholds_for
 from mmee.config import ExitConfig, ModelDims
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_TOL = 1e-2          # bf16 engine, absolute
-DELTA_CONF = 2e-2         # decisive margin on calibrated max-softmax (logit error x 1/T amplification)
-DELTA_ENT = 6e-2          # decisive margin on calibrated entropy (nats)
+LOGIT_TOL = 1e-2          # bf16 engine mode, absolute (north_star)
+LOGIT_TOL_FP32 = 1e-4     # fp32 engine mode, absolute (north_star)
+TOL = {"bf16": LOGIT_TOL, "fp32": LOGIT_TOL_FP32}
 
 _models = {}
 
 
-def _engine(name, max_batch=8):
+def _engine(name, max_batch=8, dtype="bf16"):
     from mmee.model import B200EEForSequenceClassification
 
-    if name not in _models:
+    key = (name, dtype)
+    if key not in _models:
         g, dims, ee, sd, docs = load_case(name)
-        _models[name] = (B200EEForSequenceClassification(dims, ee, sd, device=0, max_batch=max_batch), g, dims, ee, sd, docs)
-    return _models[name]
+        mb = max(max_batch, docs["pixel_values"].shape[0])
+        _models[key] = (B200EEForSequenceClassification(dims, ee, sd, device=0, max_batch=mb, dtype=dtype), g, dims, ee, sd, docs)
+    return _models[key]
 
 
 def _cuda(docs):
     return {k: v.cuda() for k, v in docs.items()}
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
 @pytest.mark.parametrize("name", ALL_CASES)
-def test_dense_logits_match_reference_golden(name):
-    model, g, dims, ee, sd, docs = _engine(name)
+def test_dense_logits_match_reference_golden(name, dtype):
+    model, g, dims, ee, sd, docs = _engine(name, dtype=dtype)
+    tol = TOL[dtype]
     out = model.forward(**_cuda(docs))
     got = out.exit_logits.cpu().numpy()
     ref = g["exit_logits"]
     assert got.shape == ref.shape
     err = np.abs(got - ref).max()
-    print(f"{name}: max|logits - reference| = {err:.3e}")
-    assert err <= LOGIT_TOL
+    print(f"{name} [{dtype}]: max|logits - reference| = {err:.3e} (tolerance {tol:g})")
+    assert err <= tol
     # predicted classes identical wherever the reference's decision is not a numerical tie
     srt = np.sort(ref, axis=-1)
-    decisive = (srt[..., -1] - srt[..., -2]) > 2 * LOGIT_TOL
+    decisive = (srt[..., -1] - srt[..., -2]) > 2 * tol
     assert (got.argmax(-1) == ref.argmax(-1))[decisive].all()
     # raw head outputs (exit_states[j][0]) and the reference-shaped output object
     n_head = g["head_logits"].shape[-1]
     heads = torch.stack([s[0] for s in out.exit_states]).cpu().numpy()
     assert heads.shape == g["head_logits"].shape
-    assert np.abs(heads - g["head_logits"]).max() <= LOGIT_TOL
+    assert np.abs(heads - g["head_logits"]).max() <= tol
     assert len(out.exit_criteria) == ref.shape[0]
-    assert np.abs(torch.stack(out.exit_criteria).cpu().numpy() - g["criteria"]).max() <= 2e-2
-    assert np.abs(out.logits.cpu().numpy() - ref[-1]).max() <= LOGIT_TOL
+    assert np.abs(torch.stack(out.exit_criteria).cpu().numpy() - g["criteria"]).max() <= 2 * tol
+    assert np.abs(out.logits.cpu().numpy() - ref[-1]).max() <= tol
     if ee.encoder_layer_strategy == "gate":
         assert n_head == 2 and len(out.gated_logits) == ref.shape[0] - 1
-        assert np.abs(torch.stack(out.gated_logits).cpu().numpy() - ref[:-1]).max() <= LOGIT_TOL
+        assert np.abs(torch.stack(out.gated_logits).cpu().numpy() - ref[:-1]).max() <= tol
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
 @pytest.mark.parametrize("name", ALL_CASES)
-def test_early_exit_matches_reference_policy(name):
-    """Exit indices vs the reference Policy results stored in the golden (calibrated logits, several thresholds)."""
-    model, g, dims, ee, sd, docs = _engine(name)
+def test_early_exit_matches_reference_policy(name, dtype):
+    """Exit indices of the real early-exit forward vs the reference Policy results stored in the golden (calibrated
+    logits, four thresholds).  Bit-exact on the decisive documents; agreement over ALL documents and the decisive
+    fraction are printed, and floored in the fp32 mode."""
+    model, g, dims, ee, sd, docs = _engine(name, dtype=dtype)
+    tol = TOL[dtype]
     temps = g["temps"]
-    ref_cal = g["exit_logits"].astype(np.float64) / temps[:, None, None]
-    from oracle import policy_port
-
-    conf = policy_port.criterion(ref_cal, "max_confidence")
-    total = agree = 0
+    dense = model.infer(**_cuda(docs), exit_threshold=2.0, criterion="max_confidence", early_exit=False, return_all=True)
+    eng_logits = dense.all_exit_logits.cpu().numpy()
+    total = agree = n_dec = 0
     for thr in (0.1, 0.5, 0.7, 0.9):
         res = model.infer(**_cuda(docs), exit_threshold=thr, temperatures=temps, criterion="max_confidence")
+        st = exit_agreement(res.exits_store, eng_logits, g["exit_logits"], temps, thr, "max_confidence")
         want = g[f"policy_cal_{thr}_exits"]
-        margin = np.abs(conf[:-1] - thr).min(axis=0) if conf.shape[0] > 1 else np.full(want.shape, 1.0)
-        decisive = margin > DELTA_CONF
-        assert (res.exits_store[decisive] == want[decisive]).all(), (thr, res.exits_store, want, margin)
+        assert np.array_equal(st["want"], want)                     # the policy port reproduces the reference's Policy
+        dm = st["decisive_mask"]
+        assert (res.exits_store[dm] == want[dm]).all(), (thr, res.exits_store, want)
         total += want.size
-        agree += int((res.exits_store == want).sum())
+        agree += int(st["agree"].sum())
+        n_dec += int(dm.sum())
         # returned logits are those of the exit taken
-        same = res.exits_store == want
-        assert np.abs(res.predictions.numpy()[same] - g[f"policy_cal_{thr}_pred"][same] * temps[want[same]][:, None]
-                      ).max() <= LOGIT_TOL
+        same = st["agree"]
+        if same.any():
+            assert np.abs(res.predictions.numpy()[same] - g[f"policy_cal_{thr}_pred"][same] * temps[want[same]][:, None]
+                          ).max() <= tol
         assert res.exit_hist.sum() == want.size
         assert abs(sum(res.exit_distribution.values()) - 1.0) < 1e-9
-    print(f"{name}: exit-layer agreement with the reference policy {agree}/{total}")
+    print(f"{name} [{dtype}]: exit-layer agreement with the reference policy: all documents {agree}/{total}, "
+          f"decisive {n_dec}/{total} (all agree)")
+    if dtype == "fp32":
+        assert n_dec >= 0.9 * total and agree >= 0.9 * total
 
 
 @pytest.mark.parametrize("name", ["tiny_ramp_conf", "tiny_gate_ent", "base_gate_ent", "tiny_modality_ramp",
@@ -123,7 +138,7 @@ def test_early_exit_equals_dense_posthoc(name, criterion):
         want, _, crit = policy_port.exit_policy_vectorised(cal, thr, criterion)
         margin = np.abs(crit[:-1] - thr).min(axis=0)
         decisive = margin > 1e-4
-        assert (ee_res.exits_store[decisive] == want[decisive]).all()
+        assert (ee_res.exits_store[decisive] == want[decisive]).all() and decisive.mean() >= 0.5
 
 
 def test_host_path_equals_device_path():
@@ -265,28 +280,98 @@ def policy_port_criterion(logits):
     return policy_port.criterion(logits, "max_confidence")
 
 
-def test_larger_batch_parity_vs_port():
-    """Error tail at a larger batch than the goldens hold: 24 base documents (padded and unpadded), all 14 exits, engine
-    vs the oracle port run on the box's host cores (the port itself is pinned to the reference goldens, max|d| = 0)."""
+@pytest.mark.parametrize("pad,dtype", [(True, "bf16"), (False, "bf16"), (True, "fp32")])
+def test_batch256_parity_and_exit_agreement_vs_port(pad, dtype):
+    """The benchmarked shape: 256 base documents (16 exit groups, two CTA waves of attention, compaction across warps),
+    gates + entropy policy (BASELINE configs[1]), 2 encoder layers + the concat exit so that the oracle port finishes
+    in seconds per chunk.  Dense logits vs the port (itself pinned to the reference goldens, max|d| = 0); real early
+    exit == the post-hoc policy on the engine's dense logits, bit for bit; agreement with the REFERENCE policy
+    (port logits + policy port) over all 256 documents, bit-exact on the decisive ones."""
     from mmee.model import B200EEForSequenceClassification
-    from oracle import port
+    from oracle import policy_port
 
-    dims = ModelDims.base()
-    ee = ExitConfig.from_dict(dict(exits=["text_visual_concat"] + list(range(1, 13)), encoder_layer_strategy="gate",
+    dims = ModelDims.base(layers=2)
+    ee = ExitConfig.from_dict(dict(exits=["text_visual_concat", 1, 2], encoder_layer_strategy="gate",
                                    inference_strategy="entropy"))
     sd = synth.make_state_dict(dims, ee, seed=3)
-    docs = synth.make_docs(dims, 24, seed=31, pad=True)
-    model = B200EEForSequenceClassification(dims, ee, sd, device=0, max_batch=24)
-    got = model.forward(**_cuda(docs)).exit_logits.cpu().numpy()
-    torch.set_num_threads(max(1, (torch.get_num_threads())))
-    want = port.forward(sd, dims, ee, docs)["exit_logits"].numpy()
+    docs = synth.make_docs(dims, 256, seed=31, pad=pad)
+    model = B200EEForSequenceClassification(dims, ee, sd, device=0, max_batch=256, dtype=dtype)
+    dev = _cuda(docs)
+    dense = model.infer(**dev, exit_threshold=-1.0, early_exit=False, return_all=True)
+    got = dense.all_exit_logits.cpu().numpy()
+    want = port_forward_chunked(sd, dims, ee, docs).numpy()
     err = np.abs(got - want)
-    print(f"24 base docs x 14 exits: max|logits - port| = {err.max():.3e}, mean = {err.mean():.3e}")
-    assert err.max() <= LOGIT_TOL
+    print(f"256 base docs (pad={pad}) [{dtype}]: max|logits - port| = {err.max():.3e}, mean = {err.mean():.3e}")
+    assert err.max() <= TOL[dtype]
     srt = np.sort(want, axis=-1)
-    decisive = (srt[..., -1] - srt[..., -2]) > 2 * LOGIT_TOL
-    assert (got.argmax(-1) == want.argmax(-1))[decisive].all()
+    dec = (srt[..., -1] - srt[..., -2]) > 2 * TOL[dtype]
+    assert (got.argmax(-1) == want.argmax(-1))[dec].all()
+    temps = spread_temperatures(want, "entropy")
+    fracs = []
+    for conf_thr in (0.5, 0.7, 0.9):
+        thr = thresholds_for("entropy", conf_thr, dims.n_labels)
+        early = model.infer(**dev, exit_threshold=thr, temperatures=temps, return_all=True)
+        posthoc = model.infer(**dev, exit_threshold=thr, temperatures=temps, early_exit=False)
+        assert np.array_equal(early.exits_store, posthoc.exits_store) and torch.equal(early.logits, posthoc.logits)
+        assert early.exit_hist.sum() == 256
+        mine, _, _ = policy_port.exit_policy_vectorised(policy_port.temperature_scale(got, temps), thr, "entropy")
+        st = exit_agreement(early.exits_store, got, want, temps, thr, "entropy")
+        dm = st["decisive_mask"]
+        assert (early.exits_store[dm] == st["want"][dm]).all()
+        # against the engine's OWN dense logits the only slack is fp32-vs-fp64 criterion arithmetic
+        own_crit = policy_port.criterion(policy_port.temperature_scale(got, temps), "entropy")
+        own_dec = np.abs(own_crit[:-1] - thr).min(axis=0) > 1e-4
+        assert (early.exits_store == mine)[own_dec].all() and own_dec.mean() > 0.99
+        fracs.append((conf_thr, st["all"], st["decisive_frac"], early.exit_hist.tolist()))
+        print(f"  threshold@{conf_thr}: agreement with the reference policy {st['all']:.3f} over all 256 documents, "
+              f"decisive fraction {st['decisive_frac']:.3f}, exits {early.exit_hist.tolist()}")
+    if dtype == "fp32":
+        assert min(f[1] for f in fracs) >= 0.98 and min(f[2] for f in fracs) >= 0.95
+    else:
+        assert min(f[1] for f in fracs) >= 0.80                     # bf16: 3e-3 logit error / T ~ 0.01 (see helpers.exit_agreement)
     model.close()
+
+
+def test_out_of_range_inputs_raise_like_the_reference():
+    """ADVICE r1: the reference raises IndexError for an input_id >= vocab or a bbox coordinate outside [0, max_2d);
+    the engine must not read out of bounds: it clamps on the device and the synchronous call reports an error."""
+    model, g, dims, ee, sd, docs = _engine("tiny_ramp_conf")
+    good = model.forward(**_cuda(docs)).exit_logits.cpu()
+    for field, value in (("input_ids", dims.vocab), ("input_ids", -1), ("bbox", dims.max_2d), ("bbox", -5)):
+        bad = {k: v.clone() for k, v in docs.items()}
+        if field == "input_ids":
+            bad["input_ids"][1, 7] = value
+        else:
+            bad["bbox"][2, 9, 2] = value
+        with pytest.raises(RuntimeError, match="out of range"):
+            model.forward(**_cuda(bad))
+        with pytest.raises(RuntimeError, match="out of range"):
+            model.infer(**bad, exit_threshold=0.5)                      # host path
+    # the engine is still usable and the flag does not stick
+    assert torch.equal(model.forward(**_cuda(docs)).exit_logits.cpu(), good)
+
+
+def test_forwards_on_different_streams_are_ordered():
+    """one set of scratch buffers per engine — a forward on another stream (or the host path, which uses the
+    engine's own stream) must not start before the previous forward has finished with them."""
+    model, g, dims, ee, sd, docs = _engine("base_gate_ent")
+    temps = g["temps"]
+    dev = _cuda(docs)
+    ref = model.infer(**dev, exit_threshold=0.5, temperatures=temps, criterion="max_confidence")
+    ref_flip = model.infer(**{k: v.flip(0) for k, v in dev.items()}, exit_threshold=0.5, temperatures=temps,
+                           criterion="max_confidence")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    flipped = {k: v.flip(0).contiguous() for k, v in dev.items()}
+    torch.cuda.synchronize()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            r1 = model.infer_device(**dev, exit_threshold=0.5, temperatures=temps, criterion="max_confidence")
+        with torch.cuda.stream(s2):                                     # no explicit dependency on s1
+            r2 = model.infer_device(**flipped, exit_threshold=0.5, temperatures=temps, criterion="max_confidence")
+        r3 = model.infer(**docs, exit_threshold=0.5, temperatures=temps, criterion="max_confidence")   # host path
+        torch.cuda.synchronize()
+        assert torch.equal(r1["logits"], ref.logits) and torch.equal(r2["logits"], ref_flip.logits)
+        assert torch.equal(r3.logits, ref.logits.cpu())
 
 
 @pytest.mark.parametrize("n_text,layers", [(77, 2), (200, 1), (448, 1)])
