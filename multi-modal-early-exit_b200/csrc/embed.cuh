@@ -110,6 +110,17 @@ __device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* l
     *reinterpret_cast<uint2*>(lo) = make_uint2(pack_bf16x2(v.x - f01.x, v.y - f01.y), pack_bf16x2(v.z - f23.x, v.w - f23.y));
   }
 }
+// Outputs of a residual-stream row: `X` (bf16, GEMM operand), optional `Xlo` (its low part) and optional `X32` (the
+// unrounded fp32 row: the fp32 engine mode adds the residual from it, so the residual path is exact as in the reference)
+struct RowOut {
+  __nv_bfloat16* X;
+  __nv_bfloat16* Xlo;
+  float* X32;
+};
+__device__ __forceinline__ void store_row4(const RowOut& o, size_t off, const float4& v) {
+  store_split4(o.X + off, o.Xlo ? o.Xlo + off : nullptr, v);
+  if (o.X32) *reinterpret_cast<float4*>(o.X32 + off) = v;
+}
 
 // one warp per text token; X row = slot*seq + t.  Vectorised variant: H = 128*NV4 and the six spatial segments
 // (4 x coord + 2 x shape) are multiples of 4 columns, so every lane gathers whole float4s (base: 6 per table).
@@ -119,6 +130,7 @@ struct TextEmbedArgs {
   const int* posid;        // [B, n_text]
   __nv_bfloat16* X;        // [*, seq, H] fused rows (model LayerNorm applied), row = slot*seq + t; nullptr: not written
   __nv_bfloat16* Xlo;      // optional low part of X (split-bf16, fp32 engine mode)
+  float* X32;              // optional fp32 copy of X (fp32 engine mode: exact residual)
   float* pre;              // [*, n_text, H] text embeddings BEFORE the model LayerNorm (text_avg exit), or nullptr
   const int* slot_doc;     // slot -> document (inputs are read by document, outputs written by slot); nullptr: identity
   const int* n_active_dev; // number of slots (nullptr: n_docs)
@@ -204,7 +216,7 @@ __global__ void text_embed_vec_kernel(const TextEmbedArgs a, EmbedWeights W) {
   warp_layernorm4<NV4>(v, H, W.ln_model_w, W.ln_model_b, eps, lane);
   const size_t orow = (static_cast<size_t>(slot) * seq + t) * H;
 #pragma unroll
-  for (int i = 0; i < NV4; ++i) store_split4(a.X + orow + 4 * (lane + 32 * i), a.Xlo ? a.Xlo + orow + 4 * (lane + 32 * i) : nullptr, v[i]);
+  for (int i = 0; i < NV4; ++i) store_row4(RowOut{a.X, a.Xlo, a.X32}, orow + 4 * (lane + 32 * i), v[i]);
 }
 
 // generic (scalar) variant for shapes the vectorised kernel does not cover (e.g. large: coord 171 / shape 170)
@@ -261,6 +273,7 @@ __global__ void text_embed_kernel(const TextEmbedArgs a, EmbedWeights W) {
       const __nv_bfloat16 hi = __float2bfloat16_rn(v[i]);
       a.X[orow + c] = hi;
       if (a.Xlo) a.Xlo[orow + c] = __float2bfloat16_rn(v[i] - __bfloat162float(hi));
+      if (a.X32) a.X32[orow + c] = v[i];
     }
   }
 }
@@ -288,9 +301,10 @@ __global__ void im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __res
 
 // one warp per visual token (doc, p); VIS rows 1..n_patch hold conv + bias + pos_embed (written by the patch GEMM)
 template <int NV>
-__global__ void visual_ln_kernel(float* __restrict__ VIS, EmbedWeights W, __nv_bfloat16* __restrict__ X,
-                                 __nv_bfloat16* __restrict__ Xlo, int write_pre, int n_docs, int n_vis, int n_text,
-                                 int seq, int H, float eps_vis, float eps) {
+__global__ void visual_ln_kernel(float* __restrict__ VIS, EmbedWeights W, RowOut out, int write_pre, int n_docs,
+                                 int n_vis, int n_text, int seq, int H, float eps_vis, float eps) {
+  __nv_bfloat16* X = out.X;
+  __nv_bfloat16* Xlo = out.Xlo;
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= n_docs * n_vis) return;
   const int lane = threadIdx.x & 31;
@@ -319,17 +333,17 @@ __global__ void visual_ln_kernel(float* __restrict__ VIS, EmbedWeights W, __nv_b
       const __nv_bfloat16 hi = __float2bfloat16_rn(v[i]);
       X[orow + c] = hi;
       if (Xlo) Xlo[orow + c] = __float2bfloat16_rn(v[i] - __bfloat162float(hi));
+      if (out.X32) out.X32[orow + c] = v[i];
     }
   }
 }
 
 // Vectorised variant for H = 128 * NV4: float4 loads, 8 B stores, grid-stride over the visual tokens.
 template <int NV4>
-__global__ void __launch_bounds__(256) visual_ln_vec_kernel(float* __restrict__ VIS, EmbedWeights W,
-                                                            __nv_bfloat16* __restrict__ X,
-                                                            __nv_bfloat16* __restrict__ Xlo, int write_pre, int n_docs,
-                                                            int n_vis, int n_text, int seq, int H, float eps_vis,
-                                                            float eps) {
+__global__ void __launch_bounds__(256) visual_ln_vec_kernel(float* __restrict__ VIS, EmbedWeights W, RowOut out,
+                                                            int write_pre, int n_docs, int n_vis, int n_text, int seq,
+                                                            int H, float eps_vis, float eps) {
+  __nv_bfloat16* X = out.X;
   const int lane = threadIdx.x & 31;
   const int total = n_docs * n_vis;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
@@ -357,8 +371,7 @@ __global__ void __launch_bounds__(256) visual_ln_vec_kernel(float* __restrict__ 
     warp_layernorm4<NV4>(v, H, W.ln_model_w, W.ln_model_b, eps, lane);
     const size_t orow = (static_cast<size_t>(doc) * seq + n_text + p) * H;
 #pragma unroll
-    for (int i = 0; i < NV4; ++i)
-      store_split4(X + orow + 4 * (lane + 32 * i), Xlo ? Xlo + orow + 4 * (lane + 32 * i) : nullptr, v[i]);
+    for (int i = 0; i < NV4; ++i) store_row4(out, orow + 4 * (lane + 32 * i), v[i]);
   }
 }
 
@@ -370,9 +383,8 @@ __global__ void __launch_bounds__(256) visual_ln_vec_kernel(float* __restrict__ 
 template <int NV4>
 __global__ void __launch_bounds__(256) embed_finish_vec_kernel(const float* __restrict__ src, int src_rows,
                                                                const int* __restrict__ src_map, EmbedWeights W,
-                                                               __nv_bfloat16* __restrict__ X,
-                                                               __nv_bfloat16* __restrict__ Xlo, int dst_off, int seq,
-                                                               int H, float eps, const int* __restrict__ n_active_dev) {
+                                                               RowOut out, int dst_off, int seq, int H, float eps,
+                                                               const int* __restrict__ n_active_dev) {
   const int lane = threadIdx.x & 31;
   const int total = *n_active_dev * src_rows;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
@@ -386,13 +398,12 @@ __global__ void __launch_bounds__(256) embed_finish_vec_kernel(const float* __re
     warp_layernorm4<NV4>(v, H, W.ln_model_w, W.ln_model_b, eps, lane);
     const size_t orow = (static_cast<size_t>(slot) * seq + dst_off + r) * H;
 #pragma unroll
-    for (int i = 0; i < NV4; ++i)
-      store_split4(X + orow + 4 * (lane + 32 * i), Xlo ? Xlo + orow + 4 * (lane + 32 * i) : nullptr, v[i]);
+    for (int i = 0; i < NV4; ++i) store_row4(out, orow + 4 * (lane + 32 * i), v[i]);
   }
 }
 
 // pool[doc][c] = mean_t X[doc*seq + t][c]; grid (ceil(H/32), n_docs), block 256 (8 warps stride the tokens)
-__global__ void meanpool_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ Xlo,
+__global__ void meanpool_kernel(const __nv_bfloat16* __restrict__ X, const float* __restrict__ X32,
                                 float* __restrict__ pool, int seq, int H) {
   __shared__ float part[8][33];
   const int doc = blockIdx.y;
@@ -402,7 +413,7 @@ __global__ void meanpool_kernel(const __nv_bfloat16* __restrict__ X, const __nv_
   if (c < H)
     for (int t = w; t < seq; t += 8) {
       const size_t i = (static_cast<size_t>(doc) * seq + t) * H + c;
-      s += Xlo ? __bfloat162float(X[i]) + __bfloat162float(Xlo[i]) : __bfloat162float(X[i]);
+      s += X32 ? X32[i] : __bfloat162float(X[i]);
     }
   part[w][threadIdx.x & 31] = s;
   __syncthreads();

@@ -86,12 +86,13 @@ __global__ void fill_nan_kernel(float* p, size_t n) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i < n) p[i] = __int_as_float(0x7fc00000);
 }
-// X_dst[new slot] = X_src[slot_src[new slot]] (bf16 rows); used only after an embedding-level exit.
-__global__ void gather_slots_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                    const int* __restrict__ slot_src, const int* __restrict__ n_dev, int seq, int H) {
+// dst[new slot] = src[slot_src[new slot]] for whole documents of `doc_bytes` bytes (a multiple of 16); used only after
+// an embedding-level exit.
+__global__ void gather_slots_kernel(const void* __restrict__ src, void* __restrict__ dst,
+                                    const int* __restrict__ slot_src, const int* __restrict__ n_dev, size_t doc_bytes) {
   const int slot = blockIdx.y;
   if (slot >= *n_dev) return;
-  const size_t per_doc = static_cast<size_t>(seq) * H / 8;     // uint4 = 8 bf16
+  const size_t per_doc = doc_bytes / 16;
   const uint4* s = reinterpret_cast<const uint4*>(src) + static_cast<size_t>(slot_src[slot]) * per_doc;
   uint4* d = reinterpret_cast<uint4*>(dst) + static_cast<size_t>(slot) * per_doc;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < per_doc;
@@ -174,6 +175,7 @@ struct mmee_engine {
   DevBuf<__nv_bfloat16> Xlo[2], A1lo;       // low parts of the split-bf16 residual stream (precise_residual)
   DevBuf<__nv_bfloat16> QKlo, VTlo, CTXlo, MIDlo, PATCHlo;   // fp32 engine mode: low parts of every other GEMM / attention operand
   DevBuf<__half> BIASlo;                    // fp32 engine mode: low part of the attention bias
+  DevBuf<float> X32[2], A132;               // fp32 engine mode: the residual stream itself in fp32 (exact residual adds)
   bool precise_residual = true;
   bool skip_pad_q = true;          // attention skips query tiles of padded text tokens; MMEE_SKIP_PAD_Q=0 turns it off
   DevBuf<float> Y, VIS, POOL, POOLV, POOLT, TXT, Z, T0, T1;
@@ -370,15 +372,16 @@ void launch_nv(int H, F&& f) {   // dispatch on values-per-lane for the warp-per
 }
 
 // LayerNorm of the active rows (fp32 Y -> bf16 X [+ low part]); vectorised when H is a multiple of 128
-void launch_ln(mmee_engine* e, const float* Y, __nv_bfloat16* X, __nv_bfloat16* Xlo, const float* w, const float* b,
-               int B, const int* m_dev, const int* slot_src, cudaStream_t st, const int* slot_doc = nullptr) {
+void launch_ln(mmee_engine* e, const float* Y, __nv_bfloat16* X, __nv_bfloat16* Xlo, float* X32, const float* w,
+               const float* b, int B, const int* m_dev, const int* slot_src, cudaStream_t st,
+               const int* slot_doc = nullptr) {
   const int H = e->H, S = e->S;
   if (!e->skip_pad_q) slot_doc = nullptr;          // one developer switch (MMEE_SKIP_PAD_Q) for every padded-row skip
   const float eps = e->d.ln_eps;
   const int rows = B * S;
   auto vec = [&](auto nv4) {
     const int blocks = std::min((rows + 7) / 8, e->sms * 16);      // grid-stride over rows, 8 warps per block
-    ln_rows_vec_kernel<decltype(nv4)::value><<<blocks, 256, 0, st>>>(Y, X, Xlo, w, b, eps, H, S, m_dev, slot_src, slot_doc,
+    ln_rows_vec_kernel<decltype(nv4)::value><<<blocks, 256, 0, st>>>(Y, X, Xlo, X32, w, b, eps, H, S, m_dev, slot_src, slot_doc,
                                                                        e->maskadd.p, e->kv_pitch, e->T, e->any_pad.p);
   };
   switch (H % 128 == 0 ? H / 128 : 0) {
@@ -389,7 +392,7 @@ void launch_ln(mmee_engine* e, const float* Y, __nv_bfloat16* X, __nv_bfloat16* 
     case 8: vec(std::integral_constant<int, 8>{}); break;
     default:
       launch_nv(H, [&](auto nv) {
-        ln_rows_kernel<decltype(nv)::value><<<(rows + 7) / 8, 256, 0, st>>>(Y, X, Xlo, w, b, eps, H, S, m_dev, slot_src);
+        ln_rows_kernel<decltype(nv)::value><<<(rows + 7) / 8, 256, 0, st>>>(Y, X, Xlo, X32, w, b, eps, H, S, m_dev, slot_src);
       });
   }
   CUDA_OK(cudaGetLastError());
@@ -582,6 +585,7 @@ void allocate(mmee_engine* e) {
     e->VTlo.alloc(static_cast<size_t>(B) * heads * 64 * e->kv_pitch, true);
     e->CTXlo.alloc(M * H, true);
     e->MIDlo.alloc(M * I, true);
+    e->X32[0].alloc(M * H, true); e->X32[1].alloc(M * H, true); e->A132.alloc(M * H, true);
   }
   e->MID.alloc(M * I, true);
   e->Y.alloc(M * H, true);
@@ -778,13 +782,14 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   ew.h_emb = e->h_emb.p; ew.w_emb = e->w_emb.p; ew.ln_emb_w = e->ln_emb_w.p; ew.ln_emb_b = e->ln_emb_b.p;
   ew.ln_model_w = e->ln_model_w.p; ew.ln_model_b = e->ln_model_b.p; ew.ln_vis_w = e->ln_vis_w.p;
   ew.ln_vis_b = e->ln_vis_b.p; ew.cls_token = e->cls_token.p; ew.pos_embed = e->pos_embed.p;
-  __nv_bfloat16* const x0_lo = split ? e->Xlo[0].p : nullptr;
+  // residual-stream outputs of the embedding stage: bf16 row (+ low part and fp32 copy in the fp32 engine mode)
+  auto xout = [&](int buf) { return RowOut{e->X[buf].p, split ? e->Xlo[buf].p : nullptr, split ? e->X32[buf].p : nullptr}; };
 
   // text embeddings of the documents in `slots` (nullptr: all B): X rows (fused, model LayerNorm applied) and / or the
   // rows before the model LayerNorm (`pre`, indexed by slot)
-  auto text_embed = [&](const int* slots, const int* n_act, __nv_bfloat16* X, __nv_bfloat16* Xlo, float* pre) {
+  auto text_embed = [&](const int* slots, const int* n_act, RowOut xo, float* pre) {
     TextEmbedArgs ta{};
-    ta.ids = ids; ta.bbox = bbox; ta.posid = e->posid.p; ta.X = X; ta.Xlo = Xlo; ta.pre = pre; ta.slot_doc = slots;
+    ta.ids = ids; ta.bbox = bbox; ta.posid = e->posid.p; ta.X = xo.X; ta.Xlo = xo.Xlo; ta.X32 = xo.X32; ta.pre = pre; ta.slot_doc = slots;
     ta.n_active_dev = n_act; ta.n_docs = B; ta.n_text = T; ta.seq = S; ta.H = H; ta.coord = d.coord; ta.shape = d.shape;
     ta.vocab = d.vocab; ta.max_2d = d.max_2d; ta.eps = d.ln_eps; ta.err_flag = e->err_flags.p + 1;
     const int blocks = (B * T + 7) / 8;
@@ -836,7 +841,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   };
   // vision branch for all B documents (EE/models/LayoutLMv3.py:358-373): patches -> conv GEMM (+bias, +pos_embed) ->
   // `norm`; X != nullptr: also the model LayerNorm into the fused rows
-  auto vision = [&](__nv_bfloat16* X, __nv_bfloat16* Xlo, bool keep_normed) {
+  auto vision = [&](RowOut xo, bool keep_normed) {
     const int per_doc = e->n_patch * e->kdim_patch / 4;
     if (e->px_async) CUDA_OK(cudaStreamWaitEvent(st, e->px_wait ? e->px_wait : e->px_ready, 0));
     im2col_kernel<<<dim3((per_doc + 255) / 256, B), 256, 0, st>>>(px, e->PATCH.p, split ? e->PATCHlo.p : nullptr, B,
@@ -849,15 +854,15 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     const int blocks = std::min((B * e->n_vis + 7) / 8, e->sms * 16);
     const int wp = keep_normed ? 1 : 0;
     switch (H % 128 == 0 ? H / 128 : 0) {
-      case 1: visual_ln_vec_kernel<1><<<blocks, 256, 0, st>>>(e->VIS.p, ew, X, Xlo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps); break;
-      case 2: visual_ln_vec_kernel<2><<<blocks, 256, 0, st>>>(e->VIS.p, ew, X, Xlo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps); break;
-      case 4: visual_ln_vec_kernel<4><<<blocks, 256, 0, st>>>(e->VIS.p, ew, X, Xlo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps); break;
-      case 6: visual_ln_vec_kernel<6><<<blocks, 256, 0, st>>>(e->VIS.p, ew, X, Xlo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps); break;
-      case 8: visual_ln_vec_kernel<8><<<blocks, 256, 0, st>>>(e->VIS.p, ew, X, Xlo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps); break;
+      case 1: visual_ln_vec_kernel<1><<<blocks, 256, 0, st>>>(e->VIS.p, ew, xo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps); break;
+      case 2: visual_ln_vec_kernel<2><<<blocks, 256, 0, st>>>(e->VIS.p, ew, xo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps); break;
+      case 4: visual_ln_vec_kernel<4><<<blocks, 256, 0, st>>>(e->VIS.p, ew, xo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps); break;
+      case 6: visual_ln_vec_kernel<6><<<blocks, 256, 0, st>>>(e->VIS.p, ew, xo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps); break;
+      case 8: visual_ln_vec_kernel<8><<<blocks, 256, 0, st>>>(e->VIS.p, ew, xo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps); break;
       default:
         launch_nv(H, [&](auto nv) {
           visual_ln_kernel<decltype(nv)::value><<<(B * e->n_vis + 7) / 8, 256, 0, st>>>(
-              e->VIS.p, ew, X, Xlo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps);
+              e->VIS.p, ew, xo, wp, B, e->n_vis, T, S, H, d.vis_ln_eps, d.ln_eps);
         });
     }
     CUDA_OK(cudaGetLastError());
@@ -867,11 +872,11 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   auto embed_finish = [&](const float* src, int rows, const int* map, int off, const int* n_act) {
     const int blocks = std::min((B * rows + 7) / 8, e->sms * 16);
     switch (H / 128) {
-      case 1: embed_finish_vec_kernel<1><<<blocks, 256, 0, st>>>(src, rows, map, ew, e->X[cur].p, x0_lo ? e->Xlo[cur].p : nullptr, off, S, H, d.ln_eps, n_act); break;
-      case 2: embed_finish_vec_kernel<2><<<blocks, 256, 0, st>>>(src, rows, map, ew, e->X[cur].p, x0_lo ? e->Xlo[cur].p : nullptr, off, S, H, d.ln_eps, n_act); break;
-      case 4: embed_finish_vec_kernel<4><<<blocks, 256, 0, st>>>(src, rows, map, ew, e->X[cur].p, x0_lo ? e->Xlo[cur].p : nullptr, off, S, H, d.ln_eps, n_act); break;
-      case 6: embed_finish_vec_kernel<6><<<blocks, 256, 0, st>>>(src, rows, map, ew, e->X[cur].p, x0_lo ? e->Xlo[cur].p : nullptr, off, S, H, d.ln_eps, n_act); break;
-      case 8: embed_finish_vec_kernel<8><<<blocks, 256, 0, st>>>(src, rows, map, ew, e->X[cur].p, x0_lo ? e->Xlo[cur].p : nullptr, off, S, H, d.ln_eps, n_act); break;
+      case 1: embed_finish_vec_kernel<1><<<blocks, 256, 0, st>>>(src, rows, map, ew, xout(cur), off, S, H, d.ln_eps, n_act); break;
+      case 2: embed_finish_vec_kernel<2><<<blocks, 256, 0, st>>>(src, rows, map, ew, xout(cur), off, S, H, d.ln_eps, n_act); break;
+      case 4: embed_finish_vec_kernel<4><<<blocks, 256, 0, st>>>(src, rows, map, ew, xout(cur), off, S, H, d.ln_eps, n_act); break;
+      case 6: embed_finish_vec_kernel<6><<<blocks, 256, 0, st>>>(src, rows, map, ew, xout(cur), off, S, H, d.ln_eps, n_act); break;
+      case 8: embed_finish_vec_kernel<8><<<blocks, 256, 0, st>>>(src, rows, map, ew, xout(cur), off, S, H, d.ln_eps, n_act); break;
       default: throw std::runtime_error("embedding-level exits need hidden % 128 == 0 and hidden <= 1024");
     }
     CUDA_OK(cudaGetLastError());
@@ -890,13 +895,13 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   bool any_embedding_exit = false;
   if (!modality_exits) {
     // pixel-independent work first: on the host path the pixel upload (96 % of the input bytes) overlaps it
-    if (T > 0) text_embed(nullptr, nullptr, e->X[0].p, x0_lo, nullptr);
+    if (T > 0) text_embed(nullptr, nullptr, xout(0), nullptr);
     bias_build(nullptr, nullptr);
-    vision(e->X[0].p, x0_lo, false);
+    vision(xout(0), false);
     mark(e, "embed", st);
     // text_visual_concat exit (EE/models/LayoutLMv3.py:581-606): mean over the 709 fused tokens after the model LayerNorm
     if (exit_no < E && d.exit_after_layer[exit_no] == 0) {
-      meanpool_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->X[cur].p, x0_lo ? e->Xlo[cur].p : nullptr, e->POOL.p, S, H);
+      meanpool_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->X[cur].p, split ? e->X32[cur].p : nullptr, e->POOL.p, S, H);
       e->launches++;
       run_exit(e->POOL.p, H, nullptr, nullptr, e->exit_heads[exit_no], false, nullptr);
       any_embedding_exit = true;
@@ -906,7 +911,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     // exit -> text embeddings -> text_avg exit -> cat + model LayerNorm -> text_visual_concat exit.  In early-exit mode
     // every step after an exit runs on the survivors only: a document that leaves at vision_avg never gets text
     // embeddings, fused rows or an attention bias (true skipping).
-    vision(nullptr, nullptr, true);                                   // VIS = norm(cls | patches + pos_embed), all documents
+    vision(RowOut{nullptr, nullptr, nullptr}, true);                                   // VIS = norm(cls | patches + pos_embed), all documents
     if (exit_no < E && d.exit_after_layer[exit_no] == MMEE_EXIT_VISION_AVG) {
       meanpool_f32_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->VIS.p, e->POOLV.p, e->n_vis, H);   // :465-468, by document
       e->launches++;
@@ -914,7 +919,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     }
     // text embeddings of the survivors (before the model LayerNorm), indexed by their current slot
     const int* txt_map = nullptr;
-    if (T > 0) text_embed(e->slot_doc[sd].p, e->n_dev.p + stage, nullptr, nullptr, e->TXT.p);
+    if (T > 0) text_embed(e->slot_doc[sd].p, e->n_dev.p + stage, RowOut{nullptr, nullptr, nullptr}, e->TXT.p);
     if (exit_no < E && d.exit_after_layer[exit_no] == MMEE_EXIT_TEXT_AVG) {
       meanpool_f32_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->TXT.p, e->POOLT.p, T, H);           // :519-521, by slot
       e->launches++;
@@ -926,7 +931,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     embed_finish(e->VIS.p, e->n_vis, e->slot_doc[sd].p, T, e->n_dev.p + stage);
     mark(e, "embed", st);
     if (exit_no < E && d.exit_after_layer[exit_no] == 0) {
-      meanpool_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->X[cur].p, x0_lo ? e->Xlo[cur].p : nullptr, e->POOL.p, S, H);   // by slot
+      meanpool_kernel<<<dim3((H + 31) / 32, B), 256, 0, st>>>(e->X[cur].p, split ? e->X32[cur].p : nullptr, e->POOL.p, S, H);   // by slot
       e->launches++;
       run_exit(e->POOL.p, H, nullptr, nullptr, e->exit_heads[exit_no], false, nullptr);
       any_embedding_exit = true;
@@ -934,11 +939,13 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   }
   if (any_embedding_exit && leave) {
     // the concat exit compacted the slots: move the survivors' fused rows to their new slots (new -> old: slot_src)
-    gather_slots_kernel<<<dim3(32, B), 256, 0, st>>>(e->X[cur].p, e->X[cur ^ 1].p, e->slot_src.p, e->n_dev.p + stage, S, H);
+    const size_t row_elems = static_cast<size_t>(S) * H;
+    gather_slots_kernel<<<dim3(32, B), 256, 0, st>>>(e->X[cur].p, e->X[cur ^ 1].p, e->slot_src.p, e->n_dev.p + stage, row_elems * 2);
     e->launches++;
-    if (x0_lo) {
-      gather_slots_kernel<<<dim3(32, B), 256, 0, st>>>(e->Xlo[cur].p, e->Xlo[cur ^ 1].p, e->slot_src.p, e->n_dev.p + stage, S, H);
-      e->launches++;
+    if (split) {
+      gather_slots_kernel<<<dim3(32, B), 256, 0, st>>>(e->Xlo[cur].p, e->Xlo[cur ^ 1].p, e->slot_src.p, e->n_dev.p + stage, row_elems * 2);
+      gather_slots_kernel<<<dim3(32, B), 256, 0, st>>>(e->X32[cur].p, e->X32[cur ^ 1].p, e->slot_src.p, e->n_dev.p + stage, row_elems * 4);
+      e->launches += 2;
     }
     cur ^= 1;
   }
@@ -1001,9 +1008,10 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     ga = GemmArgs{};
     ga.m_dev = mdev; ga.N = H; ga.K = H; ga.bias = w.bo.p; ga.out = e->Y.p; ga.ld_out = H; ga.resid = e->X[cur].p;
     ga.resid_lo = x_lo_valid ? e->Xlo[cur].p : nullptr;
+    ga.resid_f32 = split ? e->X32[cur].p : nullptr;
     launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_ctx, w.t_wo, ga, st, &e->t_ctx_lo, &w.t_wo_lo);
     mark(e, "gemm", st);
-    launch_ln(e, e->Y.p, e->A1.p, e->A1lo.p, w.ln1_w.p, w.ln1_b.p, B, mdev, nullptr, st, e->slot_doc[sd].p);
+    launch_ln(e, e->Y.p, e->A1.p, e->A1lo.p, split ? e->A132.p : nullptr, w.ln1_w.p, w.ln1_b.p, B, mdev, nullptr, st, e->slot_doc[sd].p);
     e->launches++;
     mark(e, "norm", st);
 
@@ -1013,6 +1021,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     ga = GemmArgs{};
     ga.m_dev = mdev; ga.N = H; ga.K = I; ga.bias = w.bo2.p; ga.out = e->Y.p; ga.ld_out = H; ga.resid = e->A1.p;
     ga.resid_lo = e->A1lo.p;
+    ga.resid_f32 = split ? e->A132.p : nullptr;
     launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_mid, w.t_wo2, ga, st, &e->t_mid_lo, &w.t_wo2_lo);
     mark(e, "gemm", st);
 
@@ -1025,8 +1034,8 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
       mark(e, "exit", st);
     }
     if (!last) {
-      launch_ln(e, e->Y.p, e->X[cur ^ 1].p, e->Xlo[cur ^ 1].p, w.ln2_w.p, w.ln2_b.p, B, e->m_dev.p + stage, ln_src, st,
-                e->slot_doc[sd].p);
+      launch_ln(e, e->Y.p, e->X[cur ^ 1].p, e->Xlo[cur ^ 1].p, split ? e->X32[cur ^ 1].p : nullptr, w.ln2_w.p, w.ln2_b.p, B,
+                e->m_dev.p + stage, ln_src, st, e->slot_doc[sd].p);
       e->launches++;
       cur ^= 1;
       x_lo_valid = e->precise_residual;

@@ -47,6 +47,7 @@ struct GemmArgs {
   int ld_out;
   const __nv_bfloat16* resid;   // EPI_RESID_F32: [*, N]
   const __nv_bfloat16* resid_lo;   // optional low part of a split-bf16 residual (resid + resid_lo = 16-bit mantissa), or nullptr
+  const float* resid_f32;          // fp32 engine mode: the residual itself in fp32 (exact, as the reference adds it); replaces resid / resid_lo
   // EPI_QKV
   __nv_bfloat16* vt;       // [docs][heads][64][kv_pitch]
   __nv_bfloat16* vt_lo;    // SPLIT: low parts of V^T
@@ -142,8 +143,14 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
           for (int i = 0; i < 8; ++i) {
             const int grow = row_base + (lane >> 3) + 4 * i;
             const size_t off = static_cast<size_t>(grow) * args.N + n + (lane & 7) * 4;
-            rs[i] = (grow < M) ? __ldg(reinterpret_cast<const uint2*>(args.resid + off)) : make_uint2(0u, 0u);
-            rl[i] = (grow < M && args.resid_lo) ? __ldg(reinterpret_cast<const uint2*>(args.resid_lo + off)) : make_uint2(0u, 0u);
+            if (SPLIT && args.resid_f32) {          // (rs, rl) hold the four fp32 residuals of this lane's 16 B
+              const float4 r4 = (grow < M) ? __ldg(reinterpret_cast<const float4*>(args.resid_f32 + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              rs[i] = make_uint2(__float_as_uint(r4.x), __float_as_uint(r4.y));
+              rl[i] = make_uint2(__float_as_uint(r4.z), __float_as_uint(r4.w));
+            } else {
+              rs[i] = (grow < M) ? __ldg(reinterpret_cast<const uint2*>(args.resid + off)) : make_uint2(0u, 0u);
+              rl[i] = (grow < M && args.resid_lo) ? __ldg(reinterpret_cast<const uint2*>(args.resid_lo + off)) : make_uint2(0u, 0u);
+            }
           }
         }
         uint32_t v[32];
@@ -236,9 +243,14 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
             const int grow = row_base + r;
             if (grow < M) {
               if constexpr (EPI == EPI_RESID_F32) {
-                const float2 r0 = unpack_bf16x2(rs[i].x), r1 = unpack_bf16x2(rs[i].y);
-                const float2 l0 = unpack_bf16x2(rl[i].x), l1 = unpack_bf16x2(rl[i].y);
-                val.x += r0.x + l0.x; val.y += r0.y + l0.y; val.z += r1.x + l1.x; val.w += r1.y + l1.y;
+                if (SPLIT && args.resid_f32) {
+                  val.x += __uint_as_float(rs[i].x); val.y += __uint_as_float(rs[i].y);
+                  val.z += __uint_as_float(rl[i].x); val.w += __uint_as_float(rl[i].y);
+                } else {
+                  const float2 r0 = unpack_bf16x2(rs[i].x), r1 = unpack_bf16x2(rs[i].y);
+                  const float2 l0 = unpack_bf16x2(rl[i].x), l1 = unpack_bf16x2(rl[i].y);
+                  val.x += r0.x + l0.x; val.y += r0.y + l0.y; val.z += r1.x + l1.x; val.w += r1.y + l1.y;
+                }
                 *reinterpret_cast<float4*>(static_cast<float*>(args.out) + static_cast<size_t>(grow) * args.ld_out + n + q * 4) = val;
               } else {   // EPI_PATCH
                 const int doc = grow / args.n_patch;

@@ -20,7 +20,7 @@ namespace mmee {
 // stream, Xlo = bf16(v - bf16(v)): the next residual add reads X + Xlo (16-bit mantissa) while the GEMMs read X.
 template <int NV>
 __global__ void ln_rows_kernel(const float* __restrict__ Y, __nv_bfloat16* __restrict__ X,
-                               __nv_bfloat16* __restrict__ Xlo, const float* __restrict__ w,
+                               __nv_bfloat16* __restrict__ Xlo, float* __restrict__ X32, const float* __restrict__ w,
                                const float* __restrict__ b, float eps, int H, int seq,
                                const int* __restrict__ m_dst_dev, const int* __restrict__ slot_src) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -48,6 +48,7 @@ __global__ void ln_rows_kernel(const float* __restrict__ Y, __nv_bfloat16* __res
       const __nv_bfloat16 hi = __float2bfloat16_rn(v[i]);
       out[c] = hi;
       if (out_lo) out_lo[c] = __float2bfloat16_rn(v[i] - __bfloat162float(hi));
+      if (X32) X32[static_cast<size_t>(row) * H + c] = v[i];
     }
   }
 }
@@ -57,7 +58,8 @@ __global__ void ln_rows_kernel(const float* __restrict__ Y, __nv_bfloat16* __res
 // 4 B read + 2 (+2) B written per element).
 template <int NV4>
 __global__ void __launch_bounds__(256) ln_rows_vec_kernel(const float* __restrict__ Y, __nv_bfloat16* __restrict__ X,
-                                                          __nv_bfloat16* __restrict__ Xlo, const float* __restrict__ w,
+                                                          __nv_bfloat16* __restrict__ Xlo, float* __restrict__ X32,
+                                                          const float* __restrict__ w,
                                                           const float* __restrict__ b, float eps, int H, int seq,
                                                           const int* __restrict__ m_dst_dev,
                                                           const int* __restrict__ slot_src,
@@ -109,6 +111,7 @@ __global__ void __launch_bounds__(256) ln_rows_vec_kernel(const float* __restric
         *reinterpret_cast<uint2*>(out_lo + 4 * (lane + 32 * i)) =
             make_uint2(pack_bf16x2(o0 - f01.x, o1 - f01.y), pack_bf16x2(o2 - f23.x, o3 - f23.y));
       }
+      if (X32) *reinterpret_cast<float4*>(X32 + static_cast<size_t>(row) * H + 4 * (lane + 32 * i)) = make_float4(o0, o1, o2, o3);
     }
   }
 }
