@@ -319,6 +319,10 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        warm = torch.zeros(8, device=dev)                # NCCL communicator set-up (seconds) happens here, not in a timed
+        dist.all_reduce(warm)                            # or clock-sampled region
+        dist.all_gather_into_tensor(torch.empty(8 * world, device=dev), warm)
+        torch.cuda.synchronize()
 
     if args.config == "sweep":
         run_sweep(args, world, rank, local, dev)
