@@ -81,15 +81,18 @@ static_assert(AttSmem::KB_STAGE % 1024 == 0 && AttSmem::K_BYTES % 1024 == 0 && A
               "swizzled tiles need 1024 B alignment");
 
 struct AttArgs {
-  const int* n_active_dev;
-  const uint2* slot_meta;      // slot -> {live_tiles, doc}   (see slot_meta_kernel)
+  // ragged work list of the exit stage (norm_exit.cuh SlotRows, written by plan_rows_block): slot s owns rows
+  // [meta[s].x, meta[s].x + meta[s].y) of Q / K / ctx, belongs to document meta[s].z and its query tiles are numbers
+  // meta[s].w ... in qt_slot; item = heads * meta[s].w + head * n_qt(s) + query tile
+  const int4* slot_meta;
+  const int* qt_slot;
+  const int* n_qt_dev;
   int* err_flag;               // guard: set to 1 if a deferred rescale factor underflowed (unreachable, see ATT_JUMP)
   long long* trace;            // developer trace (kTrace instantiation only): clock64 stamps of CTA 0
   __nv_bfloat16* ctx;          // [M, H]
   __nv_bfloat16* ctx_lo;       // kSplit: low part of ctx
-  int H, heads, seq;
-  int skip_pad_q;              // skip items whose query rows are all padded text tokens (att_skip_dead)
-  int tail_j;                  // key tile that holds only <= 16 real keys and is run as a 16-key tile (-1: none)
+  int H, heads, seq;           // seq: token pitch of the bias rows (max tokens per document)
+  int tail16;                  // a last key tile with <= 16 real keys runs as a 16-key tile
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -106,81 +109,47 @@ __device__ __forceinline__ void sub_ref_x2(uint32_t a, uint32_t b, uint64_t nref
   asm("mov.b64 {%0, %1}, %2;" : "=f"(ya), "=f"(yb) : "l"(y));
 }
 
-// Position in this CTA's (item, key tile) sequence; fully masked tiles are skipped.  Every role walks the same
-// sequence so the pipeline counters stay in lock-step.  Passed by value so it lives in registers.
+// Position in this CTA's (item, key tile) sequence.  Every role walks the same sequence so the pipeline counters stay
+// in lock-step.  Passed by value so it lives in registers.  An item = (slot, head, 128-row query tile); its key tiles
+// are 0 .. last_j (documents are ragged: only kept tokens have rows, so there are no padded key tiles to skip).
 struct AttCursor {
-  int item, ii, j, slot, head, q0, doc, first_j, last_j;
-  uint32_t live;               // bit j: tile j is processed (not fully padded)
+  int item, ii, j, slot, head, q0, doc, last_j, tail_j, row0, rows;
   int nitem;                   // the NEXT item this CTA processes (>= total_items: none)
-  uint2 nmeta;                 // its slot_meta, loaded one item ahead (latency hidden)
+  int4 nmeta;                  // its slot meta, loaded one item ahead (latency hidden)
   bool valid;
 };
 
-__device__ __forceinline__ uint2 att_item_meta(int item, int total_items, int n_qt, const AttArgs& args) {
-  return (item < total_items) ? __ldg(args.slot_meta + (item / n_qt) / args.heads) : make_uint2(1u, 0u);
+__device__ __forceinline__ int4 att_item_meta(int item, int total_items, const AttArgs& args) {
+  return (item < total_items) ? __ldg(args.slot_meta + __ldg(args.qt_slot + item / args.heads)) : make_int4(0, 1, 0, 0);
 }
-// Items whose 128 query rows are all padded text tokens are skipped: nobody reads those rows' outputs (their keys are
-// masked for every query, exits read the CLS row, mean-pool exits run before the encoder).  The live-tile bits of
-// slot_meta describe KEY tiles of 64 tokens; query tile qt covers key tiles 2 qt and 2 qt + 1.  Query tile 0 holds the
-// CLS row and is always processed.  Every role walks the same (deterministic) sequence.
-__device__ __forceinline__ int att_skip_dead(int item, uint2& meta, int total_items, int n_qt, int stride,
-                                             const AttArgs& args) {
-  if (!args.skip_pad_q) return item;
-  while (item < total_items) {
-    const int qt = item % n_qt;
-    if (qt == 0 || ((meta.x >> (qt * (ATT_BQ / ATT_BKV))) & ((1u << (ATT_BQ / ATT_BKV)) - 1u)) != 0u) break;
-    item += stride;
-    meta = att_item_meta(item, total_items, n_qt, args);
-  }
-  return item;
-}
-// `item` is live (att_skip_dead) or >= total_items
-__device__ __forceinline__ AttCursor att_enter(int item, int ii, uint2 meta, int total_items, int n_qt, int stride,
+__device__ __forceinline__ AttCursor att_enter(int item, int ii, int4 meta, int total_items, int stride,
                                                const AttArgs& args) {
   AttCursor c;
   c.item = item; c.ii = ii; c.valid = item < total_items;
-  c.j = 0; c.slot = 0; c.head = 0; c.q0 = 0; c.doc = 0; c.first_j = 0; c.last_j = 0; c.live = 1u;
-  c.nmeta = make_uint2(1u, 0u);
+  c.j = 0; c.slot = 0; c.head = 0; c.q0 = 0; c.doc = 0; c.last_j = 0; c.tail_j = -1; c.row0 = 0; c.rows = 1;
+  c.nmeta = make_int4(0, 1, 0, 0);
   c.nitem = total_items;
   if (!c.valid) return c;
-  const int qt = item % n_qt;
-  const int sh = item / n_qt;
-  c.head = sh % args.heads;
-  c.slot = sh / args.heads;
-  c.q0 = qt * ATT_BQ;
-  c.doc = static_cast<int>(meta.y);
-  c.live = meta.x & 0xFFFFu;
-  c.first_j = __ffs(c.live) - 1;
-  c.last_j = 31 - __clz(c.live);
-  c.j = c.first_j;
+  c.row0 = meta.x; c.rows = meta.y; c.doc = meta.z;
+  const int n_qt = (c.rows + ATT_BQ - 1) / ATT_BQ;
+  const int local = item - args.heads * meta.w;
+  c.head = local / n_qt;
+  c.q0 = (local - c.head * n_qt) * ATT_BQ;
+  c.slot = __ldg(args.qt_slot + item / args.heads);
+  c.last_j = (c.rows + ATT_BKV - 1) / ATT_BKV - 1;
+  const int rem = c.rows - c.last_j * ATT_BKV;           // real keys of the last tile
+  c.tail_j = (args.tail16 && c.last_j > 0 && rem <= 16) ? c.last_j : -1;
   c.nitem = item + stride;
-  c.nmeta = att_item_meta(c.nitem, total_items, n_qt, args);
-  c.nitem = att_skip_dead(c.nitem, c.nmeta, total_items, n_qt, stride, args);
+  c.nmeta = att_item_meta(c.nitem, total_items, args);
   return c;
 }
-__device__ __forceinline__ AttCursor att_first(int total_items, int n_qt, int stride, const AttArgs& args) {
-  int item = blockIdx.x;
-  uint2 meta = att_item_meta(item, total_items, n_qt, args);
-  item = att_skip_dead(item, meta, total_items, n_qt, stride, args);
-  return att_enter(item, 0, meta, total_items, n_qt, stride, args);
+__device__ __forceinline__ AttCursor att_first(int total_items, int stride, const AttArgs& args) {
+  const int item = blockIdx.x;
+  return att_enter(item, 0, att_item_meta(item, total_items, args), total_items, stride, args);
 }
-__device__ __forceinline__ AttCursor att_next(AttCursor c, int total_items, int n_qt, int stride, const AttArgs& args) {
-  const uint32_t rest = c.live & ~((2u << c.j) - 1u);
-  if (rest) { c.j = __ffs(rest) - 1; return c; }
-  return att_enter(c.nitem, c.ii + 1, c.nmeta, total_items, n_qt, stride, args);
-}
-
-// slot_meta[slot] = {live tiles, doc} from the per-document tile flags (keymask_kernel).
-__global__ void slot_meta_kernel(const int* __restrict__ slot_doc, const int* __restrict__ tileflag,
-                                 const int* __restrict__ n_active_dev, uint2* __restrict__ slot_meta, int n_kv) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= *n_active_dev) return;
-  const int doc = slot_doc[s];
-  uint32_t live = 0u;
-  for (int j = 0; j < n_kv; ++j)
-    if (tileflag[doc * n_kv + j] != 2) live |= 1u << j;
-  if (live == 0u) live = 1u;                     // degenerate: keep one tile so the row sum is defined
-  slot_meta[s] = make_uint2(live, static_cast<uint32_t>(doc));
+__device__ __forceinline__ AttCursor att_next(AttCursor c, int total_items, int stride, const AttArgs& args) {
+  if (c.j < c.last_j) { ++c.j; return c; }
+  return att_enter(c.nitem, c.ii + 1, c.nmeta, total_items, stride, args);
 }
 
 // tmap_q   : bf16 [M_max, 2H]                    box [128 rows x 64 cols]   (SW128)
@@ -201,9 +170,7 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
   const CUtensorMap& tmap_vt = maps.vt;
   const CUtensorMap& tmap_bias = maps.bias;
   const int S = args.seq;
-  const int n_kv = (S + ATT_BKV - 1) / ATT_BKV;
-  const int n_qt = (S + ATT_BQ - 1) / ATT_BQ;
-  const int total_items = *args.n_active_dev * args.heads * n_qt;
+  const int total_items = *args.n_qt_dev * args.heads;
   const int stride = gridDim.x;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -280,13 +247,13 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      AttCursor c = att_first(total_items, n_qt, stride, args);
+      AttCursor c = att_first(total_items, stride, args);
       uint32_t t = 0;
       int loaded_ii = -1;
       int pv_row = 0, pv_kv0 = 0;                 // V^T tile of the previous tile (loaded one tile late, see below)
       constexpr int PF_DIST = 4;                  // L2 prefetch distance in key tiles
       while (c.valid) {
-        const int row0 = c.slot * S;
+        const int row0 = c.row0;
         if (c.ii != loaded_ii) {
           loaded_ii = c.ii;
           const int qb = c.ii & 1;
@@ -316,22 +283,25 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
         // pull the tiles PF_DIST ahead into L2 (bias always comes from DRAM; K / V^T only for the first query tile
         // of a (slot, head)); one tile per step, so demand loads never queue behind a burst of prefetches
         {
-          int pj = c.j + PF_DIST, prow0 = row0, pbrow = brow, pvrow = vrow, phead = c.head;
+          int pj = c.j + PF_DIST, prow0 = row0, pbrow = brow, pvrow = vrow, phead = c.head, plast = c.last_j;
           if (pj > c.last_j) {                    // runs into the next item of this CTA
             const int nitem = c.nitem;
             if (nitem < total_items) {
-              const int nsh = nitem / n_qt;
-              const int nslot = nsh / args.heads;
-              phead = nsh % args.heads;
-              pj = pj - c.last_j - 1 + (__ffs(c.nmeta.x & 0xFFFFu) - 1);
-              prow0 = nslot * S;
-              pbrow = (static_cast<int>(c.nmeta.y) * args.heads + phead) * S + (nitem % n_qt) * ATT_BQ;
+              const int nrows = c.nmeta.y;
+              const int nn_qt = (nrows + ATT_BQ - 1) / ATT_BQ;
+              const int nlocal = nitem - args.heads * c.nmeta.w;
+              const int nslot = __ldg(args.qt_slot + nitem / args.heads);
+              phead = nlocal / nn_qt;
+              pj = pj - c.last_j - 1;
+              plast = (nrows + ATT_BKV - 1) / ATT_BKV - 1;
+              prow0 = c.nmeta.x;
+              pbrow = (c.nmeta.z * args.heads + phead) * S + (nlocal - phead * nn_qt) * ATT_BQ;
               pvrow = (nslot * args.heads + phead) * ATT_D;
             } else {
-              pj = n_kv;
+              pj = plast + 1;
             }
           }
-          if (pj < n_kv) {
+          if (pj <= plast) {
             tma_prefetch_2d(&tmap_bias, pj * ATT_BKV, pbrow);
             tma_prefetch_2d(&tmap_k, args.H + phead * ATT_D, prow0 + pj * ATT_BKV);
             tma_prefetch_2d(&tmap_vt, pj * ATT_BKV, pvrow);
@@ -349,7 +319,7 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
         }
         pv_row = vrow; pv_kv0 = kv0;
         ++t;
-        c = att_next(c, total_items, n_qt, stride, args);
+        c = att_next(c, total_items, stride, args);
       }
       if (t > 0) {
         const int sv = (t - 1) % ATT_V_STAGES;
@@ -369,13 +339,13 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
       constexpr uint32_t idesc_s16 = umma_idesc_bf16(ATT_BQ, 16);   // the 16-key tail tile (args.tail_j)
       constexpr uint32_t idesc_b16 = umma_idesc_f16(ATT_BQ, 16);
       const uint64_t di = umma_desc_sw128_kmajor(sb + SMEM::I_OFF);
-      AttCursor cs = att_first(total_items, n_qt, stride, args);   // next S = Q K^T + B I to issue (one tile ahead)
+      AttCursor cs = att_first(total_items, stride, args);   // next S = Q K^T + B I to issue (one tile ahead)
       AttCursor cp = cs;                                              // next P V to issue
       uint32_t ts = 0;
       auto issue_s = [&]() {
         const int st = ts % ATT_KB_STAGES;
         ATT_TRACE(1, ts, 0)
-        if (cs.j == cs.first_j) mbar_wait(qt_full, cs.ii & 1);      // the item's Q is in TMEM (softmax warps, below)
+        if (cs.j == 0) mbar_wait(qt_full, cs.ii & 1);               // the item's Q is in TMEM (softmax warps, below)
         mbar_wait(kb_full + st * 8, (ts / ATT_KB_STAGES) & 1);
         ATT_TRACE(1, ts, 1)
         tc_fence_after();
@@ -398,7 +368,7 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
           for (int k = 0; k < ATT_BKV / 16; ++k) umma_bf16_ss(d_s, db + 2 * k, di + 2 * k, idesc_b, 1u);
 #pragma unroll
           for (int k = 0; k < ATT_BKV / 16; ++k) umma_bf16_ss(d_s, dbl + 2 * k, di + 2 * k, idesc_b, 1u);
-        } else if (cs.j != args.tail_j) {
+        } else if (cs.j != cs.tail_j) {
 #pragma unroll
           for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ts(d_s, tmem_Q + k * 8, dk + 2 * k, idesc_s, k ? 1u : 0u);
 #pragma unroll
@@ -412,14 +382,14 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
         umma_commit(s_full + (ts & 1) * 8);
         umma_commit(kb_empty + st * 8);
         ++ts;
-        cs = att_next(cs, total_items, n_qt, stride, args);
+        cs = att_next(cs, total_items, stride, args);
       };
       if (cs.valid) issue_s();
       for (uint32_t t = 0; t < ts; ++t) {               // ts grows while tiles remain
         if (cs.valid) issue_s();                        // S_{t+1} (its TMEM buffer was released by P V_{t-1} above)
         const int sv = t % ATT_V_STAGES;
         const int b = t & 1;
-        const bool first = (cp.j == cp.first_j);
+        const bool first = (cp.j == 0);
         // P_t is in TMEM; for the first tile of an item the softmax warps have also read the previous item's O
         ATT_TRACE(1, t, 2)
         mbar_wait(p_full + b * 8, (t >> 1) & 1);
@@ -427,7 +397,7 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
         mbar_wait(v_full + sv * 8, (t / ATT_V_STAGES) & 1);
         tc_fence_after();
         const uint64_t dv = umma_desc_sw128_kmajor(sb + SMEM::V_OFF + sv * SMEM::V_STAGE);
-        const int pv_steps = (kSplit || cp.j != args.tail_j) ? ATT_BKV / 16 : 1;      // tail tile: P is [128 x 16]
+        const int pv_steps = (kSplit || cp.j != cp.tail_j) ? ATT_BKV / 16 : 1;        // tail tile: P is [128 x 16]
 #pragma unroll
         for (int k = 0; k < ATT_BKV / 16; ++k)
           if (k < pv_steps)
@@ -443,7 +413,7 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
         }
         umma_commit(o_full);
         umma_commit(v_empty + sv * 8);
-        cp = att_next(cp, total_items, n_qt, stride, args);
+        cp = att_next(cp, total_items, stride, args);
       }
     }
   } else {
@@ -452,7 +422,7 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
     const int r = quarter * 32 + lane;                        // query row within the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t t = 0;
-    AttCursor c = att_first(total_items, n_qt, stride, args);
+    AttCursor c = att_first(total_items, stride, args);
 
     float ref = 0.f, alpha_pend = 1.f;
     __nv_bfloat16* out_ptr = nullptr;                         // ctx destination of the open item (nullptr: row >= S)
@@ -541,12 +511,12 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
 
     while (c.valid) {
       const int b = t & 1;
-      const bool first = (c.j == c.first_j);                 // first processed tile of a new item
+      const bool first = (c.j == 0);                         // first key tile of a new item
       const uint32_t tS = tmem_S + lane_addr + b * ATT_BKV;
       __nv_bfloat16* prev_out = out_ptr;
       if (first) {
         const int q = c.q0 + r;
-        out_ptr = (q < S) ? args.ctx + static_cast<size_t>(c.slot * S + q) * args.H + c.head * ATT_D : nullptr;
+        out_ptr = (q < c.rows) ? args.ctx + static_cast<size_t>(c.row0 + q) * args.H + c.head * ATT_D : nullptr;
       }
       const bool tr = kTrace && warp == 2 && lane == 0;
       if (tr) { ATT_TRACE(0, t, 0) }
@@ -601,7 +571,7 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
         __syncwarp();
         tmem_st32(tS, ph);
         tmem_st32(tS + 32, pl);
-      } else if (c.j == args.tail_j) {
+      } else if (c.j == c.tail_j) {
         // 16-key tail tile: a quarter of the loads, exponentials and stores
         uint32_t v[16], pq[8];
         tmem_ld16(tS, v);
@@ -724,7 +694,7 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
         if (!(alpha_pend > 0.f)) *args.err_flag = 1;       // unreachable with the jump handling above; kept as a guard
       }
       ++t;
-      c = att_next(c, total_items, n_qt, stride, args);
+      c = att_next(c, total_items, stride, args);
     }
     if (have_item) {
       mbar_wait(o_full, (t - 1) & 1);

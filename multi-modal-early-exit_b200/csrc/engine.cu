@@ -75,12 +75,11 @@ __global__ void f32_to_bf16_split_kernel(const float* __restrict__ src, __nv_bfl
   }
 }
 __global__ void init_forward_kernel(int* slot_doc, int* out_exit, int* n_dev, int* m_dev, unsigned long long* hist,
-                                    int B, int seq, int n_hist, int* any_pad) {
+                                    int B, int seq, int n_hist) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) *any_pad = 0;
   if (i < B) { slot_doc[i] = i; out_exit[i] = -1; }
   if (i < n_hist) hist[i] = 0ull;
-  if (i == 0) { n_dev[0] = B; m_dev[0] = B * seq; }
+  if (i == 0) { n_dev[0] = B; m_dev[0] = B * seq; }     // dense upper bound; the row plan writes the ragged count
 }
 __global__ void fill_nan_kernel(float* p, size_t n) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
@@ -135,9 +134,12 @@ struct mmee_engine {
   int max_batch = 0;
   int H, L, heads, I, T, P, S, K, n_vis, n_patch, kdim_patch;
   int kv_pitch = 768, bias_pitch = 768;
-  int att_tail_j = -1, bias_width = 768;
+  int bias_width = 768;
   bool split = false;              // fp32 engine mode (mmee_model_desc.compute_dtype == MMEE_DTYPE_FP32): split-bf16 operands
-  DevBuf<int> any_pad;             // [1] set by keymask_kernel when some text token of the batch is padded
+  // ragged encoder layout (norm_exit.cuh): kept tokens per document and the row plans of two consecutive exit stages
+  DevBuf<int> doc_len, kept_idx, plan_row0[2], plan_qt_slot[2], plan_n_qt[2];
+  DevBuf<int4> plan_meta[2];
+  bool tail16 = true;              // attention: a last key tile with <= 16 real keys runs as a 16-key tile (MMEE_NO_TAIL16=1: off)
   DevBuf<float> lte_w, slot_lte;   // learned-to-exit scorer [H] (optional) and its per-slot scores
   float lte_b = 0.f;
   int m_max = 0;            // padded row capacity of activation buffers
@@ -177,17 +179,14 @@ struct mmee_engine {
   DevBuf<__half> BIASlo;                    // fp32 engine mode: low part of the attention bias
   DevBuf<float> X32[2], A132;               // fp32 engine mode: the residual stream itself in fp32 (exact residual adds)
   bool precise_residual = true;
-  bool skip_pad_q = true;          // attention skips query tiles of padded text tokens; MMEE_SKIP_PAD_Q=0 turns it off
   DevBuf<float> Y, VIS, POOL, POOLV, POOLT, TXT, Z, T0, T1;
   bool has_vision_exit = false, has_text_exit = false;
   DevBuf<__half> BIAS, bias_t2;
   DevBuf<float> maskadd, bias_t1, bias_tx, bias_ty;     // bias_tx / bias_ty: fp32 engine mode (bias_build_split_kernel)
-  DevBuf<int> tileflag, err_flags;          // err_flags: [0] attention online-softmax guard, [1] input id / box out of range
+  DevBuf<int> err_flags;                    // err_flags: [0] attention online-softmax guard, [1] input id / box out of range
   cudaEvent_t last_done = nullptr;          // end of the last forward: the next one (any stream) is ordered after it
-  DevBuf<uint2> slot_meta;
   DevBuf<long long> att_trace;
   bool trace_on = false;
-  int meta_stage = -1;
   int n_kv_tiles = 6;
   DevBuf<int> posid;
   CUtensorMap t_x[2], t_qk, t_k64, t_vt, t_bias, t_ctx, t_a1, t_mid, t_patch;
@@ -235,6 +234,12 @@ struct mmee_engine {
 namespace {
 
 int n_stages(const mmee_engine* e) { return e->d.n_exits + 3; }
+
+SlotRows plan_view(mmee_engine* e, int i) {
+  SlotRows r;
+  r.row0 = e->plan_row0[i].p; r.meta = e->plan_meta[i].p; r.qt_slot = e->plan_qt_slot[i].p; r.n_qt_dev = e->plan_n_qt[i].p;
+  return r;
+}
 
 std::vector<uint8_t> default_lut(int num_buckets, int max_distance, int n) {
   // HF relative_position_bucket (modeling_layoutlmv3.py:393-414), bidirectional: table over |rel|.
@@ -371,18 +376,19 @@ void launch_nv(int H, F&& f) {   // dispatch on values-per-lane for the warp-per
   else throw std::runtime_error("hidden size > 1024 not supported");
 }
 
-// LayerNorm of the active rows (fp32 Y -> bf16 X [+ low part]); vectorised when H is a multiple of 128
+// LayerNorm of the active rows (fp32 Y -> bf16 X [+ low part, + fp32 copy]); vectorised when H is a multiple of 128.
+// slot_src != nullptr: the rows are the survivors of an exit — destination slot s' (row plan `dst`) takes the rows of
+// source slot slot_src[s'] (row plan `src`): the compaction costs no extra pass.
 void launch_ln(mmee_engine* e, const float* Y, __nv_bfloat16* X, __nv_bfloat16* Xlo, float* X32, const float* w,
-               const float* b, int B, const int* m_dev, const int* slot_src, cudaStream_t st,
-               const int* slot_doc = nullptr) {
+               const float* b, int B, const int* m_dev, const int* slot_src, const SlotRows& dst, const SlotRows& src,
+               const int* n_dst_dev, cudaStream_t st) {
   const int H = e->H, S = e->S;
-  if (!e->skip_pad_q) slot_doc = nullptr;          // one developer switch (MMEE_SKIP_PAD_Q) for every padded-row skip
   const float eps = e->d.ln_eps;
   const int rows = B * S;
   auto vec = [&](auto nv4) {
     const int blocks = std::min((rows + 7) / 8, e->sms * 16);      // grid-stride over rows, 8 warps per block
-    ln_rows_vec_kernel<decltype(nv4)::value><<<blocks, 256, 0, st>>>(Y, X, Xlo, X32, w, b, eps, H, S, m_dev, slot_src, slot_doc,
-                                                                       e->maskadd.p, e->kv_pitch, e->T, e->any_pad.p);
+    ln_rows_vec_kernel<decltype(nv4)::value><<<blocks, 256, 0, st>>>(Y, X, Xlo, X32, w, b, eps, H, m_dev, slot_src, dst.row0,
+                                                                       src.row0, n_dst_dev);
   };
   switch (H % 128 == 0 ? H / 128 : 0) {
     case 1: vec(std::integral_constant<int, 1>{}); break;
@@ -392,7 +398,8 @@ void launch_ln(mmee_engine* e, const float* Y, __nv_bfloat16* X, __nv_bfloat16* 
     case 8: vec(std::integral_constant<int, 8>{}); break;
     default:
       launch_nv(H, [&](auto nv) {
-        ln_rows_kernel<decltype(nv)::value><<<(rows + 7) / 8, 256, 0, st>>>(Y, X, Xlo, X32, w, b, eps, H, S, m_dev, slot_src);
+        ln_rows_kernel<decltype(nv)::value><<<(rows + 7) / 8, 256, 0, st>>>(Y, X, Xlo, X32, w, b, eps, H, m_dev, slot_src,
+                                                                            dst.row0, src.row0, n_dst_dev);
       });
   }
   CUDA_OK(cudaGetLastError());
@@ -619,9 +626,16 @@ void allocate(mmee_engine* e) {
   e->n_kv_tiles = (S + ATT_BKV - 1) / ATT_BKV;
   if (e->n_kv_tiles > ATT_MAX_KV_TILES) throw std::runtime_error("too many key tiles");
   e->maskadd.alloc(static_cast<size_t>(B) * e->kv_pitch, true);
-  e->tileflag.alloc(static_cast<size_t>(B) * e->n_kv_tiles, true);
   e->err_flags.alloc(2, true);
-  e->slot_meta.alloc(B, true);
+  e->doc_len.alloc(B, true);
+  e->kept_idx.alloc(static_cast<size_t>(B) * std::max(e->T, 1), true);
+  const int max_qt = (S + ATT_BQ - 1) / ATT_BQ;
+  for (int i = 0; i < 2; ++i) {
+    e->plan_row0[i].alloc(B + 1, true);
+    e->plan_meta[i].alloc(B, true);
+    e->plan_qt_slot[i].alloc(static_cast<size_t>(B) * max_qt, true);
+    e->plan_n_qt[i].alloc(1, true);
+  }
   e->att_trace.alloc(4096, true);
   e->t_ctx = make_tmap_2d_sw128(e->CTX.p, M, H, H, 128);
   e->t_a1 = make_tmap_2d_sw128(e->A1.p, M, H, H, 128);
@@ -661,7 +675,6 @@ void allocate(mmee_engine* e) {
   e->all_crit.alloc(static_cast<size_t>(E1) * B);
   e->hist.alloc(E1, true);
   e->slot_lte.alloc(B, true);
-  e->any_pad.alloc(1, true);
   e->hist64.alloc(E1, true);
 }
 
@@ -689,7 +702,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   mark(e, "start", st);
 
   init_forward_kernel<<<(std::max(B, E1) + 255) / 256, 256, 0, st>>>(e->slot_doc[0].p, e->out_exit.p, e->n_dev.p,
-                                                                       e->m_dev.p, e->hist.p, B, S, E1, e->any_pad.p);
+                                                                       e->m_dev.p, e->hist.p, B, S, E1);
   e->launches++;
   const bool want_all = out->all_exit_logits || out->all_head_logits || out->all_criteria;
   if (want_all) {
@@ -701,8 +714,8 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   }
 
   // ---- bookkeeping of the exit stages
-  e->meta_stage = -1;
   int stage = 0;       // index into n_dev / m_dev
+  int rp = 0;          // row plan (plan_view) of the current stage; every compaction writes the other one
   int cur = 0;         // X buffer holding the current layer input
   int sd = 0;          // slot_doc ping-pong index
   int exit_no = 0;     // next exit to evaluate
@@ -710,12 +723,12 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   bool x_lo_valid = split;   // X[cur] has a low part (bf16 mode: not for the embedding output, a single bf16 rounding)
 
   auto run_exit = [&](const float* rows, size_t row_stride, const float* ln_w, const float* ln_b,
-                      const HeadW& head, bool is_final, const int* rows_slot_src) {
+                      const HeadW& head, bool is_final, const int* rows_slot_src, const int* row_off = nullptr) {
     // one fused launch: CLS rows (+LN) -> dense/tanh -> out_proj, temperature, criterion, threshold -> compaction
     const bool use_cls = gate && !is_final;               // class logits = classifier(CLS_j) ("gated logits")
     const bool need_head = !use_cls || want_all;          // the 2-way gate output is only an API output
     ExitFusedArgs xa{};
-    xa.rows = rows; xa.row_stride = row_stride; xa.slot_src = rows_slot_src; xa.ln_w = ln_w; xa.ln_b = ln_b;
+    xa.rows = rows; xa.row_stride = row_stride; xa.row_off = row_off; xa.slot_src = rows_slot_src; xa.ln_w = ln_w; xa.ln_b = ln_b;
     xa.ln_eps = d.ln_eps; xa.H = H; xa.n_active_dev = e->n_dev.p + stage;
     int jobs = 0;
     xa.head_src = -1; xa.cls_src = -1;
@@ -762,6 +775,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     ca.out_logits = e->out_logits.p; ca.out_crit = e->out_crit.p; ca.out_exit = e->out_exit.p;
     ca.all_logits = want_all ? e->all_logits.p : nullptr; ca.all_head = want_all ? e->all_head.p : nullptr;
     ca.all_crit = want_all ? e->all_crit.p : nullptr; ca.B = B; ca.n_head_max = K; ca.hist = e->hist.p;
+    ca.doc_len = e->doc_len.p; ca.next_rows = plan_view(e, rp ^ 1); ca.q_rows = ATT_BQ;
     const size_t smem = exit_fused_smem(H);
     static bool configured_dev[64] = {};
     bool& configured = configured_dev[e->device & 63];   // the attribute is per device
@@ -773,7 +787,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     exit_fused_kernel<<<grid, EXF_THREADS, smem, st>>>(xa);
     CUDA_OK(cudaGetLastError());
     e->launches++;
-    stage += 1; sd ^= 1; exit_no += 1;
+    stage += 1; sd ^= 1; rp ^= 1; exit_no += 1;
   };
 
   // ---- embeddings
@@ -822,6 +836,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     ba.maskadd = e->maskadd.p;
     ba.bins1 = d.rel_bins; ba.bins2 = d.rel2d_bins; ba.heads = heads; ba.t2_pitch = bias_table_pitch(heads); ba.n_text = T; ba.seq = S; ba.pitch = e->bias_pitch;
     ba.kv_pitch = e->kv_pitch; ba.B = B; ba.out = e->BIAS.p; ba.slot_doc = slots; ba.n_active_dev = n_act;
+    ba.doc_len = e->doc_len.p; ba.kept_idx = e->kept_idx.p; ba.n_vis = e->n_vis;
     const size_t smem = bias_build_smem(ba);
     static bool configured_dev[64] = {};
     bool& configured = configured_dev[e->device & 63];   // the attribute is per device
@@ -887,8 +902,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     posid_kernel<<<(B + 7) / 8, 256, 0, st>>>(ids, e->posid.p, B, T, d.pad_id);
     e->launches++;
   }
-  keymask_kernel<<<B, e->kv_pitch, 0, st>>>(mask, e->maskadd.p, e->tileflag.p, T, S, e->kv_pitch, e->n_kv_tiles, ATT_BKV,
-                                         e->any_pad.p);
+  keymask_kernel<<<B, e->kv_pitch, 0, st>>>(mask, e->maskadd.p, e->kept_idx.p, e->doc_len.p, T, S, e->kv_pitch);
   e->launches++;
 
   const bool modality_exits = e->has_vision_exit || e->has_text_exit;
@@ -937,16 +951,26 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
       any_embedding_exit = true;
     }
   }
-  if (any_embedding_exit && leave) {
-    // the concat exit compacted the slots: move the survivors' fused rows to their new slots (new -> old: slot_src)
-    const size_t row_elems = static_cast<size_t>(S) * H;
-    gather_slots_kernel<<<dim3(32, B), 256, 0, st>>>(e->X[cur].p, e->X[cur ^ 1].p, e->slot_src.p, e->n_dev.p + stage, row_elems * 2);
-    e->launches++;
+  // ---- dense embedding output -> ragged encoder input.  The embedding stage (and its mean-pool exits, which average
+  // over ALL 709 tokens, pads included, as the reference does) works on dense [slot, 709] rows; from here on a document
+  // owns only the rows of its kept tokens.  The same pass moves the survivors of the concat exit to their new slots.
+  {
+    plan_rows_kernel<<<1, 256, 0, st>>>(e->slot_doc[sd].p, e->doc_len.p, e->n_dev.p + stage, plan_view(e, rp), e->m_dev.p + stage, ATT_BQ);
+    // where the dense rows of slot s live: by document (no vision / text exit: the embedding stage ran in document
+    // order), else by the slot numbering of the embedding stage (identity, or new -> old after the concat exit left)
+    const int* src_index = !modality_exits ? e->slot_doc[sd].p : ((any_embedding_exit && leave) ? e->slot_src.p : nullptr);
+    auto gather = [&](const void* src, void* dst, int elem) {
+      ragged_gather_kernel<<<dim3(16, B), 256, 0, st>>>(src, dst, src_index, e->slot_doc[sd].p, e->n_dev.p + stage,
+                                                       e->plan_row0[rp].p, e->doc_len.p, e->kept_idx.p, T, e->n_vis, S, H * elem);
+      e->launches++;
+    };
+    gather(e->X[cur].p, e->X[cur ^ 1].p, 2);
     if (split) {
-      gather_slots_kernel<<<dim3(32, B), 256, 0, st>>>(e->Xlo[cur].p, e->Xlo[cur ^ 1].p, e->slot_src.p, e->n_dev.p + stage, row_elems * 2);
-      gather_slots_kernel<<<dim3(32, B), 256, 0, st>>>(e->X32[cur].p, e->X32[cur ^ 1].p, e->slot_src.p, e->n_dev.p + stage, row_elems * 4);
-      e->launches += 2;
+      gather(e->Xlo[cur].p, e->Xlo[cur ^ 1].p, 2);
+      gather(e->X32[cur].p, e->X32[cur ^ 1].p, 4);
     }
+    CUDA_OK(cudaGetLastError());
+    e->launches++;
     cur ^= 1;
   }
   if (modality_exits) {
@@ -962,19 +986,15 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     const int* mdev = e->m_dev.p + stage;
     GemmArgs ga{};
     ga.m_dev = mdev; ga.N = 3 * H; ga.K = H; ga.bias = w.bqkv.p; ga.out = e->QK.p; ga.out_lo = e->QKlo.p; ga.ld_out = 2 * H;
-    ga.vt = e->VT.p; ga.vt_lo = e->VTlo.p; ga.qk_cols = 2 * H; ga.seq = S; ga.kv_pitch = e->kv_pitch; ga.heads = heads;
+    ga.vt = e->VT.p; ga.vt_lo = e->VTlo.p; ga.qk_cols = 2 * H; ga.row0 = e->plan_row0[rp].p; ga.n_slots_dev = e->n_dev.p + stage;
+    ga.kv_pitch = e->kv_pitch; ga.heads = heads;
     launch_gemm<EPI_QKV>(e, e->bn_qkv, e->t_x[cur], w.t_wqkv, ga, st, &e->t_x_lo[cur], &w.t_wqkv_lo);
     mark(e, "gemm", st);
 
-    if (e->meta_stage != stage) {   // survivors changed since the last layer (or first layer): refresh slot -> (doc, tile flags)
-      slot_meta_kernel<<<(B + 255) / 256, 256, 0, st>>>(e->slot_doc[sd].p, e->tileflag.p, e->n_dev.p + stage, e->slot_meta.p,
-                                                      e->n_kv_tiles);
-      e->launches++;
-      e->meta_stage = stage;
-    }
     AttArgs aa;
-    aa.n_active_dev = e->n_dev.p + stage; aa.slot_meta = e->slot_meta.p; aa.ctx = e->CTX.p; aa.ctx_lo = e->CTXlo.p; aa.H = H;
-    aa.heads = heads; aa.seq = S; aa.tail_j = e->att_tail_j; aa.skip_pad_q = e->skip_pad_q ? 1 : 0; aa.err_flag = e->err_flags.p; aa.trace = e->att_trace.p;
+    aa.slot_meta = e->plan_meta[rp].p; aa.qt_slot = e->plan_qt_slot[rp].p; aa.n_qt_dev = e->plan_n_qt[rp].p;
+    aa.ctx = e->CTX.p; aa.ctx_lo = e->CTXlo.p; aa.H = H; aa.heads = heads; aa.seq = S;
+    aa.tail16 = (e->tail16 && !split) ? 1 : 0; aa.err_flag = e->err_flags.p; aa.trace = e->att_trace.p;
     {
       static bool configured_dev[64] = {};
       bool& configured = configured_dev[e->device & 63];   // the attribute is per device
@@ -988,12 +1008,7 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
       am.q = e->t_qk; am.k = e->t_k64; am.vt = e->t_vt; am.bias = e->t_bias;
       if (split) { am.q_lo = e->t_qk_lo; am.k_lo = e->t_k64_lo; am.vt_lo = e->t_vt_lo; am.bias_lo = e->t_bias_lo; }
       else { am.q_lo = e->t_qk; am.k_lo = e->t_k64; am.vt_lo = e->t_vt; am.bias_lo = e->t_bias; }
-      // items are dealt round-robin (item = CTA + k * grid, query tile = item % n_qt): a grid co-prime with n_qt makes
-      // every CTA cycle through all query tiles, so the skipped (padded) ones are spread evenly over the CTAs
-      const int n_qt = (S + ATT_BQ - 1) / ATT_BQ;
-      int att_grid = e->sms * (split ? 1 : ATT_CTAS_PER_SM);
-      if (e->skip_pad_q)
-        while (att_grid > 1 && std::gcd(att_grid, n_qt) != 1) --att_grid;
+      const int att_grid = e->sms * (split ? 1 : ATT_CTAS_PER_SM);
       if (split)
         attention_kernel<false, true><<<att_grid, ATT_THREADS, AttSmemT<true>::DYN_BYTES, st>>>(am, aa);
       else if (e->trace_on && l == 0)
@@ -1011,7 +1026,8 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     ga.resid_f32 = split ? e->X32[cur].p : nullptr;
     launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_ctx, w.t_wo, ga, st, &e->t_ctx_lo, &w.t_wo_lo);
     mark(e, "gemm", st);
-    launch_ln(e, e->Y.p, e->A1.p, e->A1lo.p, split ? e->A132.p : nullptr, w.ln1_w.p, w.ln1_b.p, B, mdev, nullptr, st, e->slot_doc[sd].p);
+    launch_ln(e, e->Y.p, e->A1.p, e->A1lo.p, split ? e->A132.p : nullptr, w.ln1_w.p, w.ln1_b.p, B, mdev, nullptr,
+              plan_view(e, rp), plan_view(e, rp), e->n_dev.p + stage, st);
     e->launches++;
     mark(e, "norm", st);
 
@@ -1028,22 +1044,23 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     const bool last = (l == e->L - 1);
     const bool exit_here = (exit_no < E && d.exit_after_layer[exit_no] == l + 1);
     const int* ln_src = nullptr;
+    const int y_rp = rp;                          // row plan under which Y was written
     if (exit_here) {
-      run_exit(e->Y.p, static_cast<size_t>(S) * H, w.ln2_w.p, w.ln2_b.p, e->exit_heads[exit_no], false, nullptr);
+      run_exit(e->Y.p, 0, w.ln2_w.p, w.ln2_b.p, e->exit_heads[exit_no], false, nullptr, e->plan_row0[y_rp].p);
       if (leave) ln_src = e->slot_src.p;
       mark(e, "exit", st);
     }
     if (!last) {
       launch_ln(e, e->Y.p, e->X[cur ^ 1].p, e->Xlo[cur ^ 1].p, split ? e->X32[cur ^ 1].p : nullptr, w.ln2_w.p, w.ln2_b.p, B,
-                e->m_dev.p + stage, ln_src, st, e->slot_doc[sd].p);
+                e->m_dev.p + stage, ln_src, plan_view(e, rp), plan_view(e, y_rp), e->n_dev.p + stage, st);
       e->launches++;
       cur ^= 1;
       x_lo_valid = e->precise_residual;
       mark(e, "norm", st);
     } else {
       // final classifier on the CLS row of the last layer (EE/models/LayoutLMv3.py:730-731); rows still live in
-      // Y under the pre-compaction slot numbering when an exit was just taken at layer L.
-      run_exit(e->Y.p, static_cast<size_t>(S) * H, w.ln2_w.p, w.ln2_b.p, e->classifier, true, ln_src);
+      // Y under the row plan of before the compaction when an exit was just taken at layer L.
+      run_exit(e->Y.p, 0, w.ln2_w.p, w.ln2_b.p, e->classifier, true, ln_src, e->plan_row0[y_rp].p);
       mark(e, "exit", st);
     }
   }
@@ -1149,23 +1166,14 @@ int mmee_create(const mmee_model_desc* desc, int device, int max_batch, mmee_eng
   e->kdim_patch = d.channels * d.patch * d.patch;
   e->kv_pitch = ((e->S + 127) / 128) * 128;
   e->bias_pitch = ((e->S + ATT_BKV - 1) / ATT_BKV) * ATT_BKV;   // whole key tiles: the pitch padding carries the -60000 mask
-  // a last key tile with <= 16 real keys (S = 709: 5) runs as a 16-key tile: the bias rows end after those 16 columns
-  // (the tensor map is that narrow: TMA zero-fills the rest of the box without reading HBM) and S / softmax / P V touch a quarter of the tile
-  e->att_tail_j = -1;
+  // a last key tile with <= 16 real keys (an unpadded document, S = 709: 5) runs as a 16-key tile (N = 16 MMAs, a quarter of
+  // the softmax work); decided per document by the attention kernel (documents are ragged)
+  e->tail16 = !getenv("MMEE_NO_TAIL16");
   e->bias_width = e->bias_pitch;
-  if (e->S > ATT_BKV && e->S % ATT_BKV != 0 && e->S % ATT_BKV <= 16 && !getenv("MMEE_NO_TAIL16")) {
-    e->att_tail_j = e->S / ATT_BKV;
-    e->bias_width = e->att_tail_j * ATT_BKV + 16;   // the row pitch stays a multiple of 128 B (a 1440 B pitch cost 5 %)
-  }
   if (e->kv_pitch > 1024) throw std::runtime_error("sequence too long for keymask_kernel");
   e->sms = prop.multiProcessorCount;
-  if (const char* sq = getenv("MMEE_SKIP_PAD_Q")) e->skip_pad_q = sq[0] != '0';                  // developer A/B switch
   if (const char* pr = getenv("MMEE_PRECISE_RESIDUAL")) e->precise_residual = pr[0] != '0';   // developer A/B switch
-  if (e->split) {                       // fp32 engine mode: split operands everywhere, full 64-key tiles in attention
-    e->precise_residual = true;
-    e->att_tail_j = -1;
-    e->bias_width = e->bias_pitch;
-  }
+  if (e->split) e->precise_residual = true;   // fp32 engine mode: split operands everywhere (and full 64-key tiles in attention)
   e->bn_h = pick_bn(e->H); e->bn_qkv = pick_bn(e->H) ; e->bn_i = pick_bn(e->I);
   if ((2 * e->H) % e->bn_qkv) e->bn_qkv = 128;
   try {

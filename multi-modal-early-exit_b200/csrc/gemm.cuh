@@ -52,7 +52,8 @@ struct GemmArgs {
   __nv_bfloat16* vt;       // [docs][heads][64][kv_pitch]
   __nv_bfloat16* vt_lo;    // SPLIT: low parts of V^T
   int qk_cols;             // 2*H
-  int seq;                 // tokens per document (709)
+  const int* row0;         // [n_slots + 1] first row of every slot (ragged documents); V^T is indexed by (slot, row - row0)
+  const int* n_slots_dev;
   int kv_pitch;            // padded token pitch of V^T rows
   int heads;
   // EPI_PATCH
@@ -132,6 +133,18 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
       const int row_base = m0 + quarter * 32;     // first row of this warp's 32-row slab
       const int row = row_base + lane;
       const bool row_ok = row < M;
+      int v_slot = 0, v_tok = 0;                  // EPI_QKV: the (slot, token) this thread's row belongs to
+      if constexpr (EPI == EPI_QKV) {
+        if (row_ok && n0 + BLOCK_N > args.qk_cols) {          // this tile holds V columns
+          int lo = 0, hi = *args.n_slots_dev - 1;
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (__ldg(args.row0 + mid) <= row) lo = mid; else hi = mid - 1;
+          }
+          v_slot = lo;
+          v_tok = row - __ldg(args.row0 + lo);
+        }
+      }
       const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
 
 #pragma unroll 1
@@ -212,8 +225,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
             }
           } else if (row_ok) {
             // V is stored transposed per (doc, head): vt[d][token] so that P*V takes a K-major B operand.
-            const int doc = row / args.seq;
-            const int tok = row - doc * args.seq;
+            const int doc = v_slot, tok = v_tok;
             const int nv = n - args.qk_cols;        // 32-aligned => one head per chunk
             const int head = nv >> 6;
             const int d0 = nv & 63;

@@ -16,20 +16,124 @@
 
 namespace mmee {
 
+// ------------------------------------------------------------------ ragged row layout of the encoder
+// Inside the encoder a document owns only the rows of its KEPT tokens: text tokens with attention_mask != 0 (plus
+// token 0, the CLS row every exit reads, even when it is masked as a key) followed by the n_vis visual tokens.  Rows of
+// padded text tokens are never computed: nothing reads them (their keys are masked for every query, HF:270-272; exits
+// read the CLS row; the mean-pool exits run on the dense embedding output before the encoder).  Slot s of an exit stage
+// owns rows [row0[s], row0[s + 1]); row0[n_active] = M is the row count of every GEMM / LayerNorm of the stage.
+//   doc_len[doc]      kept text tokens + n_vis                      (keymask_kernel, once per forward)
+//   kept_idx[doc][r]  original text position of kept text token r   (keymask_kernel)
+//   SlotRows          per exit stage: row0, the attention work list (see attention.cuh) and M
+struct SlotRows {
+  int* row0;        // [B + 1] exclusive prefix sums of the slots' row counts
+  int4* meta;       // [B] {row0, rows, doc, first query tile (prefix of ceil(rows / 128))}  (attention work list)
+  int* qt_slot;     // [sum of query tiles] query tile -> slot
+  int* n_qt_dev;    // [1] total number of 128-row query tiles
+};
+
+// largest s with row0[s] <= row (row0 ascending, row0[0] = 0, n >= 1 slots): the slot that owns `row`
+__device__ __forceinline__ int slot_of_row(const int* __restrict__ row0, int n, int row) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(row0 + mid) <= row) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// Row plan of one exit stage, by ONE thread block (any blockDim that is a multiple of 32, <= 1024): row0 / meta / qt_slot
+// for the n slots whose documents are slot_doc[0 .. n), and the totals.  s_scan: >= 2 * 32 + 2 ints of shared memory.
+__device__ __forceinline__ void plan_rows_block(const int* __restrict__ slot_doc, const int* __restrict__ doc_len, int n,
+                                                const SlotRows& out, int* __restrict__ m_dev, int q_rows, int* s_scan) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  int* s_w = s_scan;            // [32][2] per-warp totals (rows, query tiles)
+  int* s_carry = s_scan + 64;   // [2] running totals
+  if (threadIdx.x == 0) { s_carry[0] = 0; s_carry[1] = 0; }
+  __syncthreads();
+  for (int start = 0; start < n; start += blockDim.x) {
+    const int s = start + threadIdx.x;
+    const int doc = (s < n) ? slot_doc[s] : 0;
+    const int len = (s < n) ? doc_len[doc] : 0;
+    const int nq = (len + q_rows - 1) / q_rows;
+    int ir = len, iq = nq;                                  // inclusive warp scans
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int tr = __shfl_up_sync(0xffffffffu, ir, o), tq = __shfl_up_sync(0xffffffffu, iq, o);
+      if (lane >= o) { ir += tr; iq += tq; }
+    }
+    if (lane == 31) { s_w[warp * 2] = ir; s_w[warp * 2 + 1] = iq; }
+    __syncthreads();
+    int br = s_carry[0], bq = s_carry[1];
+    for (int w = 0; w < warp; ++w) { br += s_w[w * 2]; bq += s_w[w * 2 + 1]; }
+    const int r0 = br + ir - len, q0 = bq + iq - nq;
+    if (s < n) {
+      out.row0[s] = r0;
+      out.meta[s] = make_int4(r0, len, doc, q0);
+      for (int k = 0; k < nq; ++k) out.qt_slot[q0 + k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tr = 0, tq = 0;
+      for (int w = 0; w < nwarps; ++w) { tr += s_w[w * 2]; tq += s_w[w * 2 + 1]; }
+      s_carry[0] += tr; s_carry[1] += tq;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out.row0[n] = s_carry[0];
+    *out.n_qt_dev = s_carry[1];
+    *m_dev = s_carry[0];
+  }
+}
+
+// stand-alone form (first stage of the encoder, after the embedding-level exits)
+__global__ void __launch_bounds__(256) plan_rows_kernel(const int* __restrict__ slot_doc, const int* __restrict__ doc_len,
+                                                        const int* __restrict__ n_active_dev, SlotRows out,
+                                                        int* __restrict__ m_dev, int q_rows) {
+  __shared__ int s_scan[72];
+  plan_rows_block(slot_doc, doc_len, *n_active_dev, out, m_dev, q_rows, s_scan);
+}
+
+// dense embedding output -> ragged encoder input: dst[row0[s] + r] = src[src_index[s] * seq + token(r)], token(r) = the
+// r-th kept text token of the slot's document, then the visual tokens.  `elem_bytes` per element (2: bf16 rows, 4: fp32
+// copy of the fp32 engine mode); H * elem_bytes is a multiple of 16.  grid (x, slots).
+__global__ void ragged_gather_kernel(const void* __restrict__ src, void* __restrict__ dst,
+                                     const int* __restrict__ src_index, const int* __restrict__ slot_doc,
+                                     const int* __restrict__ n_active_dev, const int* __restrict__ row0,
+                                     const int* __restrict__ doc_len, const int* __restrict__ kept_idx, int n_text,
+                                     int n_vis, int seq, int row_bytes) {
+  const int slot = blockIdx.y;
+  if (slot >= *n_active_dev) return;
+  const int doc = slot_doc[slot];
+  const int len = doc_len[doc], kept = len - n_vis;
+  const int chunks = row_bytes / 16;
+  const size_t src_base = static_cast<size_t>(src_index ? src_index[slot] : slot) * seq;
+  const size_t dst_base = static_cast<size_t>(row0[slot]);
+  const int total = len * chunks;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / chunks, c = i - r * chunks;
+    const int tok = (r < kept) ? kept_idx[static_cast<size_t>(doc) * n_text + r] : n_text + (r - kept);
+    reinterpret_cast<uint4*>(dst)[(dst_base + r) * chunks + c] = reinterpret_cast<const uint4*>(src)[(src_base + tok) * chunks + c];
+  }
+}
+
 // one warp per destination row; rows >= *m_dst_dev are skipped.  Xlo (optional): low part of the split-bf16 residual
 // stream, Xlo = bf16(v - bf16(v)): the next residual add reads X + Xlo (16-bit mantissa) while the GEMMs read X.
 template <int NV>
 __global__ void ln_rows_kernel(const float* __restrict__ Y, __nv_bfloat16* __restrict__ X,
                                __nv_bfloat16* __restrict__ Xlo, float* __restrict__ X32, const float* __restrict__ w,
-                               const float* __restrict__ b, float eps, int H, int seq,
-                               const int* __restrict__ m_dst_dev, const int* __restrict__ slot_src) {
+                               const float* __restrict__ b, float eps, int H,
+                               const int* __restrict__ m_dst_dev, const int* __restrict__ slot_src,
+                               const int* __restrict__ row0_dst, const int* __restrict__ row0_src,
+                               const int* __restrict__ n_dst_dev) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= *m_dst_dev) return;
   const int lane = threadIdx.x & 31;
   size_t src_row = row;
-  if (slot_src) {
-    const int s = row / seq;
-    src_row = static_cast<size_t>(slot_src[s]) * seq + (row - s * seq);
+  if (slot_src) {                      // survivors of an exit: destination slot s' <- source slot slot_src[s'], same row offset
+    const int s = slot_of_row(row0_dst, *n_dst_dev, row);
+    src_row = static_cast<size_t>(row0_src[slot_src[s]]) + (row - row0_dst[s]);
   }
   const float* y = Y + src_row * H;
   float v[NV];
@@ -60,15 +164,15 @@ template <int NV4>
 __global__ void __launch_bounds__(256) ln_rows_vec_kernel(const float* __restrict__ Y, __nv_bfloat16* __restrict__ X,
                                                           __nv_bfloat16* __restrict__ Xlo, float* __restrict__ X32,
                                                           const float* __restrict__ w,
-                                                          const float* __restrict__ b, float eps, int H, int seq,
+                                                          const float* __restrict__ b, float eps, int H,
                                                           const int* __restrict__ m_dst_dev,
                                                           const int* __restrict__ slot_src,
-                                                          const int* __restrict__ slot_doc,
-                                                          const float* __restrict__ maskadd, int kv_pitch, int n_text,
-                                                          const int* __restrict__ any_pad) {
+                                                          const int* __restrict__ row0_dst,
+                                                          const int* __restrict__ row0_src,
+                                                          const int* __restrict__ n_dst_dev) {
   const int lane = threadIdx.x & 31;
   const int M = *m_dst_dev;
-  if (slot_doc && *any_pad == 0) slot_doc = nullptr;     // unpadded batch: no per-row mask lookups in front of the loads
+  const int n_dst = slot_src ? *n_dst_dev : 0;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   float4 w4[NV4], b4[NV4];
 #pragma unroll
@@ -78,11 +182,10 @@ __global__ void __launch_bounds__(256) ln_rows_vec_kernel(const float* __restric
   }
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps_total) {
     size_t src_row = row;
-    const int sl = row / seq, t = row - sl * seq;
-    // rows of padded text tokens are not normalised (nor moved): nothing reads them — their keys are masked, exits read
-    // the CLS row (t = 0, always kept) — and the destination keeps whatever finite values it held
-    if (slot_doc && t > 0 && t < n_text && __ldg(maskadd + static_cast<size_t>(__ldg(slot_doc + sl)) * kv_pitch + t) < 0.f) continue;
-    if (slot_src) src_row = static_cast<size_t>(slot_src[sl]) * seq + t;
+    if (slot_src) {                    // survivors of an exit: destination slot s' <- source slot slot_src[s'], same row offset
+      const int sl = slot_of_row(row0_dst, n_dst, row);
+      src_row = static_cast<size_t>(__ldg(row0_src + __ldg(slot_src + sl))) + (row - __ldg(row0_dst + sl));
+    }
     const float* y = Y + src_row * H;
     float4 v[NV4];
 #pragma unroll
@@ -146,8 +249,18 @@ struct BiasArgs {
   int heads, t2_pitch, n_text, seq, pitch, kv_pitch, B;
   const int* slot_doc;       // survivors of the embedding-level exits: only their documents get a bias (nullptr: all B)
   const int* n_active_dev;
-  __half* out;               // [B][heads][seq][pitch], indexed by DOCUMENT (the attention kernel maps slot -> doc)
+  const int* doc_len;        // [B] kept rows per document (ragged layout: bias rows / columns are indexed by kept-token rank)
+  const int* kept_idx;       // [B][n_text] original position of kept text token r
+  int n_vis;
+  __half* out;               // [B][heads][seq][pitch], indexed by DOCUMENT (the attention kernel maps slot -> doc); only the
+                             // first doc_len rows of a document are written, every column j >= doc_len holds the mask value
 };
+
+// ragged row r of a document -> original token: kept text token r, or visual token r - kept (index n_text + ...)
+__device__ __forceinline__ int bias_token_of_row(const BiasArgs& a, int doc, int len, int r) {
+  const int kept = len - a.n_vis;
+  return (r < kept) ? a.kept_idx[static_cast<size_t>(doc) * a.n_text + r] : a.n_text + (r - kept);
+}
 
 constexpr int BIAS_THREADS = 768;
 constexpr float BIAS_MASKED = -60000.0f;   // finite (0 * x stays 0 in the identity MMA) and exp2() of it is 0
@@ -189,16 +302,18 @@ __global__ void __launch_bounds__(BIAS_THREADS, 1) bias_build_kernel(BiasArgs a)
   const int j0 = (threadIdx.x - rl * chunks) * 8;
   const bool active = rl < rows_pp;
   const int half1 = a.bins1 >> 1, half2 = a.bins2 >> 1;
-  int cur_doc = -1;
+  int cur_doc = -1, cur_len = 0;
   for (int u = u_lo; u < u_hi; ++u) {
     const int dslot = u / passes;
     const int doc = a.slot_doc ? a.slot_doc[dslot] : dslot;
     const int i = (u - dslot * passes) * rows_pp + rl;
     if (doc != cur_doc) {                               // (re)load this document's key coordinates
       __syncthreads();
-      for (int t = threadIdx.x; t < a.pitch; t += blockDim.x) {
+      cur_len = a.doc_len[doc];
+      for (int r = threadIdx.x; r < a.pitch; r += blockDim.x) {
         int pos = 0, x0 = 0, y1 = 0, m = 1;
-        if (t < a.seq) {
+        if (r < cur_len) {
+          const int t = bias_token_of_row(a, doc, cur_len, r);
           if (t < a.n_text) {
             const int64_t* bb = a.bbox + (static_cast<size_t>(doc) * a.n_text + t) * 4;
             pos = t; x0 = static_cast<int>(bb[0]); y1 = static_cast<int>(bb[3]);
@@ -206,15 +321,15 @@ __global__ void __launch_bounds__(BIAS_THREADS, 1) bias_build_kernel(BiasArgs a)
             const int p = t - a.n_text;
             pos = p; x0 = a.vis_bbox[p * 4 + 0]; y1 = a.vis_bbox[p * 4 + 3];
           }
-          m = a.maskadd[static_cast<size_t>(doc) * a.kv_pitch + t] < 0.f ? 1 : 0;
+          m = a.maskadd[static_cast<size_t>(doc) * a.kv_pitch + t] < 0.f ? 1 : 0;    // a kept but masked key: CLS with mask 0
         }
-        const int tp = t + (t >> 3);
+        const int tp = r + (r >> 3);
         s_pos[tp] = pos; s_x[tp] = x0; s_y[tp] = y1; s_m[tp] = m;
       }
       cur_doc = doc;
       __syncthreads();
     }
-    if (!active || i >= a.seq) continue;
+    if (!active || i >= cur_len) continue;
     const int ip = i + (i >> 3);
     const int pi = s_pos[ip], xi = s_x[ip], yi = s_y[ip];
     const int jp0 = j0 + (j0 >> 3);                    // j0 is a multiple of 8: keys j0 .. j0+7 are contiguous from here
@@ -303,9 +418,11 @@ __global__ void bias_build_split_kernel(BiasArgs a, const float* __restrict__ tx
   const int doc = a.slot_doc ? a.slot_doc[dslot] : dslot;
   const int chunks = a.pitch >> 3;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.seq * chunks) return;
+  const int len = a.doc_len[doc];
+  if (idx >= len * chunks) return;
   const int i = idx / chunks, j0 = (idx - i * chunks) * 8;
-  auto coords = [&](int t, int& pos, int& x0, int& y1) {
+  auto coords = [&](int r, int& pos, int& x0, int& y1, int& t) {
+    t = bias_token_of_row(a, doc, len, r);
     if (t < a.n_text) {
       const int64_t* bb = a.bbox + (static_cast<size_t>(doc) * a.n_text + t) * 4;
       pos = t; x0 = static_cast<int>(bb[0]); y1 = static_cast<int>(bb[3]);
@@ -314,8 +431,8 @@ __global__ void bias_build_split_kernel(BiasArgs a, const float* __restrict__ tx
       pos = p; x0 = a.vis_bbox[p * 4 + 0]; y1 = a.vis_bbox[p * 4 + 3];
     }
   };
-  int pi, xi, yi;
-  coords(i, pi, xi, yi);
+  int pi, xi, yi, ti;
+  coords(i, pi, xi, yi, ti);
   const int half1 = a.bins1 >> 1, half2 = a.bins2 >> 1;
   int i1[8], ix[8], iy[8];
   bool masked[8];
@@ -324,14 +441,14 @@ __global__ void bias_build_split_kernel(BiasArgs a, const float* __restrict__ tx
     const int j = j0 + k;
     masked[k] = true;
     i1[k] = ix[k] = iy[k] = 0;
-    if (j < a.seq) {
-      int pj, xj, yj;
-      coords(j, pj, xj, yj);
+    if (j < len) {
+      int pj, xj, yj, tj;
+      coords(j, pj, xj, yj, tj);
       const int r1 = pj - pi, rx = xj - xi, ry = yj - yi;
       i1[k] = ((r1 > 0 ? half1 : 0) + a.lut1[min(abs(r1), a.lut1_n - 1)]) * a.t2_pitch;
       ix[k] = ((rx > 0 ? half2 : 0) + a.lut2[min(abs(rx), a.lut2_n - 1)]) * a.t2_pitch;
       iy[k] = ((ry > 0 ? half2 : 0) + a.lut2[min(abs(ry), a.lut2_n - 1)]) * a.t2_pitch;
-      masked[k] = a.maskadd[static_cast<size_t>(doc) * a.kv_pitch + j] < 0.f;
+      masked[k] = a.maskadd[static_cast<size_t>(doc) * a.kv_pitch + tj] < 0.f;
     }
   }
   const size_t head_stride = static_cast<size_t>(a.seq) * a.pitch;
@@ -350,30 +467,42 @@ __global__ void bias_build_split_kernel(BiasArgs a, const float* __restrict__ tx
   }
 }
 
-// Key-padding mask (HF:270-272 adds (1-mask)*finfo.min to the scores): maskadd[doc][j] = 0 / -inf and a per
-// (doc, key tile of `tile_keys` keys) flag: 0 = no masked key, 1 = some, 2 = every valid key masked (the tile is skipped).
-// grid B, block = kv_pitch threads (<= 1024)
-__global__ void keymask_kernel(const int64_t* __restrict__ mask, float* __restrict__ maskadd, int* __restrict__ tileflag,
-                               int n_text, int seq, int kv_pitch, int n_tiles, int tile_keys, int* __restrict__ any_pad) {
-  __shared__ int s_masked[32], s_valid[32];
+// Key-padding mask (HF:270-272 adds (1-mask)*finfo.min to the scores): maskadd[doc][t] = 0 / -inf per ORIGINAL token
+// position, and the document's kept-token list for the ragged encoder layout: kept_idx[doc][r] = position of the r-th
+// text token with attention_mask != 0 (token 0, the CLS row every exit reads, is always kept), doc_len[doc] = kept text
+// tokens + n_vis.  grid B, block = kv_pitch threads (<= 1024, a multiple of 32).
+__global__ void keymask_kernel(const int64_t* __restrict__ mask, float* __restrict__ maskadd, int* __restrict__ kept_idx,
+                               int* __restrict__ doc_len, int n_text, int seq, int kv_pitch) {
+  __shared__ int s_w[33];
   const int doc = blockIdx.x;
   const int j = threadIdx.x;
-  if (j < 32) { s_masked[j] = 0; s_valid[j] = 0; }
+  const int lane = j & 31, warp = j >> 5, nwarps = blockDim.x >> 5;
+  bool m = (j >= seq);
+  if (!m && j < n_text) m = (mask[static_cast<size_t>(doc) * n_text + j] == 0);
+  if (j < kv_pitch) maskadd[static_cast<size_t>(doc) * kv_pitch + j] = m ? -INFINITY : 0.f;
+  const int keep = (j < n_text) && (!m || j == 0);
+  int incl = keep;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_w[warp] = incl;
   __syncthreads();
-  if (j < kv_pitch) {
-    bool m = (j >= seq);
-    if (!m && j < n_text) m = (mask[static_cast<size_t>(doc) * n_text + j] == 0);
-    maskadd[static_cast<size_t>(doc) * kv_pitch + j] = m ? -INFINITY : 0.f;
-    if (j < seq) {
-      atomicAdd(&s_valid[j / tile_keys], 1);
-      if (m) atomicAdd(&s_masked[j / tile_keys], 1);
+  if (warp == 0) {
+    const int v = (lane < nwarps) ? s_w[lane] : 0;
+    int wi = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
     }
+    s_w[lane] = wi - v;                          // exclusive warp offsets
+    if (lane == 31) s_w[32] = wi;                // kept text tokens of the document
   }
   __syncthreads();
-  if (j < n_tiles) {
-    tileflag[doc * n_tiles + j] = (s_masked[j] == 0) ? 0 : (s_masked[j] == s_valid[j] ? 2 : 1);
-    if (s_masked[j] != 0) *any_pad = 1;          // batch-wide: some text token is padded (zeroed by init_forward_kernel)
-  }
+  if (keep) kept_idx[static_cast<size_t>(doc) * n_text + s_w[warp] + incl - 1] = j;
+  if (j == 0) doc_len[doc] = s_w[32] + (seq - n_text);
 }
 
 // ------------------------------------------------------------------ exit head
@@ -444,6 +573,10 @@ struct CompactArgs {
   float* all_crit;             // [(E+1), B] or nullptr
   int B, n_head_max;
   unsigned long long* hist;    // [E+1]
+  // row plan of the next stage (ragged layout)
+  const int* doc_len;          // [B]
+  SlotRows next_rows;
+  int q_rows;                  // query rows per attention item (128)
 };
 
 // ------------------------------------------------------------------ fused exit stage (one launch per exit)
@@ -459,8 +592,9 @@ struct CompactArgs {
 // No host round-trip and no extra launches: ~4x fewer launches and no exposed load latency between the stages.
 struct ExitFusedArgs {
   // (1) rows
-  const float* rows;        // fp32 rows; row of slot s starts at rows + src(s) * row_stride
-  size_t row_stride;
+  const float* rows;        // fp32 rows; row of slot s starts at rows + src(s) * row_stride, or, with row_off (ragged
+  size_t row_stride;        // encoder layout: the slot's CLS row is its first row), at rows + row_off[src(s)] * H
+  const int* row_off;
   const int* slot_src;      // optional gather map (rows not yet compacted)
   const float* ln_w;        // nullptr -> no LayerNorm (mean-pooled embedding exit)
   const float* ln_b;
@@ -549,9 +683,14 @@ __device__ __forceinline__ void compact_block(const CompactArgs& a, int* s_warp,
   }
   if (threadIdx.x == 0) {
     *a.n_next_dev = s_base;
-    *a.m_next_dev = s_base * a.seq;
     if (s_fired) atomicAdd(a.hist + a.exit_index, static_cast<unsigned long long>(s_fired));
   }
+  __syncthreads();
+  // rows of the survivors: row0 / attention work list / M of the next stage (next_slot_doc was written by this block)
+  __shared__ int s_scan[72];
+  const int n_next = s_base;
+  __threadfence_block();
+  plan_rows_block(a.next_slot_doc, a.doc_len, n_next, a.next_rows, a.m_next_dev, a.q_rows, s_scan);
 }
 
 __global__ void __launch_bounds__(EXF_THREADS) exit_fused_kernel(ExitFusedArgs a) {
@@ -582,7 +721,7 @@ __global__ void __launch_bounds__(EXF_THREADS) exit_fused_kernel(ExitFusedArgs a
       continue;
     }
     const int src = a.slot_src ? a.slot_src[slot] : slot;
-    const float* r = a.rows + static_cast<size_t>(src) * a.row_stride;
+    const float* r = a.row_off ? a.rows + static_cast<size_t>(a.row_off[src]) * H : a.rows + static_cast<size_t>(src) * a.row_stride;
     float4 v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
