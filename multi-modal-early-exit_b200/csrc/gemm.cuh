@@ -136,13 +136,13 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
       int v_slot = 0, v_tok = 0;                  // EPI_QKV: the (slot, token) this thread's row belongs to
       if constexpr (EPI == EPI_QKV) {
         if (row_ok && n0 + BLOCK_N > args.qk_cols) {          // this tile holds V columns
-          int lo = 0, hi = *args.n_slots_dev - 1;
-          while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (__ldg(args.row0 + mid) <= row) lo = mid; else hi = mid - 1;
-          }
-          v_slot = lo;
-          v_tok = row - __ldg(args.row0 + lo);
+          // proportional guess (exact for equal-length documents), then walk: row0[s] <= row < row0[s + 1]
+          const int ns = *args.n_slots_dev;
+          int sl = min(static_cast<int>(static_cast<long long>(row) * ns / M), ns - 1);
+          while (__ldg(args.row0 + sl) > row) --sl;
+          while (__ldg(args.row0 + sl + 1) <= row) ++sl;
+          v_slot = sl;
+          v_tok = row - __ldg(args.row0 + sl);
         }
       }
       const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);

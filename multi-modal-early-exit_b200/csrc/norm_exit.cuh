@@ -32,14 +32,15 @@ struct SlotRows {
   int* n_qt_dev;    // [1] total number of 128-row query tiles
 };
 
-// largest s with row0[s] <= row (row0 ascending, row0[0] = 0, n >= 1 slots): the slot that owns `row`
-__device__ __forceinline__ int slot_of_row(const int* __restrict__ row0, int n, int row) {
-  int lo = 0, hi = n - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (__ldg(row0 + mid) <= row) lo = mid; else hi = mid - 1;
-  }
-  return lo;
+// The slot that owns `row`: largest s with row0[s] <= row (row0 ascending, row0[0] = 0, row0[n] = M > row, n >= 1).
+// Starts from the proportional guess row * n / M — exact when all documents have the same number of rows (two
+// independent loads), a few slots off for ragged batches — and walks from there.
+__device__ __forceinline__ int slot_of_row(const int* __restrict__ row0, int n, int M, int row) {
+  int s = static_cast<int>(static_cast<long long>(row) * n / max(M, 1));
+  s = min(s, n - 1);
+  while (__ldg(row0 + s) > row) --s;
+  while (__ldg(row0 + s + 1) <= row) ++s;
+  return s;
 }
 
 // Row plan of one exit stage, by ONE thread block (any blockDim that is a multiple of 32, <= 1024): row0 / meta / qt_slot
@@ -132,7 +133,7 @@ __global__ void ln_rows_kernel(const float* __restrict__ Y, __nv_bfloat16* __res
   const int lane = threadIdx.x & 31;
   size_t src_row = row;
   if (slot_src) {                      // survivors of an exit: destination slot s' <- source slot slot_src[s'], same row offset
-    const int s = slot_of_row(row0_dst, *n_dst_dev, row);
+    const int s = slot_of_row(row0_dst, *n_dst_dev, *m_dst_dev, row);
     src_row = static_cast<size_t>(row0_src[slot_src[s]]) + (row - row0_dst[s]);
   }
   const float* y = Y + src_row * H;
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(256) ln_rows_vec_kernel(const float* __restric
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps_total) {
     size_t src_row = row;
     if (slot_src) {                    // survivors of an exit: destination slot s' <- source slot slot_src[s'], same row offset
-      const int sl = slot_of_row(row0_dst, n_dst, row);
+      const int sl = slot_of_row(row0_dst, n_dst, M, row);
       src_row = static_cast<size_t>(__ldg(row0_src + __ldg(slot_src + sl))) + (row - __ldg(row0_dst + sl));
     }
     const float* y = Y + src_row * H;
