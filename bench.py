@@ -398,37 +398,27 @@ def run_single(args, world, rank, local, dev):
     # over NVLink on NCCL's stream after every step WITHOUT a host round-trip; the ranks therefore do not run in
     # lock-step (a slower board only delays the gather it takes part in), and the whole job's results are read back to
     # the host once, at the end of the timed region ("final gather").
-    ring = torch.empty((max(steps, args.warmup), world * B, K + 2), dtype=torch.float32, device=dev) if world > 1 else None
-    hist_sum = torch.zeros((E1,), dtype=torch.int64, device=dev)
-    pending = []
-    state = {"i": 0, "last": None}
+    from mmee.dist import JobGatherer, pack_results
+
+    jg = JobGatherer(B, K + 2, E1, max(steps, args.warmup), dev) if world > 1 else None
+    state = {"last": None}
 
     def step_device():
         if world == 1:
             return model.infer(**dev_docs, exit_threshold=thr, temperatures=temps)
         r = model.infer_device(**dev_docs, exit_threshold=thr, temperatures=temps)
-        packed = torch.cat([r["logits"], r["exit_index"].to(torch.float32)[:, None], r["criterion"][:, None]], dim=1)
-        slot = state["i"] % ring.shape[0]
-        pending.append(dist.all_gather_into_tensor(ring[slot], packed, async_op=True))
-        hist_sum.add_(r["hist"])
-        state["i"] += 1
+        jg.push(pack_results(r["logits"], r["exit_index"], r["criterion"]), r["hist"])
         state["last"] = r
         return r
 
     def finish_device():
         if world == 1:
             return None
-        for w in pending:
-            w.wait()
-        pending.clear()
-        dist.all_reduce(hist_sum, op=dist.ReduceOp.SUM)
-        host = ring.cpu()                                # one read-back of every step's gathered results
+        fin = jg.finish()                                # waits for the gathers; ONE read-back of every step's results
         r = dict(state["last"])
         r["exit_hist"] = r["hist"].cpu().numpy()
-        r["job_results"] = host
-        r["job_hist"] = hist_sum.cpu().numpy()
-        hist_sum.zero_()
-        state["i"] = 0
+        r["job_results"] = fin["results"]
+        r["job_hist"] = fin["exit_hist"].numpy()
         return r
 
     model.set_profiling(True)
@@ -450,8 +440,8 @@ def run_single(args, world, rank, local, dev):
     if world > 1:
         docs0 = synth.make_docs(dims, B, seed=1, pad=False)
         r0 = model.infer_device(**{k: v.to(dev) for k, v in docs0.items()}, exit_threshold=thr, temperatures=temps)
-        mine = torch.cat([r0["logits"], r0["exit_index"].to(torch.float32)[:, None], r0["criterion"][:, None]], dim=1).cpu()
-        theirs = res["job_results"][(steps - 1) % ring.shape[0], :B]
+        mine = pack_results(r0["logits"], r0["exit_index"], r0["criterion"]).cpu()
+        theirs = res["job_results"][(steps - 1) % res["job_results"].shape[0], :B]
         ok = torch.tensor([1 if torch.equal(mine, theirs) else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         dp_consistency = {"checked": True, "bit_exact_on_all_ranks": bool(ok.item()), "ranks": world,
@@ -472,8 +462,7 @@ def run_single(args, world, rank, local, dev):
             def step_host():
                 up = {k: v.to(dev, non_blocking=True) for k, v in pin_docs.items()}
                 r = model.infer_device(**up, exit_threshold=thr, temperatures=temps)
-                packed = torch.cat([r["logits"], r["exit_index"].to(torch.float32)[:, None], r["criterion"][:, None]], dim=1)
-                dist.all_gather_into_tensor(out_all, packed)
+                dist.all_gather_into_tensor(out_all, pack_results(r["logits"], r["exit_index"], r["criterion"]))
                 return out_all.cpu()                 # the job's results on the host: the step ends here
             api = ("pinned host tensors -> B200EEForSequenceClassification.infer_device -> NCCL all_gather of the "
                    "job's results -> host, every step")
@@ -593,6 +582,7 @@ def run_sweep(args, world, rank, local, dev):
     the whole sweep (every threshold over every document of the shard)."""
     import torch.distributed as dist
 
+    from mmee.dist import pack_results
     from mmee.model import B200EEForSequenceClassification
 
     dims, ee, MB, text, dtype = workload("sweep")
@@ -623,7 +613,7 @@ def run_sweep(args, world, rank, local, dev):
         parts, hist = [], torch.zeros((E1,), dtype=torch.int64, device=dev)
         for d in shards:
             r = model.infer_device(**d, exit_threshold=thr, temperatures=temps)
-            parts.append(torch.cat([r["logits"], r["exit_index"].to(torch.float32)[:, None], r["criterion"][:, None]], dim=1))
+            parts.append(pack_results(r["logits"], r["exit_index"], r["criterion"]))
             hist += r["hist"]
         packed = torch.cat(parts, dim=0)
         if world > 1:

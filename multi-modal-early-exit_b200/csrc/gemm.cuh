@@ -138,7 +138,8 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
         if (row_ok && n0 + BLOCK_N > args.qk_cols) {          // this tile holds V columns
           // proportional guess (exact for equal-length documents), then walk: row0[s] <= row < row0[s + 1]
           const int ns = *args.n_slots_dev;
-          int sl = min(static_cast<int>(static_cast<long long>(row) * ns / M), ns - 1);
+          int sl = static_cast<int>(static_cast<float>(row) * (static_cast<float>(ns) / static_cast<float>(M)));   // a guess: float is fine
+          sl = max(min(sl, ns - 1), 0);
           while (__ldg(args.row0 + sl) > row) --sl;
           while (__ldg(args.row0 + sl + 1) <= row) ++sl;
           v_slot = sl;

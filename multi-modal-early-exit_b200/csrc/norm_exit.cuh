@@ -36,8 +36,8 @@ struct SlotRows {
 // Starts from the proportional guess row * n / M — exact when all documents have the same number of rows (two
 // independent loads), a few slots off for ragged batches — and walks from there.
 __device__ __forceinline__ int slot_of_row(const int* __restrict__ row0, int n, int M, int row) {
-  int s = static_cast<int>(static_cast<long long>(row) * n / max(M, 1));
-  s = min(s, n - 1);
+  int s = static_cast<int>(static_cast<float>(row) * (static_cast<float>(n) / static_cast<float>(max(M, 1))));   // a guess: float is fine
+  s = max(min(s, n - 1), 0);
   while (__ldg(row0 + s) > row) --s;
   while (__ldg(row0 + s + 1) <= row) ++s;
   return s;

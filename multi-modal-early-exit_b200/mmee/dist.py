@@ -48,3 +48,50 @@ def gather_results_fixed(packed: torch.Tensor, hist: torch.Tensor, out: torch.Te
     dist.all_gather_into_tensor(out, packed, group=group)
     dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
     return out
+
+
+def pack_results(logits: torch.Tensor, exit_index: torch.Tensor, criterion: torch.Tensor) -> torch.Tensor:
+    """[n, K + 2] fp32 rows: logits | exit index | criterion — one tensor per step for the gather."""
+    return torch.cat([logits, exit_index.to(torch.float32)[:, None], criterion.to(torch.float32)[:, None]], dim=1)
+
+
+class JobGatherer:
+    """The data-parallel job's results without a per-step host round-trip ("final gather").
+
+    Every step, each rank pushes its packed per-document results ([n_local, K + 2], see `pack_results`) and its exit
+    histogram; the rows are all-gathered asynchronously (NCCL's own stream over NVLink) into slot `step % capacity` of
+    a preallocated device ring and the histogram is accumulated on the device.  Nothing waits: a rank goes straight on
+    to its next forward, so the ranks do not run in lock-step.  `finish()` waits for the outstanding gathers, sums the
+    histograms over the ranks and returns the ring on the host — one device->host copy for the whole job.
+    Equal shards (n_local documents on every rank); `gather_results` handles uneven ones."""
+
+    def __init__(self, n_local: int, n_cols: int, n_hist: int, capacity: int, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.n_local = n_local
+        self.ring = torch.empty((max(capacity, 1), self.world * n_local, n_cols), dtype=torch.float32, device=device)
+        self.hist = torch.zeros((n_hist,), dtype=torch.int64, device=device)
+        self.pending = []
+        self.steps = 0
+
+    def push(self, packed: torch.Tensor, hist: torch.Tensor) -> int:
+        """Enqueue the gather of one step's results; returns the ring slot they land in."""
+        slot = self.steps % self.ring.shape[0]
+        self.pending.append((dist.all_gather_into_tensor(self.ring[slot], packed.contiguous(), group=self.group,
+                                                         async_op=True), packed))      # keep `packed` alive until waited
+        self.hist.add_(hist.to(self.hist.dtype))
+        self.steps += 1
+        return slot
+
+    def finish(self) -> Dict[str, torch.Tensor]:
+        """-> {"results": host [capacity, world * n_local, n_cols] (slots of the last `capacity` steps, rows in rank
+        order), "exit_hist": host int64 [n_hist] summed over steps and ranks, "steps": int}; resets the gatherer."""
+        for work, _ in self.pending:
+            work.wait()
+        self.pending.clear()
+        total = self.hist.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+        out = {"results": self.ring.cpu(), "exit_hist": total.cpu(), "steps": self.steps}
+        self.hist.zero_()
+        self.steps = 0
+        return out

@@ -171,6 +171,23 @@ def _gather_worker(rank, world, port_no, n_total, out_dir):
     gather_results_fixed(packed, h2, out)
     ok = ok and torch.equal(out[:, :16], logits[:n_eq]) and torch.equal(out[:, 16].int(), exits[:n_eq])
     ok = ok and torch.equal(h2, torch.bincount(exits[:n_eq].long(), minlength=14))
+    # per-step asynchronous gather into a ring, one read-back at the end (what bench.py does at N > 1)
+    from mmee.dist import JobGatherer, pack_results
+    jg = JobGatherer(per, 18, 14, capacity=3, device="cpu")
+    want_hist = torch.zeros(14, dtype=torch.int64)
+    for step in range(5):                                         # more steps than ring slots: the last 3 survive
+        lg = logits[:n_eq] + step
+        mine = slice(rank * per, (rank + 1) * per)
+        slot = jg.push(pack_results(lg[mine], exits[mine], crit[mine]), torch.bincount(exits[mine].long(), minlength=14))
+        ok = ok and slot == step % 3
+        want_hist += torch.bincount(exits[:n_eq].long(), minlength=14)
+    fin = jg.finish()
+    ok = ok and fin["steps"] == 5 and torch.equal(fin["exit_hist"], want_hist)
+    for step in (2, 3, 4):
+        rows = fin["results"][step % 3]
+        ok = ok and torch.equal(rows[:, :16], logits[:n_eq] + step) and torch.equal(rows[:, 16].int(), exits[:n_eq])
+        ok = ok and torch.equal(rows[:, 17], crit[:n_eq])
+    ok = ok and jg.steps == 0 and int(jg.hist.sum()) == 0
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("1" if ok else "0")
     dist.destroy_process_group()
 
