@@ -93,6 +93,7 @@ struct AttArgs {
   __nv_bfloat16* ctx_lo;       // kSplit: low part of ctx
   int H, heads, seq;           // seq: token pitch of the bias rows (max tokens per document)
   int tail16;                  // a last key tile with <= 16 real keys runs as a 16-key tile
+  int experiment;              // developer timing experiment (results are WRONG): bit 0 skip K / V^T loads, bit 1 skip bias loads
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -273,9 +274,16 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
         mbar_wait(kb_empty + st * 8, ((t / ATT_KB_STAGES) & 1) ^ 1);
         ATT_TRACE(2, t, 1)
         const uint32_t sk = sb + SMEM::KB_OFF + st * SMEM::KB_STAGE;
+        if (!kSplit && args.experiment && t >= 4) {
+          const uint32_t bytes = ((args.experiment & 1) ? 0 : SMEM::K_BYTES) + ((args.experiment & 2) ? 0 : SMEM::B_BYTES);
+          if (bytes) mbar_expect_tx(kb_full + st * 8, bytes); else mbar_arrive(kb_full + st * 8);
+          if (!(args.experiment & 1)) tma_load_2d(sk, &tmap_k, kb_full + st * 8, args.H + c.head * ATT_D, row0 + kv0);
+          if (!(args.experiment & 2)) tma_load_2d(sk + SMEM::NP * SMEM::K_BYTES, &tmap_bias, kb_full + st * 8, kv0, brow);
+        } else {
         mbar_expect_tx(kb_full + st * 8, SMEM::KB_STAGE);
         tma_load_2d(sk, &tmap_k, kb_full + st * 8, args.H + c.head * ATT_D, row0 + kv0);
         tma_load_2d(sk + SMEM::NP * SMEM::K_BYTES, &tmap_bias, kb_full + st * 8, kv0, brow);
+        }
         if constexpr (kSplit) {
           tma_load_2d(sk + SMEM::K_BYTES, &maps.k_lo, kb_full + st * 8, args.H + c.head * ATT_D, row0 + kv0);
           tma_load_2d(sk + 2 * SMEM::K_BYTES + SMEM::B_BYTES, &maps.bias_lo, kb_full + st * 8, kv0, brow);
@@ -312,10 +320,14 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
         if (t > 0) {
           const int sv = (t - 1) % ATT_V_STAGES;
           mbar_wait(v_empty + sv * 8, (((t - 1) / ATT_V_STAGES) & 1) ^ 1);
+          if (!kSplit && (args.experiment & 1) && t >= 4) {
+            mbar_arrive(v_full + sv * 8);
+          } else {
           mbar_expect_tx(v_full + sv * 8, SMEM::NP * ATT_D * ATT_BKV * 2);
           tma_load_2d(sb + SMEM::V_OFF + sv * SMEM::V_STAGE, &tmap_vt, v_full + sv * 8, pv_kv0, pv_row);
           if constexpr (kSplit)
             tma_load_2d(sb + SMEM::V_OFF + sv * SMEM::V_STAGE + SMEM::V_BYTES, &maps.vt_lo, v_full + sv * 8, pv_kv0, pv_row);
+          }
         }
         pv_row = vrow; pv_kv0 = kv0;
         ++t;

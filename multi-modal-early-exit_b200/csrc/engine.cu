@@ -994,7 +994,8 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     AttArgs aa;
     aa.slot_meta = e->plan_meta[rp].p; aa.qt_slot = e->plan_qt_slot[rp].p; aa.n_qt_dev = e->plan_n_qt[rp].p;
     aa.ctx = e->CTX.p; aa.ctx_lo = e->CTXlo.p; aa.H = H; aa.heads = heads; aa.seq = S;
-    aa.tail16 = (e->tail16 && !split) ? 1 : 0; aa.err_flag = e->err_flags.p; aa.trace = e->att_trace.p;
+    aa.tail16 = (e->tail16 && !split) ? 1 : 0;
+    aa.experiment = getenv("MMEE_ATT_EXPERIMENT") ? atoi(getenv("MMEE_ATT_EXPERIMENT")) : 0; aa.err_flag = e->err_flags.p; aa.trace = e->att_trace.p;
     {
       static bool configured_dev[64] = {};
       bool& configured = configured_dev[e->device & 63];   // the attribute is per device
