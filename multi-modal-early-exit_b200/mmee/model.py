@@ -369,6 +369,12 @@ class B200EEForSequenceClassification:
         return EarlyExitResult(exits_store=ex, predictions=logits.to(torch.float64), exit_distribution=dist,
                                criteria=crit.numpy(), exit_hist=h, logits=logits)
 
+    def sync(self) -> None:
+        """Wait for the forwards enqueued on torch's current stream (`infer_device` is asynchronous) and raise if a
+        device-side check tripped (input ids / boxes out of range, attention guard): `mmee_sync`."""
+        stream = torch.cuda.current_stream(torch.device("cuda", self.device_index)).cuda_stream or 1
+        _lib.check(self._lib.mmee_sync(self._h, C.c_void_p(stream)))
+
     # ------------------------------------------------------------------ introspection
     def last_launch_count(self) -> int:
         return int(self._lib.mmee_last_launch_count(self._h))
