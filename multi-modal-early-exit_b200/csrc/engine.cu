@@ -109,6 +109,7 @@ struct LayerW {
   DevBuf<float> bqkv, bo, bi, bo2, ln1_w, ln1_b, ln2_w, ln2_b;
   CUtensorMap t_wqkv, t_wo, t_wi, t_wo2;
   CUtensorMap t_wqkv_lo, t_wo_lo, t_wi_lo, t_wo2_lo;
+  std::vector<CUtensorMap> t_wo2_c, t_wo2_lo_c;             // fp32 engine mode: MLP-down weight in K chunks (see kchunk)
 };
 
 struct HeadW {
@@ -178,6 +179,13 @@ struct mmee_engine {
   DevBuf<__nv_bfloat16> QKlo, VTlo, CTXlo, MIDlo, PATCHlo;   // fp32 engine mode: low parts of every other GEMM / attention operand
   DevBuf<__half> BIASlo;                    // fp32 engine mode: low part of the attention bias
   DevBuf<float> X32[2], A132;               // fp32 engine mode: the residual stream itself in fp32 (exact residual adds)
+  // fp32 engine mode: the tensor core adds each K = 16 product block into the fp32 accumulator with truncation, so the
+  // error of a long contraction grows linearly with K (measured: 2e-5 relative at K = 3072 x 3 segments).  The MLP-down
+  // GEMM (K = inter) therefore runs in chunks of <= 1024: every chunk is its own launch whose residual epilogue adds
+  // the running sum Y in fp32 (round to nearest).
+  int kchunk = 0, n_kchunks = 1;
+  std::vector<CUtensorMap> t_mid_c, t_mid_lo_c;
+  DevBuf<float> zero_bias;
   bool precise_residual = true;
   DevBuf<float> Y, VIS, POOL, POOLV, POOLT, TXT, Z, T0, T1;
   bool has_vision_exit = false, has_text_exit = false;
@@ -523,6 +531,10 @@ void finalize(mmee_engine* e) {
       w.t_wo_lo = make_tmap_2d_sw128(w.wo_lo.p, H, H, H, wbox(e->bn_h));
       w.t_wi_lo = make_tmap_2d_sw128(w.wi_lo.p, I, H, H, wbox(e->bn_i));
       w.t_wo2_lo = make_tmap_2d_sw128(w.wo2_lo.p, H, I, I, wbox(e->bn_h));
+      for (int c = 0; c < e->n_kchunks; ++c) {
+        w.t_wo2_c.push_back(make_tmap_2d_sw128(w.wo2.p + static_cast<size_t>(c) * e->kchunk, H, e->kchunk, I, wbox(e->bn_h)));
+        w.t_wo2_lo_c.push_back(make_tmap_2d_sw128(w.wo2_lo.p + static_cast<size_t>(c) * e->kchunk, H, e->kchunk, I, wbox(e->bn_h)));
+      }
     }
   }
   e->t_patch_w = make_tmap_2d_sw128(e->patch_w.p, H, e->kdim_patch, e->kdim_patch, wbox(e->bn_h));
@@ -653,6 +665,13 @@ void allocate(mmee_engine* e) {
     e->t_a1_lo = make_tmap_2d_sw128(e->A1lo.p, M, H, H, 128);
     e->t_mid_lo = make_tmap_2d_sw128(e->MIDlo.p, M, I, I, 128);
     e->t_patch_lo = make_tmap_2d_sw128(e->PATCHlo.p, mp, e->kdim_patch, e->kdim_patch, 128);
+    e->kchunk = (I > 1024 && I % 1024 == 0) ? 1024 : ((I > 768 && I % 768 == 0) ? 768 : I);
+    e->n_kchunks = I / e->kchunk;
+    for (int c = 0; c < e->n_kchunks; ++c) {
+      e->t_mid_c.push_back(make_tmap_2d_sw128(e->MID.p + static_cast<size_t>(c) * e->kchunk, M, e->kchunk, I, 128));
+      e->t_mid_lo_c.push_back(make_tmap_2d_sw128(e->MIDlo.p + static_cast<size_t>(c) * e->kchunk, M, e->kchunk, I, 128));
+    }
+    e->zero_bias.alloc(H, true);
   }
 
   const int st = n_stages(e);
@@ -1039,7 +1058,16 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     ga.m_dev = mdev; ga.N = H; ga.K = I; ga.bias = w.bo2.p; ga.out = e->Y.p; ga.ld_out = H; ga.resid = e->A1.p;
     ga.resid_lo = e->A1lo.p;
     ga.resid_f32 = split ? e->A132.p : nullptr;
-    launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_mid, w.t_wo2, ga, st, &e->t_mid_lo, &w.t_wo2_lo);
+    if (split && e->n_kchunks > 1) {
+      // K chunks: Y = A1 + b + MID[:, 0:kc] W[:, 0:kc]^T, then Y += MID[:, c] W[:, c]^T in fp32 (see kchunk)
+      for (int c = 0; c < e->n_kchunks; ++c) {
+        ga.K = e->kchunk;
+        if (c > 0) { ga.bias = e->zero_bias.p; ga.resid_f32 = e->Y.p; }
+        launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_mid_c[c], w.t_wo2_c[c], ga, st, &e->t_mid_lo_c[c], &w.t_wo2_lo_c[c]);
+      }
+    } else {
+      launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_mid, w.t_wo2, ga, st, &e->t_mid_lo, &w.t_wo2_lo);
+    }
     mark(e, "gemm", st);
 
     const bool last = (l == e->L - 1);
