@@ -33,15 +33,7 @@
 
 namespace mmee {
 
-// Softmax warps.  kHalf (the bf16 throughput kernel): EIGHT warps, two threads per query row — warps w and w + 4 own
-// the same TMEM lane quarter and split every 64-key tile into its two 32-key halves.  The softmax warps are bound by the
-// length of their own per-tile instruction stream (tcgen05.ld -> 64 x (FADD, EX2, pack) -> tcgen05.st), not by a pipe:
-// halving the stream per thread halves the latency of the S -> P step.  The two threads of a row exchange one value per
-// tile (row maximum of the first tile, later the running maximum of s - ref) through shared memory and a 64-thread
-// named barrier.  Otherwise (fp32 mode, developer trace) four warps, one thread per row.
-__host__ __device__ constexpr int att_sm_warps(bool half) { return half ? 8 : 4; }
-__host__ __device__ constexpr int att_threads(bool half) { return 64 + att_sm_warps(half) * 32; }
-constexpr int ATT_SM_WARPS = 4;
+constexpr int ATT_SM_WARPS = 4;      // softmax warps: one thread per query row
 constexpr int ATT_THREADS = 64 + ATT_SM_WARPS * 32;
 constexpr int ATT_CTAS_PER_SM = 2;
 constexpr int ATT_BQ = 128;    // query rows per CTA
@@ -76,8 +68,7 @@ struct AttSmemT {
   static constexpr int BAR_OFF = I_OFF + I_BYTES;
   // q_full[2] q_empty[2] kb_full[KB] kb_empty[KB] v_full[V] v_empty[V] s_full[2] p_full[2] o_full[1] qt_full[1]
   static constexpr int N_BARS = 2 + 2 + 2 * ATT_KB_STAGES + 2 * ATT_V_STAGES + 2 + 2 + 1 + 1;
-  static constexpr int XCH_OFF = BAR_OFF + N_BARS * 8 + 16;    // kHalf: exchange buffer of the row halves, float [2][2][128]
-  static constexpr int TOTAL = XCH_OFF + 2 * 2 * ATT_BQ * 4;
+  static constexpr int TOTAL = BAR_OFF + N_BARS * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL;                      // the dynamic smem base itself is 1024 B aligned
   static constexpr uint32_t TMEM_COLS = kSplit ? 512 : 256;
 };
@@ -171,12 +162,10 @@ struct AttMaps {
   CUtensorMap q, k, vt, bias, q_lo, k_lo, vt_lo, bias_lo;
 };
 
-template <bool kTrace, bool kSplit = false, bool kHalf = false>
-__global__ void __launch_bounds__(att_threads(kHalf), kSplit ? 1 : ATT_CTAS_PER_SM)
+template <bool kTrace, bool kSplit = false>
+__global__ void __launch_bounds__(ATT_THREADS, kSplit ? 1 : ATT_CTAS_PER_SM)
 attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
-  static_assert(!(kHalf && (kSplit || kTrace)), "two threads per row: bf16 throughput kernel only");
   using SMEM = AttSmemT<kSplit>;
-  constexpr int SMW = att_sm_warps(kHalf);
   const CUtensorMap& tmap_q = maps.q;
   const CUtensorMap& tmap_k = maps.k;
   const CUtensorMap& tmap_vt = maps.vt;
@@ -222,13 +211,13 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
     }
     uint64_t* b = bars;
     for (int i = 0; i < 2; ++i) mbar_init(b++, 1);                  // q_full
-    for (int i = 0; i < 2; ++i) mbar_init(b++, SMW);                // q_empty: the softmax warps copied Q to TMEM
+    for (int i = 0; i < 2; ++i) mbar_init(b++, ATT_SM_WARPS);       // q_empty: the softmax warps copied Q to TMEM
     for (int i = 0; i < 2 * ATT_KB_STAGES; ++i) mbar_init(b++, 1);  // kb_full, kb_empty (S commit)
     for (int i = 0; i < 2 * ATT_V_STAGES; ++i) mbar_init(b++, 1);   // v_full, v_empty (P V commit)
     for (int i = 0; i < 2; ++i) mbar_init(b++, 1);                  // s_full
-    for (int i = 0; i < 2; ++i) mbar_init(b++, SMW);                // p_full
+    for (int i = 0; i < 2; ++i) mbar_init(b++, ATT_SM_WARPS);       // p_full
     mbar_init(b++, 1);                                              // o_full
-    mbar_init(b++, SMW);                                            // qt_full
+    mbar_init(b++, ATT_SM_WARPS);                                   // qt_full
     fence_mbar_init();
   }
   // constant rows 64..79 of every V^T tile: row 64 = 1.0 (PV then also yields the row sum of P), rest 0
@@ -438,195 +427,6 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
         umma_commit(v_empty + sv * 8);
         cp = att_next(cp, total_items, stride, args);
       }
-    }
-  } else if constexpr (kHalf) {
-    // ------------------------------------------------------------ softmax (warps 2..9), two threads per query row
-    const int quarter = warp & 3;                             // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;                         // which 32 keys of every 64-key tile (and 32 output dims)
-    const int r = quarter * 32 + lane;                        // query row within the tile == TMEM lane
-    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    float* xbuf = reinterpret_cast<float*>(smem + SMEM::XCH_OFF);
-    const uint32_t bar_id = 1u + static_cast<uint32_t>(quarter);   // named barrier of the warp pair (w, w + 4)
-    uint32_t xcnt = 0;
-    // max over the two halves of the row; double-buffered: exchange k + 2 reuses the slot of exchange k, and the partner
-    // has read that slot before it arrived at the barrier of exchange k + 1
-    auto xchg_max = [&](float v) -> float {
-      float* bfr = xbuf + (xcnt & 1u) * (2 * ATT_BQ);
-      bfr[half * ATT_BQ + r] = v;
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-      const float o = bfr[(half ^ 1) * ATT_BQ + r];
-      ++xcnt;
-      return fmaxf(v, o);
-    };
-    uint32_t t = 0;
-    AttCursor c = att_first(total_items, stride, args);
-    float ref = 0.f, alpha_pend = 1.f;
-    __nv_bfloat16* out_ptr = nullptr;                         // this thread's 32 ctx columns of the open item (nullptr: row beyond the document)
-    bool have_item = false;
-
-    // O (TMEM) / row sum -> ctx[row, head*64 + half*32 .. +31]; the caller has waited for the item's last P V
-    auto store_item = [&](__nv_bfloat16* dst_row) {
-      uint32_t v[32];
-      const uint32_t lsum = tmem_ld1(tmem_O + lane_addr + ATT_D);
-      tmem_ld32(tmem_O + lane_addr + half * 32, v);
-      tmem_ld_wait();
-      const float inv = 1.0f / __uint_as_float(lsum);
-      if (dst_row) {
-        uint4* dst = reinterpret_cast<uint4*>(dst_row);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          dst[i] = make_uint4(pack_bf16x2(__uint_as_float(v[i * 8 + 0]) * inv, __uint_as_float(v[i * 8 + 1]) * inv),
-                              pack_bf16x2(__uint_as_float(v[i * 8 + 2]) * inv, __uint_as_float(v[i * 8 + 3]) * inv),
-                              pack_bf16x2(__uint_as_float(v[i * 8 + 4]) * inv, __uint_as_float(v[i * 8 + 5]) * inv),
-                              pack_bf16x2(__uint_as_float(v[i * 8 + 6]) * inv, __uint_as_float(v[i * 8 + 7]) * inv));
-      }
-    };
-    // Q of item `ii`: this thread's half (32 bf16 = 16 TMEM columns) of its row, smem (TMA, SW128) -> TMEM A operand
-    auto q_to_tmem = [&](int ii) {
-      const int qb = ii & 1;
-      mbar_wait(q_full + qb * 8, (ii >> 1) & 1);
-      const uint32_t qrow = sb + SMEM::Q_OFF + qb * SMEM::Q_STAGE + r * 128;
-      uint32_t q[16];
-#pragma unroll
-      for (int cch = 0; cch < 4; ++cch) {
-        const uint4 x = lds128(qrow + (((half * 4 + cch) ^ (r & 7)) << 4));
-        q[4 * cch] = x.x; q[4 * cch + 1] = x.y; q[4 * cch + 2] = x.z; q[4 * cch + 3] = x.w;
-      }
-      tmem_st16(tmem_Q + lane_addr + half * 16, q);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(qt_full); mbar_arrive(q_empty + qb * 8); }
-    };
-    if (c.valid) q_to_tmem(0);
-
-    while (c.valid) {
-      const int b = t & 1;
-      const bool first = (c.j == 0);                         // first key tile of a new item
-      const uint32_t tS = tmem_S + lane_addr + b * ATT_BKV;
-      __nv_bfloat16* prev_out = out_ptr;
-      if (first) {
-        const int q = c.q0 + r;
-        out_ptr = (q < c.rows) ? args.ctx + static_cast<size_t>(c.row0 + q) * args.H + c.head * ATT_D + half * 32 : nullptr;
-      }
-      mbar_wait(s_full + b * 8, (t >> 1) & 1);      // S_t = Q K^T + bias (+ key mask) is complete
-      tc_fence_after();
-      // last tile of this item: every S MMA that reads the item's Q has completed -> stage the next item's Q
-      if (c.j == c.last_j && c.nitem < total_items) q_to_tmem(c.ii + 1);
-
-      float pmax;
-      if (c.j == c.tail_j) {
-        // 16-key tail tile (never the first tile of an item): half 0 does the 16 keys, half 1 only takes part in the exchange
-        uint32_t v[16], pq[8];
-        float m = -INFINITY;
-        if (half == 0) {
-          tmem_ld16(tS, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float a0 = __uint_as_float(v[2 * i]) - ref, a1 = __uint_as_float(v[2 * i + 1]) - ref;
-            m = fmaxf(m, fmaxf(a0, a1));
-            pq[i] = pack_bf16x2(fast_exp2(a0), fast_exp2(a1));
-          }
-        }
-        pmax = xchg_max(m);
-        if (pmax > ATT_JUMP) {                       // see the full-tile path below
-          const float dq = ceilf(pmax);
-          ref += dq;
-          alpha_pend *= fast_exp2(-dq);
-          pmax -= dq;
-          if (half == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              pq[i] = pack_bf16x2(fast_exp2(__uint_as_float(v[2 * i]) - ref), fast_exp2(__uint_as_float(v[2 * i + 1]) - ref));
-          }
-        }
-        __syncwarp();
-        if (half == 0) tmem_st8(tS, pq);
-      } else {
-        uint32_t v[32];                                // the 32 scores; P pairs are packed in place (v[i] <- keys 2i, 2i + 1)
-        tmem_ld32(tS + half * 32, v);
-        tmem_ld_wait();
-        if (first) {
-          // exact row maximum of the first tile as the reference (max over both halves), then p = exp2(s - ref)
-          float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
-#pragma unroll
-          for (int i = 2; i < 32; i += 2) m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-          ref = xchg_max(m0);
-        }
-        float m0 = -INFINITY;
-        uint64_t nref2;
-        asm("mov.b64 %0, {%1, %1};" : "=l"(nref2) : "f"(-ref));
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float a0, a1;                                // s - ref, two per packed-fp32 instruction (FADD2)
-          sub_ref_x2(v[2 * i], v[2 * i + 1], nref2, a0, a1);
-          m0 = fmaxf(m0, fmaxf(a0, a1));
-          v[i] = pack_bf16x2(fast_exp2(a0), fast_exp2(a1));
-        }
-        pmax = first ? 0.f : xchg_max(m0);             // one exchange per tile: the row maximum (first) or the running one
-        if (pmax > ATT_JUMP) {
-          // a score of this tile is more than 2^40 above the row reference: raise the reference NOW, recompute this
-          // row's P against it (the scores are still in TMEM) and fold the factor into the rescale of O below; both
-          // halves of the row take the same decision
-          const float dq = ceilf(pmax);
-          ref += dq;
-          alpha_pend *= fast_exp2(-dq);
-          pmax -= dq;
-          tmem_ld32(tS + half * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            v[i] = pack_bf16x2(fast_exp2(__uint_as_float(v[2 * i]) - ref), fast_exp2(__uint_as_float(v[2 * i + 1]) - ref));
-        }
-        __syncwarp();
-        tmem_st16(tS + half * 16, v);
-      }
-
-      // ---- P V_{t-1} must be complete before O is read (new item) or rescaled, and before P V_t may be issued
-      if (t > 0) {
-        mbar_wait(o_full, (t - 1) & 1);
-        tc_fence_after();
-        if (first) {
-          if (have_item) store_item(prev_out);
-        } else if (__any_sync(0xffffffffu, alpha_pend != 1.0f)) {    // rare: an earlier tile raised the row reference
-          if (half == 0) {                                           // (the partner warp sees the same rows and factors)
-            uint32_t o[32];
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              tmem_ld32(tmem_O + lane_addr + hh * 32, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha_pend);
-              tmem_st32(tmem_O + lane_addr + hh * 32, o);
-            }
-            const uint32_t ls = tmem_ld1(tmem_O + lane_addr + ATT_D);
-            tmem_ld_wait();
-            tmem_st1(tmem_O + lane_addr + ATT_D, __float_as_uint(__uint_as_float(ls) * alpha_pend));
-          }
-        }
-      }
-      have_item = true;
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full + b * 8);
-
-      // ---- reference for the following tiles (lazy: only when a score ran more than 2^8 above it)
-      alpha_pend = 1.f;
-      if (pmax > ATT_LAZY) {
-        const float dq = ceilf(pmax);
-        ref += dq;
-        alpha_pend = fast_exp2(-dq);
-        if (!(alpha_pend > 0.f)) *args.err_flag = 1;       // unreachable with the jump handling above; kept as a guard
-      }
-      ++t;
-      c = att_next(c, total_items, stride, args);
-    }
-    if (have_item) {
-      mbar_wait(o_full, (t - 1) & 1);
-      tc_fence_after();
-      store_item(out_ptr);
     }
   } else {
     // ------------------------------------------------------------ softmax (warps 2..5), thread = query row

@@ -140,7 +140,6 @@ struct mmee_engine {
   // ragged encoder layout (norm_exit.cuh): kept tokens per document and the row plans of two consecutive exit stages
   DevBuf<int> doc_len, kept_idx, plan_row0[2], plan_qt_slot[2], plan_n_qt[2];
   DevBuf<int4> plan_meta[2];
-  bool att_full_row = false;       // developer A/B switch (MMEE_ATT_FULLROW=1): one softmax thread per query row (the round-1 kernel)
   bool tail16 = true;              // attention: a last key tile with <= 16 real keys runs as a 16-key tile (MMEE_NO_TAIL16=1: off)
   DevBuf<float> lte_w, slot_lte;   // learned-to-exit scorer [H] (optional) and its per-slot scores
   float lte_b = 0.f;
@@ -1020,7 +1019,6 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
       static bool configured_dev[64] = {};
       bool& configured = configured_dev[e->device & 63];   // the attribute is per device
       if (!configured) {
-        CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
         CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
         CUDA_OK(cudaFuncSetAttribute(attention_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
         CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmemT<true>::DYN_BYTES));
@@ -1035,10 +1033,8 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
         attention_kernel<false, true><<<att_grid, ATT_THREADS, AttSmemT<true>::DYN_BYTES, st>>>(am, aa);
       else if (e->trace_on && l == 0)
         attention_kernel<true, false><<<att_grid, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(am, aa);
-      else if (e->att_full_row)
-        attention_kernel<false, false><<<att_grid, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(am, aa);
       else
-        attention_kernel<false, false, true><<<att_grid, att_threads(true), AttSmem::DYN_BYTES, st>>>(am, aa);
+        attention_kernel<false, false><<<att_grid, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(am, aa);
       CUDA_OK(cudaGetLastError());
       e->launches++;
     }
@@ -1202,7 +1198,6 @@ int mmee_create(const mmee_model_desc* desc, int device, int max_batch, mmee_eng
   // a last key tile with <= 16 real keys (an unpadded document, S = 709: 5) runs as a 16-key tile (N = 16 MMAs, a quarter of
   // the softmax work); decided per document by the attention kernel (documents are ragged)
   e->tail16 = !getenv("MMEE_NO_TAIL16");
-  e->att_full_row = getenv("MMEE_ATT_FULLROW") != nullptr;
   e->bias_width = e->bias_pitch;
   if (e->kv_pitch > 1024) throw std::runtime_error("sequence too long for keymask_kernel");
   e->sms = prop.multiProcessorCount;
