@@ -2,7 +2,9 @@
 
     python tests/debug_stages.py [tiny|base] [n_docs]
 
-Runs a 1-layer model so the activation buffers hold layer-0 intermediates after the forward."""
+Runs a 1-layer model on UNPADDED documents (the encoder buffers use the ragged row layout: without padding a document's
+rows are its 709 tokens in order, so the buffers compare one to one) so the activation buffers hold layer-0
+intermediates after the forward.  X0 = dense embedding output, X1 = the same rows after the ragged gather."""
 import os
 import sys
 
@@ -38,7 +40,7 @@ def main():
     ee = ExitConfig.from_dict(dict(exits=["text_visual_concat", 1], encoder_layer_strategy="ramp",
                                    inference_strategy="max_confidence"))
     sd = synth.make_state_dict(dims, ee, seed=0)
-    docs = synth.make_docs(dims, n, seed=3)
+    docs = synth.make_docs(dims, n, seed=3, pad=False)
     S, H, T, h = dims.seq, dims.hidden, dims.n_text, dims.heads
     model = B200EEForSequenceClassification(dims, ee, sd, device=0, max_batch=n)
     dev = {k: v.cuda() for k, v in docs.items()}
