@@ -1488,6 +1488,9 @@ template <int NE>
 void launch_policy_hist(bool strict, unsigned blocks, size_t smem, const mmee_policy_store* ps, const double* thr,
                         int64_t n_thr, int cmp, int n_test, int fallback, long long* hist, long long* correct) {
   const unsigned long long* cm = ps->has_labels ? ps->cmask.p : nullptr;
+  // [chunk][E1 + 1] doubles of staged criteria: above the 48 KB default from E1 = 24 on
+  CUDA_OK(cudaFuncSetAttribute(policy_hist_kernel<NE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  CUDA_OK(cudaFuncSetAttribute(policy_hist_kernel<NE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   if (strict)
     policy_hist_kernel<NE, true><<<blocks, POLICY_HIST_THREADS, smem>>>(ps->crit.p, cm, thr, ps->E1, ps->N, n_thr, cmp,
                                                                         n_test, fallback, hist, correct);

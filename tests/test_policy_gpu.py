@@ -210,6 +210,23 @@ def test_large_mixture_sweep_equals_oracle(crit_name):
             assert np.array_equal(pol.hist[t], np.bincount(want, minlength=E1))
 
 
+def test_mixture_sweep_many_exits():
+    """A store with 40 exits (criteria stage above the 48 KB default shared-memory limit, 64-wide register histogram)."""
+    from mmee.policy import PolicyStore
+    rng = np.random.default_rng(12)
+    E1, N, K, M = 40, 700, 8, 3000
+    labels = rng.integers(0, K, size=N)
+    lg = rng.normal(size=(E1, N, K)) * np.linspace(0.5, 3.0, E1)[:, None, None]
+    with PolicyStore(lg, "max_confidence", labels=labels) as st:
+        csf = st.criteria()
+        lo, hi = np.percentile(csf, 5, axis=1), np.percentile(csf, 99.5, axis=1)
+        thr2d = lo[None, :] + rng.random((M, E1)) * (hi - lo)[None, :]
+        res = st.mixture_sweep(thr2d)
+        ex = (csf[None, :, :] >= thr2d[:, :, None]).argmax(1)
+        assert np.array_equal(res.hist, (ex[:, :, None] == np.arange(E1)[None, None, :]).sum(1))
+        assert np.array_equal(res.correct, ((lg.argmax(-1) == labels[None, :]).T[np.arange(N)[None, :], ex]).sum(1))
+
+
 def test_sweep_with_exits_beyond_grid_limit():
     """n_thr > 65 535 with the index matrix requested: chunked over grid.y."""
     from mmee.policy import PolicyStore
