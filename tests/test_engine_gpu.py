@@ -332,6 +332,53 @@ def test_batch256_parity_and_exit_agreement_vs_port(pad, dtype):
     model.close()
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_many_ragged_documents_multi_chunk_compaction(dtype):
+    """600 documents (the compaction / row-plan block walks the slots in three chunks of 256) with text lengths from 2
+    to 512, all three embedding-level exits and encoder exits: real early exit == post-hoc policy on the dense run, bit
+    for bit, at thresholds that spread the documents over every exit; dense logits vs the oracle port; the row plan
+    keeps every document's rows together (a wrong prefix sum shows up as garbage logits)."""
+    from mmee.model import B200EEForSequenceClassification
+
+    dims = ModelDims.tiny(layers=3)
+    ee = ExitConfig.from_dict(dict(exits=["vision_avg", "text_avg", "text_visual_concat", 1, 2, 3],
+                                   encoder_layer_strategy="ramp", inference_strategy="max_confidence"))
+    sd = synth.make_state_dict(dims, ee, seed=13, std=0.05)
+    n = 600
+    docs = synth.make_docs(dims, n, seed=61, pad=True)
+    g = torch.Generator().manual_seed(3)
+    short = torch.randint(2, 40, (n,), generator=g)
+    for d in range(0, n, 7):                                      # every 7th document is very short
+        L = int(short[d])
+        docs["input_ids"][d, L:] = dims.pad_id
+        docs["input_ids"][d, L - 1] = 2
+        docs["attention_mask"][d, L:] = 0
+        docs["bbox"][d, L - 1:] = 0
+    model = B200EEForSequenceClassification(dims, ee, sd, device=0, max_batch=n, dtype=dtype)
+    dev = _cuda(docs)
+    dense = model.infer(**dev, exit_threshold=2.0, early_exit=False, return_all=True)
+    al = dense.all_exit_logits.cpu().numpy()
+    assert np.isfinite(al).all()
+    want = port_forward_chunked(sd, dims, ee, docs, chunk=64).numpy()
+    err = np.abs(al - want).max()
+    print(f"600 ragged tiny documents [{dtype}]: max|logits - port| = {err:.3e}")
+    assert err <= TOL[dtype]
+    temps = spread_temperatures(al, "max_confidence")
+    seen = np.zeros(al.shape[0], dtype=np.int64)
+    for thr in (0.46, 0.55, 0.7, 0.85, 0.97):
+        a = model.infer(**dev, exit_threshold=thr, temperatures=temps, return_all=True)
+        b = model.infer(**dev, exit_threshold=thr, temperatures=temps, early_exit=False)
+        assert np.array_equal(a.exits_store, b.exits_store) and torch.equal(a.logits, b.logits)
+        assert np.array_equal(a.exit_hist, b.exit_hist) and a.exit_hist.sum() == n
+        x, y = a.all_exit_logits.cpu().numpy(), al
+        reached = np.arange(x.shape[0])[:, None] <= a.exits_store[None, :]
+        assert np.array_equal(x[reached], y[reached]) and np.isnan(x[~reached]).all()
+        seen += a.exit_hist
+    print("  documents per exit over the five thresholds:", seen.tolist())
+    assert (seen > 0).sum() >= 5                                   # the thresholds really spread the exits
+    model.close()
+
+
 def test_out_of_range_inputs_raise_like_the_reference():
     """ADVICE r1: the reference raises IndexError for an input_id >= vocab or a bbox coordinate outside [0, max_2d);
     the engine must not read out of bounds: it clamps on the device and the synchronous call reports an error."""
