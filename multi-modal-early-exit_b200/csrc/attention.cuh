@@ -256,14 +256,27 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
       while (c.valid) {
         const int row0 = c.row0;
         if (c.ii != loaded_ii) {
+          // Q tiles are loaded ONE ITEM AHEAD: at the first key tile of item ii the producer fetches the Q of item
+          // ii + 1 into the other Q buffer (free since the softmax warps copied item ii - 1's Q to TMEM), so that the
+          // copy of the next Q to TMEM at the end of this item finds it in shared memory (loaded on arrival at the
+          // item, it was ~2500 cycles late: the producer runs only two key tiles ahead of the MMAs)
           loaded_ii = c.ii;
-          const int qb = c.ii & 1;
+          auto load_q = [&](int k, int qrow, int qhead) {          // Q of this CTA's k-th item -> buffer k & 1
+            const int qb = k & 1;
+            mbar_wait(q_empty + qb * 8, ((k >> 1) & 1) ^ 1);
+            mbar_expect_tx(q_full + qb * 8, SMEM::Q_STAGE);
+            tma_load_2d(sb + SMEM::Q_OFF + qb * SMEM::Q_STAGE, &tmap_q, q_full + qb * 8, qhead * ATT_D, qrow);
+            if constexpr (kSplit)
+              tma_load_2d(sb + SMEM::Q_OFF + qb * SMEM::Q_STAGE + SMEM::Q_BYTES, &maps.q_lo, q_full + qb * 8, qhead * ATT_D, qrow);
+          };
           ATT_TRACE(2, t, 2)
-          mbar_wait(q_empty + qb * 8, ((c.ii >> 1) & 1) ^ 1);
-          mbar_expect_tx(q_full + qb * 8, SMEM::Q_STAGE);
-          tma_load_2d(sb + SMEM::Q_OFF + qb * SMEM::Q_STAGE, &tmap_q, q_full + qb * 8, c.head * ATT_D, row0 + c.q0);
-          if constexpr (kSplit)
-            tma_load_2d(sb + SMEM::Q_OFF + qb * SMEM::Q_STAGE + SMEM::Q_BYTES, &maps.q_lo, q_full + qb * 8, c.head * ATT_D, row0 + c.q0);
+          if (c.ii == 0) load_q(0, row0 + c.q0, c.head);
+          if (c.nitem < total_items) {
+            const int nn_qt = (c.nmeta.y + ATT_BQ - 1) / ATT_BQ;
+            const int nlocal = c.nitem - args.heads * c.nmeta.w;
+            const int nhead = nlocal / nn_qt;
+            load_q(c.ii + 1, c.nmeta.x + (nlocal - nhead * nn_qt) * ATT_BQ, nhead);
+          }
         }
         const int kv0 = c.j * ATT_BKV;
         const int brow = (c.doc * args.heads + c.head) * S + c.q0;
@@ -346,7 +359,6 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, ATT_BKV);
-      constexpr uint32_t idesc_b = umma_idesc_f16(ATT_BQ, ATT_BKV);
       constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, ATT_DV);
       constexpr uint32_t idesc_s16 = umma_idesc_bf16(ATT_BQ, 16);   // the 16-key tail tile (args.tail_j)
       constexpr uint32_t idesc_b16 = umma_idesc_f16(ATT_BQ, 16);
@@ -376,15 +388,21 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
           for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ts(d_s, tmem_Qlo + k * 8, dk + 2 * k, idesc_s, 1u);
 #pragma unroll
           for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ts(d_s, tmem_Q + k * 8, dkl + 2 * k, idesc_s, 1u);
+          // bias x identity, block-diagonal (see the bf16 path below)
 #pragma unroll
-          for (int k = 0; k < ATT_BKV / 16; ++k) umma_bf16_ss(d_s, db + 2 * k, di + 2 * k, idesc_b, 1u);
+          for (int k = 0; k < ATT_BKV / 16; ++k) umma_bf16_ss(d_s + 16 * k, db + 2 * k, di + 130 * k, idesc_b16, 1u);
 #pragma unroll
-          for (int k = 0; k < ATT_BKV / 16; ++k) umma_bf16_ss(d_s, dbl + 2 * k, di + 2 * k, idesc_b, 1u);
+          for (int k = 0; k < ATT_BKV / 16; ++k) umma_bf16_ss(d_s + 16 * k, dbl + 2 * k, di + 130 * k, idesc_b16, 1u);
         } else if (cs.j != cs.tail_j) {
 #pragma unroll
           for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ts(d_s, tmem_Q + k * 8, dk + 2 * k, idesc_s, k ? 1u : 0u);
+          // += bias16 x I, block by block: key block k of the bias tile only meets the k-th 16 x 16 diagonal block of
+          // the identity, so each of the four MMAs has N = 16 (output columns 16k .. 16k + 15) instead of N = 64: a
+          // quarter of the tensor-pipe time, the same bits (the off-diagonal blocks only ever added exact zeros), and
+          // the four no longer form a dependent chain on one accumulator.  Identity rows 16k .. at byte 2048 k (two
+          // 8-row swizzle atoms), its K block k at +32 k bytes: descriptor + 128 k + 2 k.
 #pragma unroll
-          for (int k = 0; k < ATT_BKV / 16; ++k) umma_bf16_ss(d_s, db + 2 * k, di + 2 * k, idesc_b, 1u);   // += bias16 x I
+          for (int k = 0; k < ATT_BKV / 16; ++k) umma_bf16_ss(d_s + 16 * k, db + 2 * k, di + 130 * k, idesc_b16, 1u);
         } else {
           // only keys 0..15 of the tile exist: N = 16 (K rows 0..15, bias columns 0..15, one identity block)
 #pragma unroll

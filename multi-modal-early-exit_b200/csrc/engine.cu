@@ -1019,8 +1019,8 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
       static bool configured_dev[64] = {};
       bool& configured = configured_dev[e->device & 63];   // the attribute is per device
       if (!configured) {
-        CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
-        CUDA_OK(cudaFuncSetAttribute(attention_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
+        CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES + 16 * 1024));
+        CUDA_OK(cudaFuncSetAttribute(attention_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES + 16 * 1024));
         CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmemT<true>::DYN_BYTES));
         configured = true;
       }
@@ -1028,13 +1028,17 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
       am.q = e->t_qk; am.k = e->t_k64; am.vt = e->t_vt; am.bias = e->t_bias;
       if (split) { am.q_lo = e->t_qk_lo; am.k_lo = e->t_k64_lo; am.vt_lo = e->t_vt_lo; am.bias_lo = e->t_bias_lo; }
       else { am.q_lo = e->t_qk; am.k_lo = e->t_k64; am.vt_lo = e->t_vt; am.bias_lo = e->t_bias; }
-      const int att_grid = e->sms * (split ? 1 : ATT_CTAS_PER_SM);
+      // developer experiment MMEE_ATT_ONE_CTA=1: one attention CTA per SM (extra dynamic shared memory keeps the second
+      // one out) — shows what a softmax warp does when it has its scheduler's MUFU to itself
+      static const bool one_cta = getenv("MMEE_ATT_ONE_CTA") != nullptr;
+      const int att_grid = e->sms * ((split || one_cta) ? 1 : ATT_CTAS_PER_SM);
+      const size_t att_smem = AttSmem::DYN_BYTES + (one_cta ? 16 * 1024 : 0);
       if (split)
         attention_kernel<false, true><<<att_grid, ATT_THREADS, AttSmemT<true>::DYN_BYTES, st>>>(am, aa);
       else if (e->trace_on && l == 0)
-        attention_kernel<true, false><<<att_grid, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(am, aa);
+        attention_kernel<true, false><<<att_grid, ATT_THREADS, att_smem, st>>>(am, aa);
       else
-        attention_kernel<false, false><<<att_grid, ATT_THREADS, AttSmem::DYN_BYTES, st>>>(am, aa);
+        attention_kernel<false, false><<<att_grid, ATT_THREADS, att_smem, st>>>(am, aa);
       CUDA_OK(cudaGetLastError());
       e->launches++;
     }
