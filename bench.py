@@ -341,9 +341,10 @@ def calibrate_temperatures(model, dims, kind, dev, n_docs=64):
     return spread_temperatures(cal.all_exit_logits.cpu().numpy(), kind)
 
 
-def timed_region(fn, steps, warmup, world, dev, finish=None):
+def timed_region(fn, steps, warmup, world, dev, finish=None, before_timed=None):
     """W untimed + K timed calls of fn bracketed by barrier + synchronize on both sides, CUDA events on the current
-    stream, MAX over ranks.  `finish` (optional) runs inside the timed region after the last step (final gather)."""
+    stream, MAX over ranks.  `finish` (optional) runs inside the timed region after the last step (final gather);
+    `before_timed` (optional) runs after the warm-up, outside the timed region."""
     import torch.distributed as dist
 
     for _ in range(warmup):
@@ -351,6 +352,8 @@ def timed_region(fn, steps, warmup, world, dev, finish=None):
     if finish:
         finish()
     torch.cuda.synchronize()
+    if before_timed:
+        before_timed()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -438,10 +441,10 @@ def run_single(args, world, rank, local, dev):
         r["job_hist"] = job_hist
         return r
 
-    model.set_profiling(True)
     with ClockSampler(local, enabled=True) as clk:
-        ms_step, res = timed_region(step_device, steps, args.warmup, world, dev, finish_device)
-    stage = model.last_stage_ms()          # per-stage CUDA-event times of the last timed step
+        ms_step, res = timed_region(step_device, steps, args.warmup, world, dev, finish_device,
+                                    before_timed=lambda: model.set_profiling(True))
+    stage = model.last_stage_ms()          # per-stage CUDA-event times, averaged over the timed steps
     launches = model.last_launch_count()
     model.set_profiling(False)
     value = world * B / (ms_step / 1000.0)
@@ -556,7 +559,7 @@ def run_single(args, world, rank, local, dev):
                 "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
                 "attention": {"achieved": attn_tf, "unit": "TFLOP/s", "frac": (attn_tf / pk["tf_sust"]) if attn_tf else None,
                               "traffic": att_traffic},
-                "stage_ms": stage,
+                "stage_ms": stage, "stage_ms_note": "CUDA events between the stages of every timed step, averaged over the timed steps",
                 "whole_step_frac": (gemm_flops + attn_flops) / (ms_step / 1000.0) / 1e12 / pk["tf_sust"]}
     if dtype == "fp32":
         roofline["note"] = ("algorithmic (fp32-equivalent) FLOPs; the tensor cores execute 3x that in bf16 products: "

@@ -125,8 +125,9 @@ int  mmee_forward_collect(mmee_engine* e, int ticket, const mmee_outputs* out);
 
 /* Number of kernels launched by the engine in the last forward (for the bench's gpu_launches). */
 int64_t mmee_last_launch_count(mmee_engine* e);
-/* Device time of the named stage of the last forward in ms ("total", "embed", "gemm", "attention", "norm", "exit");
- * only recorded when mmee_set_profiling(e, 1) is on (adds event records between stages). */
+/* Device time per stage ("total", "embed", "gemm", "attention", "norm", "exit"), SUMMED in ms over the forwards run
+ * since profiling was switched on or last collected, and the number of those forwards ("forwards"): only recorded when
+ * mmee_set_profiling(e, 1) is on (adds event records between stages; calling it again restarts the accumulation). */
 int  mmee_set_profiling(mmee_engine* e, int on);
 /* Wait for the forwards enqueued on `cuda_stream` (NULL: the engine's own stream), fold the stage events and turn a
  * tripped attention guard into an error: what the synchronous entry points do before they return, for callers of the

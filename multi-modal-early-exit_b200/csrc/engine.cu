@@ -713,8 +713,10 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
   const bool leave = pol->mode == 1;
   const bool gate = d.head_kind == 1;
   e->launches = 0;
-  for (auto& x : e->ev) cudaEventDestroy(x.second);
-  e->ev.clear();
+  if (!e->profiling || e->ev.size() > 100000) {          // profiling: the events of every forward since the last
+    for (auto& x : e->ev) cudaEventDestroy(x.second);    // collect are kept and folded together (stage averages)
+    e->ev.clear();
+  }
   // the engine has ONE set of scratch buffers: a forward on any stream is ordered after the previous forward (recorded
   // at its end below), whichever stream that one ran on
   CUDA_OK(cudaStreamWaitEvent(st, e->last_done, 0));
@@ -1130,17 +1132,25 @@ void check_error_flags(mmee_engine* e) {
   }
 }
 
+// Folds the stage events of every forward recorded since the last call into per-stage SUMS (ms) plus the number of
+// forwards ("forwards"); callers divide.  The interval between one forward's "end" and the next one's "start" is not
+// a stage.  No new events -> the previous result stays.
 void collect_profile(mmee_engine* e) {
-  e->stage_ms.clear();
   if (!e->profiling || e->ev.size() < 2) return;
-  double total = 0;
-  for (size_t i = 1; i < e->ev.size(); ++i) {
+  e->stage_ms.clear();
+  double total = 0, forwards = 0;
+  for (size_t i = 0; i < e->ev.size(); ++i) {
+    if (e->ev[i].first == "start") { forwards += 1; continue; }
+    if (i == 0) continue;
     float ms = 0;
-    cudaEventElapsedTime(&ms, e->ev[i - 1].second, e->ev[i].second);
+    if (cudaEventElapsedTime(&ms, e->ev[i - 1].second, e->ev[i].second) != cudaSuccess) continue;
     e->stage_ms[e->ev[i].first] += ms;
     total += ms;
   }
   e->stage_ms["total"] = total;
+  e->stage_ms["forwards"] = forwards;
+  for (auto& x : e->ev) cudaEventDestroy(x.second);
+  e->ev.clear();
 }
 
 }  // namespace
@@ -1743,6 +1753,9 @@ int mmee_calibration_stats(int device, int n_exits_plus1, int64_t n_samples, int
 
 int mmee_set_profiling(mmee_engine* e, int on) {
   if (!e) return -1;
+  for (auto& x : e->ev) cudaEventDestroy(x.second);    // (re)start the accumulation
+  e->ev.clear();
+  e->stage_ms.clear();
   e->profiling = (on & 1) != 0;
   e->trace_on = (on & 2) != 0;     // developer trace of the first layer's attention kernel (debug_read "ATT_TRACE")
   return 0;

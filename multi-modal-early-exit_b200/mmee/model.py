@@ -391,9 +391,14 @@ class B200EEForSequenceClassification:
         return buf
 
     def last_stage_ms(self) -> Dict[str, float]:
+        """Per-stage device time in ms, AVERAGED over the forwards run since `set_profiling(True)` (or the previous
+        call); "forwards" = how many that were."""
         _lib.check(self._lib.mmee_collect_profile(self._h))
-        return {k: float(self._lib.mmee_last_stage_ms(self._h, k.encode()))
-                for k in ("total", "embed", "gemm", "attention", "norm", "exit", "end")}
+        n = float(self._lib.mmee_last_stage_ms(self._h, b"forwards")) or 1.0
+        out = {k: float(self._lib.mmee_last_stage_ms(self._h, k.encode())) / n
+               for k in ("total", "embed", "gemm", "attention", "norm", "exit", "end")}
+        out["forwards"] = n
+        return out
 
     def bucket_lut_in_use(self, which: int) -> np.ndarray:
         buf = np.zeros(4096, dtype=np.uint8)
