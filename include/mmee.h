@@ -150,7 +150,8 @@ int64_t mmee_debug_read(mmee_engine* e, const char* name, void* host_dst, int64_
  * f64 store, EE/utils.py:160-164); every scan after that moves only thresholds in and counts out.
  *   logits       f64 [E1, N, K]   per-exit logits incl. the final classifier (EE/utils.py:160-193 `logits_store`)
  *   temperatures f64 [E1] or NULL logits[e] / T_e before the criterion (EE/generic_scaling.py:54-61)
- *   criterion    0 max softmax ; 1 entropy (EE/models/EE_modules.py:149-160)
+ *   criterion    0 max softmax ; 1 entropy (EE/models/EE_modules.py:149-160) ; 2 the "margin" CSF of
+ *                EE/thresh.py:48-62 as the reference computes it (smallest minus second-smallest logit; larger fires)
  *   labels       i64 [N] or NULL  enables correct_out
  * All buffers in HOST memory. */
 typedef struct mmee_policy_store mmee_policy_store;

@@ -1524,7 +1524,8 @@ void policy_store_scan(mmee_policy_store* ps, const double* thresholds, int64_t 
   const int64_t N = ps->N;
   // mode 0: EE/policy.py:28-45 (strict, last exit unconditional); mode 1: EE/thresh.py:184-185 (>=, every exit
   // tested, nothing fired -> exit 0; the entropy CSF is the negated entropy, EE/large_scale.py:15)
-  const int cmp = mode == 0 ? (ps->criterion == 0 ? POLICY_GT : POLICY_LT) : (ps->criterion == 0 ? POLICY_GE : POLICY_LE);
+  // larger = more confident for max softmax and margin, smaller for entropy
+  const int cmp = mode == 0 ? (ps->criterion == 1 ? POLICY_LT : POLICY_GT) : (ps->criterion == 1 ? POLICY_LE : POLICY_GE);
   const int n_test = mode == 0 ? E1 - 1 : E1;
   const int fallback = mode == 0 ? E1 - 1 : 0;
   std::vector<double> neg;
@@ -1582,7 +1583,7 @@ mmee_policy_store* policy_store_create(int device, int E1, int64_t N, int K, con
                                        int criterion, const int64_t* labels) {
   if (!logits) throw std::runtime_error("null argument");
   if (E1 < 1 || N < 1 || K < 1) throw std::runtime_error("bad shape");
-  if (criterion != 0 && criterion != 1) throw std::runtime_error("criterion must be 0 (max_confidence) or 1 (entropy)");
+  if (criterion < 0 || criterion > 2) throw std::runtime_error("criterion must be 0 (max_confidence), 1 (entropy) or 2 (margin)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     throw std::runtime_error("no CUDA device: libmmee has no CPU fallback");

@@ -49,7 +49,17 @@ __global__ void policy_crit_kernel(const double* __restrict__ logits, const doub
     if (v > m) { m = v; am = k; }
   }
   double c;
-  if (criterion == 0) {
+  if (criterion == 2) {
+    // CSF "margin" exactly as the reference computes it (EE/thresh.py:48-52 = EE/large_scale.py:28-32,
+    // `top12_margin_np`): np.sort ascending, values[0] - values[1], i.e. the SMALLEST minus the second smallest scaled
+    // logit (<= 0) — not a top-1 / top-2 margin; kept bug-compatible so stores swept with it give the reference's numbers
+    double lo1 = INFINITY, lo2 = INFINITY;
+    for (int k = 0; k < K; ++k) {
+      const double v = temps ? x[k] / temps[e] : x[k];
+      if (v < lo1) { lo2 = lo1; lo1 = v; } else if (v < lo2) { lo2 = v; }
+    }
+    c = lo1 - lo2;
+  } else if (criterion == 0) {
     // scipy.special.softmax: exp(x - max) / sum; its maximum is exp(0) / sum
     double s = 0.0;
     for (int k = 0; k < K; ++k) s += exp((temps ? x[k] / temps[e] : x[k]) - m);

@@ -21,8 +21,10 @@ import torch
 
 from . import _lib
 
-CRITERIA = {"max_confidence": 0, "entropy": 1}
-CSF_TO_CRITERION = {"msp": "max_confidence", "entropy": "entropy"}      # EE/large_scale.py:12-18 CSF_dict names
+CRITERIA = {"max_confidence": 0, "entropy": 1, "margin": 2}
+# EE/large_scale.py:12-18 / EE/thresh.py:56-62 CSF_dict names.  "margin" is the reference's `top12_margin_np` AS WRITTEN
+# (np.sort ascending, values[0] - values[1]: smallest minus second-smallest logit), kept bug-compatible.
+CSF_TO_CRITERION = {"msp": "max_confidence", "entropy": "entropy", "margin": "margin"}
 MODES = {"policy": 0, "check_2D_threshold": 1}
 
 

@@ -98,6 +98,10 @@ def csf(logits: np.ndarray, name: str = "msp") -> np.ndarray:
         return softmax64(logits).max(axis=-1)
     if name == "entropy":
         return -entropy64(logits)
+    if name == "margin":
+        # EE/thresh.py:48-52 `top12_margin_np` as written: ascending sort, values[0] - values[1]
+        values = np.sort(np.asarray(logits, dtype=np.float64), axis=-1)
+        return values[..., 0] - values[..., 1]
     raise NotImplementedError(name)
 
 

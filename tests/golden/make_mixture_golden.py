@@ -52,7 +52,7 @@ def main():
     out = {}
     for name, (seed, E1, N, K, npe, M) in {"mix_a": (1, 6, 1500, 16, 10, 400), "mix_b": (2, 14, 900, 16, 10, 300)}.items():
         lg, labels = synthetic_store(seed, E1, N, K)
-        for csf_name in ("msp", "entropy"):
+        for csf_name in (("msp", "entropy", "margin") if name == "mix_a" else ("msp", "entropy")):
             CSF = ns["CSF_dict"][csf_name]
             ns["CSF"] = CSF                                     # thresh.py's opt0_2D reads the module-level CSF
             csf_logits = np.apply_along_axis(CSF, -1, lg)

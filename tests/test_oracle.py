@@ -116,7 +116,7 @@ def test_lte_port_matches_reference_golden(name):
     assert np.abs(r["logits"].numpy() - g["logits"]).max() < 1e-4
 
 
-@pytest.mark.parametrize("tag", ["mix_a_msp", "mix_a_entropy", "mix_b_msp", "mix_b_entropy"])
+@pytest.mark.parametrize("tag", ["mix_a_msp", "mix_a_entropy", "mix_a_margin", "mix_b_msp", "mix_b_entropy"])
 def test_mixture_port_matches_reference_golden(tag):
     """oracle check_2d_threshold / opt0_2d / generate_thresholds / evaluate_exit_logits against what the reference's
     own functions produced (tests/golden/make_mixture_golden.py runs them unmodified)."""

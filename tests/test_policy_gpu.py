@@ -140,18 +140,18 @@ def _mixture_case(tag):
     return g, lg, labels
 
 
-@pytest.mark.parametrize("tag", ["mix_a_msp", "mix_a_entropy", "mix_b_msp", "mix_b_entropy"])
+@pytest.mark.parametrize("tag", ["mix_a_msp", "mix_a_entropy", "mix_a_margin", "mix_b_msp", "mix_b_entropy"])
 def test_mixture_sweep_matches_reference_golden(tag):
     """Device `check_2D_threshold` semantics (>=, every exit tested, argmax-0 fallback, negated entropy) against the
     exits / accuracy / average exit the REFERENCE's opt0_2D + evaluate_exit_logits produced
     (tests/golden/make_mixture_golden.py)."""
     from mmee.policy import PolicyStore, generate_thresholds
     g, lg, labels = _mixture_case(tag)
-    crit_name = "max_confidence" if tag.endswith("msp") else "entropy"
+    crit_name = {"msp": "max_confidence", "entropy": "entropy", "margin": "margin"}[tag.split("_")[-1]]
     thr2d, want = g[tag + "_thr2d"], g[tag + "_exits"]
     N = lg.shape[1]
     with PolicyStore(lg, crit_name, labels=labels) as st:
-        csf = st.criteria() if crit_name == "max_confidence" else -st.criteria()
+        csf = -st.criteria() if crit_name == "entropy" else st.criteria()      # larger = more confident (CSF_dict)
         assert np.allclose(csf.sum(1), g[tag + "_csf_sum"], rtol=1e-12)
         # the same mixtures as the reference's generate_thresholds from the device criteria (percentiles of the same
         # values; the last ulp of a criterion can move a percentile by an ulp)
