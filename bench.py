@@ -531,7 +531,7 @@ def run_single(args, world, rank, local, dev):
         padded = {"value": B / (ms_pad / 1000.0), "unit": "docs/s", "ms_per_step": ms_pad,
                   "mean_real_text_tokens": float(pdocs["attention_mask"].sum(1).float().mean()),
                   "mean_exit_layer": float(np.dot(ph, np.clip(np.array(model.exit_layers + [dims.layers]), 0, None)) / ph.sum()),
-                  "note": "same engine, thresholds and temperatures; padded keys are masked and fully padded key tiles skipped"}
+                  "note": "same engine, thresholds and temperatures; ragged documents: rows of padded text tokens are dropped after the embedding stage (no GEMM / LayerNorm / attention work for them)"}
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM): algorithmic FLOPs of the docs that reached each layer
     hist = res["exit_hist"].astype(np.int64)
