@@ -110,30 +110,6 @@ __device__ __forceinline__ void sub_ref_x2(uint32_t a, uint32_t b, uint64_t nref
   asm("mov.b64 {%0, %1}, %2;" : "=f"(ya), "=f"(yb) : "l"(y));
 }
 
-// exp2 of two scores on the FMA / ALU pipes instead of the MUFU (kPoly): the exp phase of the softmax warps is bound by
-// the MUFU (16 lanes/clk/SM shared by the two co-resident CTAs), the FMA pipe has slack.  x = n + f with
-// n = round(x) (magic-number add), 2^f on [-0.5, 0.5] by a minimax cubic (max relative error 7.5e-5, far inside the
-// bf16 rounding of P), 2^n by adding n to the exponent field.  Scores below -126 (masked keys: -60000) are clamped:
-// they yield 2^-126 = 1.2e-38 instead of 0, which neither the row sum nor P V can see.  10 issue slots per pair.
-__device__ __forceinline__ void exp2_poly_x2(float a0, float a1, float& p0, float& p1) {
-  a0 = fmaxf(a0, -126.f);
-  a1 = fmaxf(a1, -126.f);
-  uint64_t x, t, r, f, p;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a0), "f"(a1));
-  const uint64_t magic = f32x2_pack(12582912.f, 12582912.f), nmagic = f32x2_pack(-12582912.f, -12582912.f);
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(x), "l"(magic));          // low mantissa bits of t = round(x)
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(t), "l"(nmagic));         // round(x) as a float
-  f = f32x2_fma(r, f32x2_pack(-1.f, -1.f), x);                              // f = x - round(x)
-  p = f32x2_fma(f, f32x2_pack(0.05517147481441498f, 0.05517147481441498f), f32x2_pack(0.242610901594162f, 0.242610901594162f));
-  p = f32x2_fma(p, f, f32x2_pack(0.6932609677314758f, 0.6932609677314758f));
-  p = f32x2_fma(p, f, f32x2_pack(0.9999281167984009f, 0.9999281167984009f));
-  uint32_t u0, u1, t0, t1;
-  asm("mov.b64 {%0, %1}, %2;" : "=r"(u0), "=r"(u1) : "l"(p));
-  asm("mov.b64 {%0, %1}, %2;" : "=r"(t0), "=r"(t1) : "l"(t));
-  p0 = __uint_as_float(u0 + (t0 << 23));
-  p1 = __uint_as_float(u1 + (t1 << 23));
-}
-
 // Position in this CTA's (item, key tile) sequence.  Every role walks the same sequence so the pipeline counters stay
 // in lock-step.  Passed by value so it lives in registers.  An item = (slot, head, 128-row query tile); its key tiles
 // are 0 .. last_j (documents are ragged: only kept tokens have rows, so there are no padded key tiles to skip).
@@ -186,10 +162,9 @@ struct AttMaps {
   CUtensorMap q, k, vt, bias, q_lo, k_lo, vt_lo, bias_lo;
 };
 
-template <bool kTrace, bool kSplit = false, int kPoly = 0>
+template <bool kTrace, bool kSplit = false>
 __global__ void __launch_bounds__(ATT_THREADS, kSplit ? 1 : ATT_CTAS_PER_SM)
 attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
-  static_assert(kPoly == 0 || (!kSplit && !kTrace), "polynomial exp2: bf16 throughput kernel only");
   using SMEM = AttSmemT<kSplit>;
   const CUtensorMap& tmap_q = maps.q;
   const CUtensorMap& tmap_k = maps.k;
@@ -688,14 +663,7 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
             m0 = fmaxf(m0, fmaxf(a0, a1));
             m1 = fmaxf(m1, fmaxf(c0, c1));
             pk[i] = pack_bf16x2(fast_exp2(a0), fast_exp2(a1));
-            // kPoly: keys 32 .. 63 of the tile (every second pair of them for kPoly == 1) take the FMA-pipe exp2
-            if (kPoly == 2 || (kPoly == 1 && (i & 1))) {
-              float e0, e1;
-              exp2_poly_x2(c0, c1, e0, e1);
-              pk[16 + i] = pack_bf16x2(e0, e1);
-            } else {
-              pk[16 + i] = pack_bf16x2(fast_exp2(c0), fast_exp2(c1));
-            }
+            pk[16 + i] = pack_bf16x2(fast_exp2(c0), fast_exp2(c1));
           }
           pmax = fmaxf(m0, m1);
         }

@@ -140,7 +140,6 @@ struct mmee_engine {
   // ragged encoder layout (norm_exit.cuh): kept tokens per document and the row plans of two consecutive exit stages
   DevBuf<int> doc_len, kept_idx, plan_row0[2], plan_qt_slot[2], plan_n_qt[2];
   DevBuf<int4> plan_meta[2];
-  int att_poly = 0;                // attention: share of the exponentials computed on the FMA pipe (0 none, 1 a quarter, 2 half); MMEE_ATT_POLY
   bool tail16 = true;              // attention: a last key tile with <= 16 real keys runs as a 16-key tile (MMEE_NO_TAIL16=1: off)
   DevBuf<float> lte_w, slot_lte;   // learned-to-exit scorer [H] (optional) and its per-slot scores
   float lte_b = 0.f;
@@ -1024,8 +1023,6 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
       if (!configured) {
         CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES + 16 * 1024));
         CUDA_OK(cudaFuncSetAttribute(attention_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES + 16 * 1024));
-        CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES + 16 * 1024));
-        CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES + 16 * 1024));
         CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmemT<true>::DYN_BYTES));
         configured = true;
       }
@@ -1042,10 +1039,6 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
         attention_kernel<false, true><<<att_grid, ATT_THREADS, AttSmemT<true>::DYN_BYTES, st>>>(am, aa);
       else if (e->trace_on && l == 0)
         attention_kernel<true, false><<<att_grid, ATT_THREADS, att_smem, st>>>(am, aa);
-      else if (e->att_poly == 1)
-        attention_kernel<false, false, 1><<<att_grid, ATT_THREADS, att_smem, st>>>(am, aa);
-      else if (e->att_poly == 2)
-        attention_kernel<false, false, 2><<<att_grid, ATT_THREADS, att_smem, st>>>(am, aa);
       else
         attention_kernel<false, false><<<att_grid, ATT_THREADS, att_smem, st>>>(am, aa);
       CUDA_OK(cudaGetLastError());
@@ -1219,7 +1212,6 @@ int mmee_create(const mmee_model_desc* desc, int device, int max_batch, mmee_eng
   // a last key tile with <= 16 real keys (an unpadded document, S = 709: 5) runs as a 16-key tile (N = 16 MMAs, a quarter of
   // the softmax work); decided per document by the attention kernel (documents are ragged)
   e->tail16 = !getenv("MMEE_NO_TAIL16");
-  if (const char* ap = getenv("MMEE_ATT_POLY")) e->att_poly = atoi(ap);
   e->bias_width = e->bias_pitch;
   if (e->kv_pitch > 1024) throw std::runtime_error("sequence too long for keymask_kernel");
   e->sms = prop.multiProcessorCount;

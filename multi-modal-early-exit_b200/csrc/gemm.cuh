@@ -96,6 +96,16 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 // Two elements at a time: the polynomial runs on the packed-fp32 pipe (FFMA2 on sm_100: one issue slot per pair), so the
 // GELU epilogue of the MLP-up GEMM spends 6 + 2 x 5 instead of 2 x 11 FMA/ALU-pipe slots per pair.  Same arithmetic
 // (round-to-nearest FMAs in the same order) as gelu_erf_fast: bit-identical results.
+__device__ __forceinline__ uint64_t f32x2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 __device__ __forceinline__ void gelu_erf_fast2(float x0, float x1, float& y0, float& y1) {
   const float z0 = fminf(fabsf(x0) * 0.70710678118654752f, 4.3f);
   const float z1 = fminf(fabsf(x1) * 0.70710678118654752f, 4.3f);

@@ -295,18 +295,6 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
 }
 
 // ---------------------------------------------------------------- small math helpers
-// packed fp32 pairs (FFMA2 / FADD2 on sm_100: one issue slot per pair)
-__device__ __forceinline__ uint64_t f32x2_pack(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
