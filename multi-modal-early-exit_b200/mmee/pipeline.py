@@ -89,3 +89,42 @@ def get_logits(model, config, test_loader: Iterable[dict]) -> Tuple[np.ndarray, 
     cfg["labelset"] = "test"
     dump_logits(model, logits_store, references, cfg, name=name)
     return logits_store, references, None
+
+
+def full_test_iteration(logits, references, config, start_threshold: float, step: float, device: int = 0):
+    """The threshold sweep of EE/eval.py:227-274 (`--full_test True`): for every `t in np.arange(start_threshold, 1,
+    step)` the configured policy is applied to the stored logits — `t` is the global `exit_threshold`, or, for
+    `accuracy_calibration_heuristic`, the `epsilon` the per-exit thresholds are derived with (:242-245) — and one result
+    dict per sweep point is collected and written to `<checkpoint dir>/<policy>/calibrated-metrics.json` (or
+    `non-calibrated-metrics.json`, :264-272).  The reference re-runs the whole Python policy loop per point; here all
+    points go through ONE device scan (`mmee.policy.PolicyStore`).  Each dict holds what that scan yields: accuracy,
+    exit distribution and average exit (the reference adds the other `calc_metrics` scores and the FLOP accounting of
+    `EE/analysis.py`, which are outside this path)."""
+    from .policy import PolicyStore, heuristic_thresholds
+
+    lg = np.asarray(logits, dtype=np.float64)
+    E1 = lg.shape[0]
+    sweep = np.arange(start_threshold, 1, step)
+    policy = config.get("exit_policy", "max_confidence_global_thresholding_policy")
+    if policy == "accuracy_calibration_heuristic":
+        if "calibration_metrics" not in config:
+            raise Exception("calibration_metrics not in config -> Set calibrate flag to True")
+        rows = np.stack([heuristic_thresholds(config["calibration_metrics"], float(eps), E1) for eps in sweep])
+        key = "epsilon"
+    elif policy == "max_confidence_global_thresholding_policy":
+        rows = np.repeat(sweep[:, None], E1, axis=1)
+        key = "exit_threshold"
+    else:
+        raise NotImplementedError(policy)
+    with PolicyStore(lg, "max_confidence", labels=np.asarray(references).reshape(-1), device=device) as store:
+        res = store.scan(rows, per_exit=True, want_exits=False)
+    results = []
+    for t, value in enumerate(sweep):
+        results.append({key: float(value), "accuracy": float(res.accuracy[t]), "average_exit": float(res.mean_exit[t]),
+                        "exit_distribution": {int(e): float(res.hist[t, e]) / res.n_samples for e in range(E1)}})
+    out_dir = os.path.join(config_to_checkpoint(config), policy)
+    os.makedirs(out_dir, exist_ok=True)
+    name = "calibrated-metrics.json" if config.get("calibrate") else "non-calibrated-metrics.json"
+    with open(os.path.join(out_dir, name), "w+") as f:
+        json.dump(results, f, indent=4)
+    return results

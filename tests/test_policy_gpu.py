@@ -210,6 +210,43 @@ def test_large_mixture_sweep_equals_oracle(crit_name):
             assert np.array_equal(pol.hist[t], np.bincount(want, minlength=E1))
 
 
+def test_full_test_iteration_equals_policy_loop(tmp_path):
+    """EE/eval.py:227-274: one device scan for the whole sweep == the policy oracle applied threshold by threshold
+    (global thresholds and the accuracy / ECE heuristic swept over epsilon); result files as the reference names them."""
+    import json
+    import os
+
+    from mmee.pipeline import full_test_iteration
+    rng = np.random.default_rng(21)
+    E1, N, K = 6, 800, 16
+    labels = rng.integers(0, K, size=N)
+    lg = rng.normal(size=(E1, N, K)) * np.linspace(1.0, 3.0, E1)[:, None, None]
+    lg[:, np.arange(N), labels] += np.linspace(0.5, 2.5, E1)[:, None]
+    cfg = {"checkpoint": "org/ckpt", "test_dataset": "ds/rvl", "results_root": str(tmp_path), "calibrate": True,
+           "exit_policy": "max_confidence_global_thresholding_policy"}
+    res = full_test_iteration(lg, labels, cfg, 0.3, 0.05)
+    thrs = np.arange(0.3, 1, 0.05)
+    assert len(res) == len(thrs)
+    crit = policy_port.criterion(lg, "max_confidence")
+    for r, thr in zip(res, thrs):
+        want, pred, dist = policy_port.exit_policy_vectorised(lg, thr, "max_confidence")
+        if (np.abs(crit[:-1] - thr).min(axis=0) > MARGIN).all():
+            assert r["accuracy"] == pytest.approx(float((pred.argmax(-1) == labels).mean()), abs=1e-15)
+            assert r["average_exit"] == pytest.approx(float(want.mean()), abs=1e-12)
+        assert abs(sum(r["exit_distribution"].values()) - 1.0) < 1e-12 and r["exit_threshold"] == pytest.approx(thr)
+    out = os.path.join(str(tmp_path), "results", "ckpt-rvl", "max_confidence_global_thresholding_policy", "calibrated-metrics.json")
+    assert len(json.load(open(out))) == len(thrs)
+    cfg2 = dict(cfg, exit_policy="accuracy_calibration_heuristic", calibrate=False,
+                calibration_metrics={"accuracy": [0.5, 0.6, 0.7, 0.75, 0.8, 0.85], "ece": [0.2, 0.15, 0.12, 0.1, 0.08, 0.05]})
+    res2 = full_test_iteration(lg, labels, cfg2, 0.1, 0.2)
+    for r in res2:
+        thr = heuristic_thresholds(cfg2["calibration_metrics"], r["epsilon"], E1)
+        want, pred, _ = policy_port.exit_policy(lg, thr, "max_confidence")
+        assert r["accuracy"] == pytest.approx(float((pred.argmax(-1) == labels).mean()), abs=1e-15)
+        assert r["average_exit"] == pytest.approx(float(want.mean()), abs=1e-12)
+    assert os.path.exists(os.path.join(str(tmp_path), "results", "ckpt-rvl", "accuracy_calibration_heuristic", "non-calibrated-metrics.json"))
+
+
 def test_mixture_sweep_many_exits():
     """A store with 40 exits (criteria stage above the 48 KB default shared-memory limit, 64-wide register histogram)."""
     from mmee.policy import PolicyStore
