@@ -173,6 +173,7 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
   const int S = args.seq;
   const int total_items = *args.n_qt_dev * args.heads;
   const int stride = gridDim.x;
+  if (total_items == 0) return;    // every document has left: no barrier / TMEM set-up for an empty launch
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 32-bit shared-window address of the working area; all hot-loop accesses use these addresses

@@ -300,6 +300,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int lane = threadIdx.x & 31;
 
   const int M = args.m_dev ? *args.m_dev : args.m_static;
+  if (M <= 0) return;              // every document has left: no barrier / TMEM set-up for an empty launch
   const int m_blocks = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int n_blocks = args.N / BLOCK_N;
   const int k_blocks = args.K / GEMM_BLOCK_K;
@@ -471,6 +472,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const bool leader = rank == 0;
 
   const int M = args.m_dev ? *args.m_dev : args.m_static;
+  if (M <= 0) return;              // every document has left (both CTAs of the pair read the same M): empty launch
   const int m_blocks = (M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);      // 256-row tiles
   const int n_blocks = args.N / BLOCK_N;
   const int k_blocks = args.K / GEMM_BLOCK_K;
