@@ -404,8 +404,8 @@ def run_single(args, world, rank, local, dev):
     from mmee.dist import JobGatherer, pack_results
 
     # One job = `steps` batches per GPU.  Every step is enqueued without waiting (infer_device: results stay on the GPU)
-    # and its packed per-document results go into a device ring — through an asynchronous NCCL all_gather at N > 1, a
-    # device copy at N = 1 — and the whole job's results are read back to the host ONCE, inside the timed region
+    # and its packed per-document results go into a local device ring; at the end of the job the rings are all-gathered
+    # (N > 1: one NCCL call) and the whole job's results are read back to the host ONCE, inside the timed region
     # ("final gather").  The same code path at every N.
     cap = max(steps, args.warmup)
     jg = JobGatherer(B, K + 2, E1, cap, dev) if world > 1 else None
@@ -591,9 +591,9 @@ def run_single(args, world, rank, local, dev):
         if world > 1:
             line["dp_consistency"] = dp_consistency
             line["clocks_per_gpu"] = clocks_all
-            line["gather"] = ("per step: one async NCCL all_gather of [256, K+2] per rank into a device ring, no host "
-                              "sync; one all_reduce of the exit histogram and one device->host read-back of all "
-                              "steps' results at the end of the timed region")
+            line["gather"] = ("every step's [256, K+2] results are kept in a local device ring; ONE NCCL all_gather of "
+                              "the rings + one all_reduce of the exit histogram + one device->host read-back at the "
+                              "end of the timed region (no collective while the job computes)")
         line["config"]["job"] = (f"{args.steps} batches per GPU enqueued back to back; every step's per-document results "
                                  "are kept in a device ring and read back to the host once, inside the timed region")
         print(json.dumps(line), flush=True)

@@ -56,29 +56,30 @@ def pack_results(logits: torch.Tensor, exit_index: torch.Tensor, criterion: torc
 
 
 class JobGatherer:
-    """The data-parallel job's results without a per-step host round-trip ("final gather").
+    """The data-parallel job's results with ONE collective at the end ("final gather").
 
     Every step, each rank pushes its packed per-document results ([n_local, K + 2], see `pack_results`) and its exit
-    histogram; the rows are all-gathered asynchronously (NCCL's own stream over NVLink) into slot `step % capacity` of
-    a preallocated device ring and the histogram is accumulated on the device.  Nothing waits: a rank goes straight on
-    to its next forward, so the ranks do not run in lock-step.  `finish()` waits for the outstanding gathers, sums the
-    histograms over the ranks and returns the ring on the host — one device->host copy for the whole job.
-    Equal shards (n_local documents on every rank); `gather_results` handles uneven ones."""
+    histogram; they are copied into slot `step % capacity` of a LOCAL device ring and the histogram is accumulated on
+    the device.  Nothing waits and no collective runs while the job computes: a rank goes straight on to its next
+    forward (a per-step all_gather, even an asynchronous one, parks NCCL's CTAs on a few SMs until the slowest rank
+    arrives, and the engine's persistent one-CTA-per-SM kernels then wait for those SMs: +1 ms per step at 8 GPUs,
+    measured).  `finish()` all-gathers the rings of all ranks in one call (NCCL over NVLink on GPUs, gloo on CPU
+    tensors), sums the histograms over the ranks and returns the job's results on the host — one collective and one
+    device->host copy for the whole job.  Equal shards (n_local documents on every rank); `gather_results` handles
+    uneven ones."""
 
     def __init__(self, n_local: int, n_cols: int, n_hist: int, capacity: int, device, group=None):
         self.group = group
         self.world = dist.get_world_size(group)
         self.n_local = n_local
-        self.ring = torch.empty((max(capacity, 1), self.world * n_local, n_cols), dtype=torch.float32, device=device)
+        self.local = torch.empty((max(capacity, 1), n_local, n_cols), dtype=torch.float32, device=device)
         self.hist = torch.zeros((n_hist,), dtype=torch.int64, device=device)
-        self.pending = []
         self.steps = 0
 
     def push(self, packed: torch.Tensor, hist: torch.Tensor) -> int:
-        """Enqueue the gather of one step's results; returns the ring slot they land in."""
-        slot = self.steps % self.ring.shape[0]
-        self.pending.append((dist.all_gather_into_tensor(self.ring[slot], packed.contiguous(), group=self.group,
-                                                         async_op=True), packed))      # keep `packed` alive until waited
+        """Keep one step's results (device copy on the current stream); returns the ring slot they land in."""
+        slot = self.steps % self.local.shape[0]
+        self.local[slot].copy_(packed)
         self.hist.add_(hist.to(self.hist.dtype))
         self.steps += 1
         return slot
@@ -86,12 +87,14 @@ class JobGatherer:
     def finish(self) -> Dict[str, torch.Tensor]:
         """-> {"results": host [capacity, world * n_local, n_cols] (slots of the last `capacity` steps, rows in rank
         order), "exit_hist": host int64 [n_hist] summed over steps and ranks, "steps": int}; resets the gatherer."""
-        for work, _ in self.pending:
-            work.wait()
-        self.pending.clear()
+        cap, n, cols = self.local.shape
+        flat = torch.empty((self.world * cap, n, cols), dtype=torch.float32, device=self.local.device)
+        dist.all_gather_into_tensor(flat, self.local, group=self.group)       # rank-major concatenation along dim 0
+        everyone = flat.view(self.world, cap, n, cols)
         total = self.hist.clone()
         dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
-        out = {"results": self.ring.cpu(), "exit_hist": total.cpu(), "steps": self.steps}
+        results = everyone.permute(1, 0, 2, 3).reshape(cap, self.world * n, cols).cpu()
+        out = {"results": results, "exit_hist": total.cpu(), "steps": self.steps}
         self.hist.zero_()
         self.steps = 0
         return out
