@@ -136,3 +136,37 @@ def test_mixture_port_matches_reference_golden(tag):
         acc, avg, dist = policy_port.evaluate_exit_logits(lg, labels, exits[t])
         assert acc == g[tag + "_acc"][t] and avg == g[tag + "_avg_exit"][t]
         assert abs(sum(dist.values()) - 1.0) < 1e-12
+
+
+def test_policy_port_properties_randomised():
+    """Randomised properties of the policy restatement (hypothesis): the per-sample double loop of EE/policy.py:28-45
+    equals the vectorised form for any logits / per-exit thresholds, exits are monotone in a global threshold, the last
+    exit always fires, and check_2d_threshold is the argmax-of->= rule with its all-False -> 0 corner."""
+    from hypothesis import given, settings, strategies as st
+    from hypothesis.extra import numpy as hnp
+
+    @settings(max_examples=60, deadline=None)
+    @given(hnp.arrays(np.float64, st.tuples(st.integers(1, 5), st.integers(1, 12), st.integers(2, 6)),
+                      elements=st.floats(-6, 6, allow_nan=False, width=32)),
+           st.floats(0.05, 0.999), st.floats(0.05, 0.999), st.sampled_from(["max_confidence", "entropy"]))
+    def check(lg, t1, t2, kind):
+        E1, N, K = lg.shape
+        lo, hi = sorted((t1, t2))
+        scale = 1.0 if kind == "max_confidence" else np.log(K)
+        a = policy_port.exit_policy(lg, lo * scale, kind)
+        b = policy_port.exit_policy_vectorised(lg, lo * scale, kind)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        c = policy_port.exit_policy_vectorised(lg, hi * scale, kind)
+        # a higher confidence threshold exits later; a higher entropy threshold exits earlier
+        assert (c[0] >= b[0]).all() if kind == "max_confidence" else (c[0] <= b[0]).all()
+        assert (a[0] <= E1 - 1).all() and abs(sum(a[2].values()) - 1.0) < 1e-12
+        thr = np.linspace(lo, hi, E1)
+        d = policy_port.exit_policy(lg, thr * scale, kind)
+        e = policy_port.exit_policy_vectorised(lg, thr * scale, kind)
+        assert np.array_equal(d[0], e[0])
+        csf = policy_port.csf(lg, "msp")
+        ex = policy_port.check_2d_threshold(csf, thr)
+        fire = csf >= thr[:, None]
+        assert np.array_equal(ex, np.where(fire.any(0), fire.argmax(0), 0))
+
+    check()
