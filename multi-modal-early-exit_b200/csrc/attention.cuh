@@ -248,7 +248,7 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       AttCursor c = att_first(total_items, stride, args);
       uint32_t t = 0;
       int loaded_ii = -1;
@@ -358,7 +358,7 @@ attention_kernel(const __grid_constant__ AttMaps maps, const AttArgs args) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, ATT_BKV);
       constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BQ, ATT_DV);
       constexpr uint32_t idesc_s16 = umma_idesc_bf16(ATT_BQ, 16);   // the 16-key tail tile (args.tail_j)

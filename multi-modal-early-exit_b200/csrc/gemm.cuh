@@ -329,7 +329,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -349,7 +349,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
@@ -502,7 +502,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
@@ -521,7 +521,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && leader) {
+    if (leader && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
