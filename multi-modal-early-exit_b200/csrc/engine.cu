@@ -175,7 +175,14 @@ struct mmee_engine {
 
   // activations
   DevBuf<__nv_bfloat16> X[2], QK, VT, CTX, A1, MID, PATCH;
-  DevBuf<__nv_bfloat16> Xlo[2], A1lo;       // low parts of the split-bf16 residual stream (precise_residual)
+  DevBuf<__nv_bfloat16> Xlo[2], A1lo;       // low parts of the split-bf16 residual stream (precise_residual without y_resid)
+  // y_resid (bf16 mode, H % 128 == 0): residual adds recompute LayerNorm(pre-LN sums) instead of reading (hi, lo) pairs.
+  // Y2 = out-projection output (Y stays the MLP-down output the next layer's residual is recomputed from), per-row
+  // (mean, rstd) of both LayerNorms, and for the post-MLP one the source row in Y (exit compaction moves rows)
+  bool y_resid = false;
+  DevBuf<float> Y2;
+  DevBuf<float2> ln_stats1, ln_stats2;
+  DevBuf<int> ln_src2;
   DevBuf<__nv_bfloat16> QKlo, VTlo, CTXlo, MIDlo, PATCHlo;   // fp32 engine mode: low parts of every other GEMM / attention operand
   DevBuf<__half> BIASlo;                    // fp32 engine mode: low part of the attention bias
   DevBuf<float> X32[2], A132;               // fp32 engine mode: the residual stream itself in fp32 (exact residual adds)
@@ -389,14 +396,14 @@ void launch_nv(int H, F&& f) {   // dispatch on values-per-lane for the warp-per
 // source slot slot_src[s'] (row plan `src`): the compaction costs no extra pass.
 void launch_ln(mmee_engine* e, const float* Y, __nv_bfloat16* X, __nv_bfloat16* Xlo, float* X32, const float* w,
                const float* b, int B, const int* m_dev, const int* slot_src, const SlotRows& dst, const SlotRows& src,
-               const int* n_dst_dev, cudaStream_t st) {
+               const int* n_dst_dev, cudaStream_t st, float2* stats_out = nullptr, int* src_out = nullptr) {
   const int H = e->H, S = e->S;
   const float eps = e->d.ln_eps;
   const int rows = B * S;
   auto vec = [&](auto nv4) {
     const int blocks = std::min((rows + 7) / 8, e->sms * 16);      // grid-stride over rows, 8 warps per block
     ln_rows_vec_kernel<decltype(nv4)::value><<<blocks, 256, 0, st>>>(Y, X, Xlo, X32, w, b, eps, H, m_dev, slot_src, dst.row0,
-                                                                       src.row0, n_dst_dev);
+                                                                       src.row0, n_dst_dev, stats_out, src_out);
   };
   switch (H % 128 == 0 ? H / 128 : 0) {
     case 1: vec(std::integral_constant<int, 1>{}); break;
@@ -405,6 +412,7 @@ void launch_ln(mmee_engine* e, const float* Y, __nv_bfloat16* X, __nv_bfloat16* 
     case 6: vec(std::integral_constant<int, 6>{}); break;
     case 8: vec(std::integral_constant<int, 8>{}); break;
     default:
+      if (stats_out) throw std::runtime_error("residual statistics need the vectorised LayerNorm (H % 128 == 0)");
       launch_nv(H, [&](auto nv) {
         ln_rows_kernel<decltype(nv)::value><<<(rows + 7) / 8, 256, 0, st>>>(Y, X, Xlo, X32, w, b, eps, H, m_dev, slot_src,
                                                                             dst.row0, src.row0, n_dst_dev);
@@ -596,7 +604,9 @@ void allocate(mmee_engine* e) {
   e->VT.alloc(static_cast<size_t>(B) * heads * 64 * e->kv_pitch, true);
   e->CTX.alloc(M * H, true);
   e->A1.alloc(M * H, true);
-  if (e->precise_residual) {
+  if (e->y_resid) {
+    e->Y2.alloc(M * H, true); e->ln_stats1.alloc(M, true); e->ln_stats2.alloc(M, true); e->ln_src2.alloc(M, true);
+  } else if (e->precise_residual) {
     e->Xlo[0].alloc(M * H, true); e->Xlo[1].alloc(M * H, true); e->A1lo.alloc(M * H, true);
   }
   if (e->split) {
@@ -1046,14 +1056,24 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     }
     mark(e, "attention", st);
 
+    // y_resid: the out-projection writes Y2 (Y still holds the previous layer's MLP-down sums, from which this residual
+    // is recomputed through the row map the last LayerNorm left); the first layer adds the embedding output itself
+    const bool yr = e->y_resid;
+    float* y_att = yr ? e->Y2.p : e->Y.p;
     ga = GemmArgs{};
-    ga.m_dev = mdev; ga.N = H; ga.K = H; ga.bias = w.bo.p; ga.out = e->Y.p; ga.ld_out = H; ga.resid = e->X[cur].p;
-    ga.resid_lo = x_lo_valid ? e->Xlo[cur].p : nullptr;
+    ga.m_dev = mdev; ga.N = H; ga.K = H; ga.bias = w.bo.p; ga.out = y_att; ga.ld_out = H; ga.resid = e->X[cur].p;
+    ga.resid_lo = (x_lo_valid && !yr) ? e->Xlo[cur].p : nullptr;
     ga.resid_f32 = split ? e->X32[cur].p : nullptr;
+    if (yr && x_lo_valid) {
+      const LayerW& pw = e->layers[l - 1];
+      ga.resid = nullptr;
+      ga.resid_y = e->Y.p; ga.resid_stats = e->ln_stats2.p; ga.resid_src = e->ln_src2.p;
+      ga.resid_w = pw.ln2_w.p; ga.resid_b = pw.ln2_b.p;
+    }
     launch_gemm<EPI_RESID_F32>(e, e->bn_h, e->t_ctx, w.t_wo, ga, st, &e->t_ctx_lo, &w.t_wo_lo);
     mark(e, "gemm", st);
-    launch_ln(e, e->Y.p, e->A1.p, e->A1lo.p, split ? e->A132.p : nullptr, w.ln1_w.p, w.ln1_b.p, B, mdev, nullptr,
-              plan_view(e, rp), plan_view(e, rp), e->n_dev.p + stage, st);
+    launch_ln(e, y_att, e->A1.p, yr ? nullptr : e->A1lo.p, split ? e->A132.p : nullptr, w.ln1_w.p, w.ln1_b.p, B, mdev, nullptr,
+              plan_view(e, rp), plan_view(e, rp), e->n_dev.p + stage, st, yr ? e->ln_stats1.p : nullptr, nullptr);
     e->launches++;
     mark(e, "norm", st);
 
@@ -1062,8 +1082,13 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
     launch_gemm<EPI_GELU_BF16>(e, e->bn_i, e->t_a1, w.t_wi, ga, st, &e->t_a1_lo, &w.t_wi_lo);
     ga = GemmArgs{};
     ga.m_dev = mdev; ga.N = H; ga.K = I; ga.bias = w.bo2.p; ga.out = e->Y.p; ga.ld_out = H; ga.resid = e->A1.p;
-    ga.resid_lo = e->A1lo.p;
+    ga.resid_lo = yr ? nullptr : e->A1lo.p;
     ga.resid_f32 = split ? e->A132.p : nullptr;
+    if (yr) {                                     // residual = LayerNorm1(Y2), same rows
+      ga.resid = nullptr;
+      ga.resid_y = e->Y2.p; ga.resid_stats = e->ln_stats1.p; ga.resid_src = nullptr;
+      ga.resid_w = w.ln1_w.p; ga.resid_b = w.ln1_b.p;
+    }
     if (split && e->n_kchunks > 1) {
       // K chunks: Y = A1 + b + MID[:, 0:kc] W[:, 0:kc]^T, then Y += MID[:, c] W[:, c]^T in fp32 (see kchunk)
       for (int c = 0; c < e->n_kchunks; ++c) {
@@ -1086,8 +1111,9 @@ void forward_device(mmee_engine* e, int B, const int64_t* ids, const int64_t* bb
       mark(e, "exit", st);
     }
     if (!last) {
-      launch_ln(e, e->Y.p, e->X[cur ^ 1].p, e->Xlo[cur ^ 1].p, split ? e->X32[cur ^ 1].p : nullptr, w.ln2_w.p, w.ln2_b.p, B,
-                e->m_dev.p + stage, ln_src, plan_view(e, rp), plan_view(e, y_rp), e->n_dev.p + stage, st);
+      launch_ln(e, e->Y.p, e->X[cur ^ 1].p, yr ? nullptr : e->Xlo[cur ^ 1].p, split ? e->X32[cur ^ 1].p : nullptr, w.ln2_w.p,
+                w.ln2_b.p, B, e->m_dev.p + stage, ln_src, plan_view(e, rp), plan_view(e, y_rp), e->n_dev.p + stage, st,
+                yr ? e->ln_stats2.p : nullptr, yr ? e->ln_src2.p : nullptr);
       e->launches++;
       cur ^= 1;
       x_lo_valid = e->precise_residual;
@@ -1217,6 +1243,8 @@ int mmee_create(const mmee_model_desc* desc, int device, int max_batch, mmee_eng
   e->sms = prop.multiProcessorCount;
   if (const char* pr = getenv("MMEE_PRECISE_RESIDUAL")) e->precise_residual = pr[0] != '0';   // developer A/B switch
   if (e->split) e->precise_residual = true;   // fp32 engine mode: split operands everywhere (and full 64-key tiles in attention)
+  e->y_resid = e->precise_residual && !e->split && e->H % 128 == 0;
+  if (const char* yr = getenv("MMEE_Y_RESID")) e->y_resid = e->y_resid && yr[0] != '0';   // developer A/B switch
   e->bn_h = pick_bn(e->H); e->bn_qkv = pick_bn(e->H) ; e->bn_i = pick_bn(e->I);
   if ((2 * e->H) % e->bn_qkv) e->bn_qkv = 128;
   try {
@@ -1463,6 +1491,7 @@ int64_t mmee_debug_read(mmee_engine* e, const char* name, void* host_dst, int64_
     else if (n == "A1") { src = e->A1.p; bytes = e->A1.n * 2; }
     else if (n == "MID") { src = e->MID.p; bytes = e->MID.n * 2; }
     else if (n == "Y") { src = e->Y.p; bytes = e->Y.n * 4; }
+    else if (n == "Y2") { src = e->Y2.p; bytes = e->Y2.n * 4; }
     else if (n == "VIS") { src = e->VIS.p; bytes = e->VIS.n * 4; }
     else if (n == "POOL") { src = e->POOL.p; bytes = e->POOL.n * 4; }
     else if (n == "ATT_TRACE") { src = e->att_trace.p; bytes = e->att_trace.n * 8; }

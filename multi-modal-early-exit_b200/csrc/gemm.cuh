@@ -32,7 +32,7 @@ constexpr int GEMM_THREADS = 64 + GEMM_EPI_WARPS * 32;
 enum GemmEpilogue : int {
   EPI_BIAS_BF16 = 0,   // out_bf16[m, n] = acc + bias[n]
   EPI_GELU_BF16 = 1,   // out_bf16[m, n] = gelu_erf(acc + bias[n])
-  EPI_RESID_F32 = 2,   // out_f32 [m, n] = acc + bias[n] + resid_bf16[m, n] (+ resid_lo_bf16[m, n])
+  EPI_RESID_F32 = 2,   // out_f32 [m, n] = acc + bias[n] + resid_bf16[m, n] (+ resid_lo_bf16[m, n])  |  + LayerNorm(resid_y[src(m)])[n]
   EPI_QKV = 3,         // n < qk_cols: qk_bf16[m, n];  else V^T: vt[doc][head][d][kv_pitch]
   EPI_PATCH = 4,       // patch-embed rows (doc*n_patch + p): out_f32[(doc*n_vis + 1 + p), n] = acc + bias + pos[1+p, n]
 };
@@ -48,6 +48,14 @@ struct GemmArgs {
   const __nv_bfloat16* resid;   // EPI_RESID_F32: [*, N]
   const __nv_bfloat16* resid_lo;   // optional low part of a split-bf16 residual (resid + resid_lo = 16-bit mantissa), or nullptr
   const float* resid_f32;          // fp32 engine mode: the residual itself in fp32 (exact, as the reference adds it); replaces resid / resid_lo
+  // bf16 mode, "residual from the pre-LayerNorm sums": the residual of output row r is LayerNorm(resid_y[src(r)]),
+  // recomputed here in fp32 from the sums the LayerNorm kernel read (it left mean / rstd per row), so that kernel
+  // writes no low part and the residual is exact.  Replaces resid / resid_lo when resid_y != nullptr.
+  const float* resid_y;            // [*, N] fp32 pre-LayerNorm sums (never the buffer `out` points to)
+  const float2* resid_stats;       // [rows] (mean, rstd) of output row r's residual row
+  const int* resid_src;            // [rows] row of resid_y behind output row r (an exit compaction in between), nullptr: r
+  const float* resid_w;            // [N] LayerNorm weight / bias of that LayerNorm
+  const float* resid_b;
   // EPI_QKV
   __nv_bfloat16* vt;       // [docs][heads][64][kv_pitch]
   __nv_bfloat16* vt_lo;    // SPLIT: low parts of V^T
@@ -125,11 +133,36 @@ __device__ __forceinline__ void gelu_erf_fast2(float x0, float x1, float& y0, fl
   y1 = x1 * ((x1 >= 0.f) ? (1.0f - h1) : h1);
 }
 
+// "Residual from the pre-LayerNorm sums" (GemmArgs::resid_y): per tile, the source rows and LayerNorm statistics of the
+// eight rows this lane adds residuals to (rows (lane >> 3) + 4 i of the warp's 32-row slab, the coalesced store
+// layout).  Loaded BEFORE the wait for the accumulator, so neither the row-map -> sums dependency nor the statistics
+// sit in the per-chunk critical path (loaded per chunk, the two dependent round trips made the residual GEMMs 40 %
+// slower than with (hi, lo) pairs).
+struct GemmResidRows {
+  int src[8];
+  float2 ms[8];      // (mean, rstd)
+};
+template <int EPI, bool SPLIT>
+__device__ __forceinline__ void gemm_resid_rows(const GemmArgs& args, int M, int m0, int quarter, int lane, GemmResidRows& rr) {
+  if constexpr (EPI == EPI_RESID_F32 && !SPLIT) {
+    if (args.resid_y) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        // rows past M read row 0 (valid memory, result unused): every load below is unconditional, so the compiler
+        // issues the eight of a chunk back to back (as branches they were serialised: one exposed latency each)
+        const int grow = min(m0 + quarter * 32 + (lane >> 3) + 4 * i, M - 1);
+        rr.src[i] = args.resid_src ? __ldg(args.resid_src + grow) : grow;
+        rr.ms[i] = __ldg(args.resid_stats + grow);
+      }
+    }
+  }
+}
+
 // Epilogue of one 128-row x BLOCK_N accumulator for one epilogue warp (TMEM lane quarter `quarter`, column half
 // `half` of PARTS column parts): TMEM -> registers -> (+bias, activation) -> per-warp swizzled smem transpose -> coalesced global stores.
 template <int BLOCK_N, int EPI, int PARTS = 2, bool SPLIT = false>
 __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, int m0, int n0, uint32_t tmem_acc,
-                                                   uint8_t* stg, int quarter, int half, int lane) {
+                                                   uint8_t* stg, int quarter, int half, int lane, const GemmResidRows& rr) {
       const int row_base = m0 + quarter * 32;     // first row of this warp's 32-row slab
       const int row = row_base + lane;
       const bool row_ok = row < M;
@@ -152,6 +185,13 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
       for (int c = half * (BLOCK_N / PARTS); c < (half + 1) * (BLOCK_N / PARTS); c += 32) {
         const int n = n0 + c;
         uint2 rs[8], rl[8];
+        float4 ln_g = make_float4(0.f, 0.f, 0.f, 0.f), ln_b = ln_g;   // resid_y: LayerNorm weight / bias of this lane's 4 columns
+        if constexpr (EPI == EPI_RESID_F32 && !SPLIT) {
+          if (args.resid_y) {
+            ln_g = __ldg(reinterpret_cast<const float4*>(args.resid_w + n + (lane & 7) * 4));
+            ln_b = __ldg(reinterpret_cast<const float4*>(args.resid_b + n + (lane & 7) * 4));
+          }
+        }
         if constexpr (EPI == EPI_RESID_F32) {       // residual loads first: independent of the accumulator
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -159,6 +199,10 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
             const size_t off = static_cast<size_t>(grow) * args.N + n + (lane & 7) * 4;
             if (SPLIT && args.resid_f32) {          // (rs, rl) hold the four fp32 residuals of this lane's 16 B
               const float4 r4 = (grow < M) ? __ldg(reinterpret_cast<const float4*>(args.resid_f32 + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              rs[i] = make_uint2(__float_as_uint(r4.x), __float_as_uint(r4.y));
+              rl[i] = make_uint2(__float_as_uint(r4.z), __float_as_uint(r4.w));
+            } else if (!SPLIT && args.resid_y) {    // the four fp32 pre-LayerNorm sums behind this lane's 16 B
+              const float4 r4 = __ldg(reinterpret_cast<const float4*>(args.resid_y + static_cast<size_t>(rr.src[i]) * args.N + n + (lane & 7) * 4));
               rs[i] = make_uint2(__float_as_uint(r4.x), __float_as_uint(r4.y));
               rl[i] = make_uint2(__float_as_uint(r4.z), __float_as_uint(r4.w));
             } else {
@@ -259,6 +303,13 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, int M, 
                 if (SPLIT && args.resid_f32) {
                   val.x += __uint_as_float(rs[i].x); val.y += __uint_as_float(rs[i].y);
                   val.z += __uint_as_float(rl[i].x); val.w += __uint_as_float(rl[i].y);
+                } else if (!SPLIT && args.resid_y) {
+                  // the LayerNorm kernel's own expression (ln_rows_vec_kernel), on the sums it read
+                  const float2 ms = rr.ms[i];       // q == lane & 7: ln_g / ln_b are this lane's columns
+                  val.x += (__uint_as_float(rs[i].x) - ms.x) * ms.y * ln_g.x + ln_b.x;
+                  val.y += (__uint_as_float(rs[i].y) - ms.x) * ms.y * ln_g.y + ln_b.y;
+                  val.z += (__uint_as_float(rl[i].x) - ms.x) * ms.y * ln_g.z + ln_b.z;
+                  val.w += (__uint_as_float(rl[i].y) - ms.x) * ms.y * ln_g.w + ln_b.w;
                 } else {
                   const float2 r0 = unpack_bf16x2(rs[i].x), r1 = unpack_bf16x2(rs[i].y);
                   const float2 l0 = unpack_bf16x2(rl[i].x), l1 = unpack_bf16x2(rl[i].y);
@@ -392,7 +443,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // pull the NEXT tile's residual slab (32 rows x BLOCK_N/2 bf16 of this warp) into L2 while this tile's
         // MMAs are still running: the residual was written a layer ago and has long left the cache
         const int nt = tile + gridDim.x;
-        if (nt < total_tiles) {
+        if (nt < total_tiles && args.resid) {
           const int pr = (nt / n_blocks) * GEMM_BLOCK_M + quarter * 32 + lane;
           if (pr < M) {
             const __nv_bfloat16* pp = args.resid + static_cast<size_t>(pr) * args.N + (nt % n_blocks) * BLOCK_N +
@@ -403,9 +454,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
       }
+      GemmResidRows rr;
+      gemm_resid_rows<EPI, SPLIT>(args, M, m0, quarter, lane, rr);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      gemm_epilogue_warp<BLOCK_N, EPI, 2, SPLIT>(args, M, m0, n0, tmem_base + acc * BLOCK_N, stg, quarter, half, lane);
+      gemm_epilogue_warp<BLOCK_N, EPI, 2, SPLIT>(args, M, m0, n0, tmem_base + acc * BLOCK_N, stg, quarter, half, lane, rr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -557,9 +610,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int tile = pair; tile < total_tiles; tile += n_pairs) {
       const int m0 = (tile / n_blocks) * 2 * GEMM_BLOCK_M + static_cast<int>(rank) * GEMM_BLOCK_M;
       const int n0 = (tile % n_blocks) * BLOCK_N;
+      GemmResidRows rr;
+      gemm_resid_rows<EPI, SPLIT>(args, M, m0, quarter, lane, rr);
       mbar_wait(tmem_full + acc * 8, acc_phase);
       tc_fence_after();
-      gemm_epilogue_warp<BLOCK_N, EPI, PARTS, SPLIT>(args, M, m0, n0, tmem_base + acc * BLOCK_N, stg, quarter, half, lane);
+      gemm_epilogue_warp<BLOCK_N, EPI, PARTS, SPLIT>(args, M, m0, n0, tmem_base + acc * BLOCK_N, stg, quarter, half, lane, rr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tmem_empty + acc * 8, 0);

@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(256) ln_rows_vec_kernel(const float* __restric
                                                           const int* __restrict__ slot_src,
                                                           const int* __restrict__ row0_dst,
                                                           const int* __restrict__ row0_src,
-                                                          const int* __restrict__ n_dst_dev) {
+                                                          const int* __restrict__ n_dst_dev,
+                                                          float2* __restrict__ stats_out, int* __restrict__ src_out) {
   const int lane = threadIdx.x & 31;
   const int M = *m_dst_dev;
   const int n_dst = slot_src ? *n_dst_dev : 0;
@@ -202,6 +203,12 @@ __global__ void __launch_bounds__(256) ln_rows_vec_kernel(const float* __restric
       q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
     }
     const float rstd = rsqrtf(warp_sum(q) / H + eps);
+    // "residual from the pre-LayerNorm sums" (gemm.cuh, GemmArgs::resid_y): the next residual add recomputes this row
+    // in fp32 from Y[src_row] with these statistics instead of reading a low part
+    if (stats_out && lane == 0) {
+      stats_out[row] = make_float2(mean, rstd);
+      if (src_out) src_out[row] = static_cast<int>(src_row);
+    }
     __nv_bfloat16* out = X + static_cast<size_t>(row) * H;
     __nv_bfloat16* out_lo = Xlo ? Xlo + static_cast<size_t>(row) * H : nullptr;
 #pragma unroll
