@@ -56,6 +56,7 @@ struct GemmArgs {
   const int* resid_src;            // [rows] row of resid_y behind output row r (an exit compaction in between), nullptr: r
   const float* resid_w;            // [N] LayerNorm weight / bias of that LayerNorm
   const float* resid_b;
+  int resid_prefetch;              // pair kernel: pull the next tile's rows of resid_y into L2 while this tile's MMAs run
   // EPI_QKV
   __nv_bfloat16* vt;       // [docs][heads][64][kv_pitch]
   __nv_bfloat16* vt_lo;    // SPLIT: low parts of V^T
@@ -610,6 +611,21 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int tile = pair; tile < total_tiles; tile += n_pairs) {
       const int m0 = (tile / n_blocks) * 2 * GEMM_BLOCK_M + static_cast<int>(rank) * GEMM_BLOCK_M;
       const int n0 = (tile % n_blocks) * BLOCK_N;
+      if constexpr (EPI == EPI_RESID_F32 && !SPLIT) {
+        // the residual sums of the NEXT tile of this pair (this lane's row, this warp's column part: BLOCK_N / PARTS
+        // fp32) -> L2: they were written a GEMM or a layer ago and have long left the cache
+        const int nt = tile + n_pairs;
+        if (args.resid_y && args.resid_prefetch && nt < total_tiles) {
+          const int pr = (nt / n_blocks) * 2 * GEMM_BLOCK_M + static_cast<int>(rank) * GEMM_BLOCK_M + quarter * 32 + lane;
+          if (pr < M) {
+            const size_t srow = args.resid_src ? static_cast<size_t>(__ldg(args.resid_src + pr)) : static_cast<size_t>(pr);
+            const char* pp = reinterpret_cast<const char*>(args.resid_y + srow * args.N + (nt % n_blocks) * BLOCK_N +
+                                                           half * (BLOCK_N / PARTS));
+#pragma unroll
+            for (int b = 0; b < (BLOCK_N / PARTS) * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + b));
+          }
+        }
+      }
       GemmResidRows rr;
       gemm_resid_rows<EPI, SPLIT>(args, M, m0, quarter, lane, rr);
       mbar_wait(tmem_full + acc * 8, acc_phase);
